@@ -1,0 +1,942 @@
+// CUDA-core kernels: the fp32 path (any shape), and the bandwidth-bound pieces shared with the
+// tensor-core path (first layer with in-kernel coordinates, last layer + MSE loss, layer-0 gradient,
+// partial reductions, multi-tensor Adam, masks, k-means and int8 fake quantisation).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "tc_kernels.cuh"
+
+namespace sb {
+
+constexpr int kMaxLayers = 16;
+constexpr int kMaxTensors = 2 * kMaxLayers;
+constexpr int kMaxOut = 4;
+
+// Where the input coordinates of pixel p (local index inside this handle's rows) come from.
+struct CoordSrc {
+  const float* lin_h;   // [H] or null
+  const float* lin_w;   // [W] or null
+  const float* coords;  // [npix, 2] or null
+  int width;            // image width
+  int row_begin;        // first image row of this handle
+};
+
+// siren.py:125-128: x = (grid - 0.5) * 2, features ordered (h, w) (data.py:82-86, 'ij' meshgrid)
+__device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh, float& xw) {
+  float gh, gw;
+  if (c.coords) {
+    const float2 v = reinterpret_cast<const float2*>(c.coords)[p];
+    gh = v.x;
+    gw = v.y;
+  } else {
+    const int r = int(p / c.width), col = int(p - int64_t(r) * c.width);
+    gh = __ldg(c.lin_h + c.row_begin + r);
+    gw = __ldg(c.lin_w + col);
+  }
+  xh = (gh - 0.5f) * 2.0f;
+  xw = (gw - 0.5f) * 2.0f;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic fp32 tiled GEMM (64x64x16 tiles, 4x4 per thread) with fused epilogues
+// ------------------------------------------------------------------------------------------
+enum SimtOp {
+  OP_NT_SINE = 0,  // C = A[M,K] * B[N,K]^T + bias ; Z <- C, Out <- sin(omega*C)     (forward)
+  OP_NT_LIN = 1,   // C = A * B^T + bias ; Out <- C                                   (last layer)
+  OP_NN_DCOS = 2,  // C = A[M,K] * B[K,N] ; Out <- C * omega*cos(omega*Z)              (dX + dsine)
+  OP_TN_PART = 3   // C = A[K,M]^T * B[K,N] over k in this split ; Out[split] <- C     (dW partial)
+};
+
+struct SimtGemmArgs {
+  const float* A;
+  const float* B;
+  const float* bias;
+  float* Z;    // pre-activation (written by NT_SINE, read by NN_DCOS)
+  float* Out;
+  float* ColSum;  // TN_PART: per-split column sums of A (bias gradient) or null
+  int M, N, K;
+  int lda, ldb, ldo;
+  float omega;
+  int ksplit_len;  // TN_PART: rows of K per split (gridDim.z splits)
+};
+
+template <int OP>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmArgs a) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  int k_begin = 0, k_end = a.K;
+  if (OP == OP_TN_PART) {
+    k_begin = blockIdx.z * a.ksplit_len;
+    k_end = min(a.K, k_begin + a.ksplit_len);
+  }
+  float acc[4][4] = {};
+  float csum[4] = {};
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
+    // load A tile -> As[k][m], B tile -> Bs[k][n]
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      int kk, mm;
+      float v = 0.f;
+      if (OP == OP_TN_PART) {  // A is [K, M] row-major
+        kk = i >> 6;
+        mm = i & 63;
+        if (k0 + kk < k_end && m0 + mm < a.M) v = a.A[int64_t(k0 + kk) * a.lda + m0 + mm];
+      } else {  // A is [M, K] row-major
+        mm = i >> 4;
+        kk = i & 15;
+        if (k0 + kk < k_end && m0 + mm < a.M) v = a.A[int64_t(m0 + mm) * a.lda + k0 + kk];
+      }
+      As[kk][mm] = v;
+    }
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      int kk, nn;
+      float v = 0.f;
+      if (OP == OP_NT_SINE || OP == OP_NT_LIN) {  // B is [N, K]
+        nn = i >> 4;
+        kk = i & 15;
+        if (k0 + kk < k_end && n0 + nn < a.N) v = a.B[int64_t(n0 + nn) * a.ldb + k0 + kk];
+      } else {  // B is [K, N]
+        kk = i >> 6;
+        nn = i & 63;
+        if (k0 + kk < k_end && n0 + nn < a.N) v = a.B[int64_t(k0 + kk) * a.ldb + n0 + nn];
+      }
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      if (OP == OP_TN_PART) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) csum[i] += av[i];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.N) continue;
+      float c = acc[i][j];
+      if (OP == OP_NT_SINE) {
+        c += a.bias[n];
+        a.Z[int64_t(m) * a.ldo + n] = c;
+        a.Out[int64_t(m) * a.ldo + n] = sinf(c * a.omega);
+      } else if (OP == OP_NT_LIN) {
+        a.Out[int64_t(m) * a.ldo + n] = c + a.bias[n];
+      } else if (OP == OP_NN_DCOS) {
+        const float z = a.Z[int64_t(m) * a.ldo + n];
+        a.Out[int64_t(m) * a.ldo + n] = c * (a.omega * cosf(z * a.omega));
+      } else {
+        a.Out[(int64_t(blockIdx.z) * a.M + m) * a.ldo + n] = c;
+      }
+    }
+    if (OP == OP_TN_PART && a.ColSum && blockIdx.x == 0 && tx == 0)
+      a.ColSum[int64_t(blockIdx.z) * a.M + m] = csum[i];
+  }
+}
+
+// materialise x = (grid - 0.5) * 2 as [npix, 2] fp32 (fp32 path only)
+__global__ void simt_coords_kernel(CoordSrc c, float* x, int64_t npix) {
+  const int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (p >= npix) return;
+  float xh, xw;
+  load_xy(c, p, xh, xw);
+  reinterpret_cast<float2*>(x)[p] = make_float2(xh, xw);
+}
+
+// fp32 path: pred / loss / dL/dy from the last layer's output y [npix, C].
+//   mode 0: forward only (pred).  mode 1: MSE loss, g = (pred-img) (seed, unscaled).
+//   mode 2: g = 0.5 * dpred.
+// With outermost_linear == 0 the last layer is a sine layer: y holds z, pred = sin(w z)/2+.5.
+struct LossArgs {
+  const float* y;
+  const float* img;    // mode 1: target; mode 2: dpred
+  float* pred;         // may be null
+  float* g;            // dL/dz of the last layer (seed units), may be null in mode 0
+  float* loss_partial; // [gridDim.x]
+  int64_t n;           // npix * C
+  int mode;
+  int outermost_linear;
+  float omega;
+};
+__global__ void __launch_bounds__(256) simt_loss_kernel(const LossArgs a) {
+  float lsum = 0.f;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < a.n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float z = a.y[i];
+    const float o = a.outermost_linear ? z : sinf(z * a.omega);
+    const float pred = o / 2 + 0.5f;
+    if (a.pred) a.pred[i] = pred;
+    if (a.mode != 0) {
+      float g;
+      if (a.mode == 1) {
+        const float d = pred - a.img[i];
+        lsum += d * d;
+        g = d;
+      } else {
+        g = 0.5f * a.img[i];
+      }
+      if (!a.outermost_linear) g *= a.omega * cosf(z * a.omega);
+      a.g[i] = g;
+    }
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = lsum;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && a.loss_partial) a.loss_partial[blockIdx.x] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// tensor-core path, layer 0: a0 = sin(w0 * (W0 x + b0)) with in-kernel coordinates -> signed-half
+// (siren.py:62,66 for the is_first layer; K = 2 is not a tensor-core shape)
+// ------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) tc_first_layer_kernel(CoordSrc c, const float* __restrict__ w0,
+                                                             const float* __restrict__ b0,
+                                                             float omega, __half* __restrict__ act0,
+                                                             int64_t npix, int64_t npix_pad) {
+  // each thread: 8 consecutive columns of one pixel
+  constexpr int TPR = W / 8;         // threads per row
+  constexpr int RPB = 256 / TPR;     // rows per block iteration
+  const int tc = threadIdx.x % TPR, tr = threadIdx.x / TPR;
+  float wa[8], wb[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    wa[j] = w0[(tc * 8 + j) * 2 + 0] * omega;
+    wb[j] = w0[(tc * 8 + j) * 2 + 1] * omega;
+    bb[j] = b0[tc * 8 + j] * omega;
+  }
+  for (int64_t p = int64_t(blockIdx.x) * RPB + tr; p < npix_pad; p += int64_t(gridDim.x) * RPB) {
+    uint32_t o[4] = {0, 0, 0, 0};
+    if (p < npix) {
+      float xh, xw;
+      load_xy(c, p, xh, xw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t0 = fmaf(xh, wa[2 * j], fmaf(xw, wb[2 * j], bb[2 * j]));
+        const float t1 = fmaf(xh, wa[2 * j + 1], fmaf(xw, wb[2 * j + 1], bb[2 * j + 1]));
+        o[j] = sine_signed_half2(t0, t1);
+      }
+    }
+    reinterpret_cast<uint4*>(act0 + p * W)[tc] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tensor-core path, last layer (W -> C <= 4, CUDA cores) fused with y/2+0.5, the MSE loss, the
+// gradient seed, dA = g W_last, dZ of the last hidden layer (cos rebuilt from the signed-half)
+// and the last layer's weight / bias gradients.  One warp per pixel row.
+//   (siren.py:64,110-118,131; train_helper.py:151-154 F.mse_loss and its backward)
+// ------------------------------------------------------------------------------------------
+struct LastArgs {
+  const __half* act;     // [npix_pad, W] signed-half, last hidden activation
+  __half* dz;            // [npix_pad, W] out (mode != 0)
+  const float* w;        // [C, W]
+  const float* b;        // [C]
+  const float* img;      // mode 1: target [npix, C]; mode 2: dpred [npix, C]
+  float* pred;           // [npix, C] or null
+  float* part;           // per-block partials: [grid][C*W + C + 1] (dW, db, sum sq err)
+  const float* gscale;   // device scalar: seed scale G
+  int64_t npix, npix_pad;
+  int C;
+  int mode;              // 0 forward only, 1 MSE, 2 external dpred
+  int outermost_linear;
+  float omega_last;      // omega of the last layer (only when it is a sine layer)
+  float omega_prev;      // omega of the layer that produced `act`
+};
+
+template <int W>
+__global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
+  constexpr int NCH = (W + 255) / 256;            // 8-column chunks per lane
+  constexpr int ACTIVE = (W / 8) < 32 ? (W / 8) : 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool on = lane < ACTIVE;
+  float wr[kMaxOut][NCH * 8];
+  float dwacc[kMaxOut][NCH * 8];
+  float dbacc[kMaxOut] = {};
+  float lsum = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < kMaxOut; ++cc)
+#pragma unroll
+    for (int j = 0; j < NCH * 8; ++j) {
+      const int col = (j / 8) * 256 + lane * 8 + (j % 8);
+      wr[cc][j] = (on && cc < a.C) ? a.w[cc * W + col] : 0.f;
+      dwacc[cc][j] = 0.f;
+    }
+  const float G = (a.mode != 0) ? *a.gscale : 1.f;
+  const int64_t nwarps = int64_t(gridDim.x) * 8;
+  for (int64_t p = int64_t(blockIdx.x) * 8 + warp; p < a.npix_pad; p += nwarps) {
+    if (p >= a.npix) {  // padding rows: zero gradient so the dW reduction ignores them
+      if (a.mode != 0 && on)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+          reinterpret_cast<uint4*>(a.dz + p * W)[ch * 32 + lane] = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    uint32_t raw[NCH * 4];
+    float av[NCH * 8];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (on) v = reinterpret_cast<const uint4*>(a.act + p * W)[ch * 32 + lane];
+      raw[ch * 4 + 0] = v.x;
+      raw[ch * 4 + 1] = v.y;
+      raw[ch * 4 + 2] = v.z;
+      raw[ch * 4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < NCH * 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw[j]));
+      av[2 * j] = f.x;
+      av[2 * j + 1] = f.y;
+    }
+    float y[kMaxOut];
+#pragma unroll
+    for (int cc = 0; cc < kMaxOut; ++cc) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NCH * 8; ++j) s = fmaf(av[j], wr[cc][j], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      y[cc] = s;
+    }
+    float g[kMaxOut];
+#pragma unroll
+    for (int cc = 0; cc < kMaxOut; ++cc) {
+      g[cc] = 0.f;
+      if (cc < a.C) {
+        const float z = y[cc] + a.b[cc];
+        const float o = a.outermost_linear ? z : sinf(z * a.omega_last);
+        const float pred = o / 2 + 0.5f;
+        if (a.pred && lane == cc) a.pred[p * a.C + cc] = pred;
+        if (a.mode == 1) {
+          const float d = pred - a.img[p * a.C + cc];
+          if (lane == 0) lsum += d * d;
+          g[cc] = d * G;
+        } else if (a.mode == 2) {
+          g[cc] = 0.5f * a.img[p * a.C + cc] * G;
+        }
+        if (!a.outermost_linear) g[cc] *= a.omega_last * cosf(z * a.omega_last);
+      }
+    }
+    if (a.mode != 0) {
+#pragma unroll
+      for (int cc = 0; cc < kMaxOut; ++cc) {
+        if (lane == 0) dbacc[cc] += g[cc];
+#pragma unroll
+        for (int j = 0; j < NCH * 8; ++j) dwacc[cc][j] = fmaf(g[cc], av[j], dwacc[cc][j]);
+      }
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t o4[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < kMaxOut; ++cc) {
+            d0 = fmaf(g[cc], wr[cc][ch * 8 + 2 * j2], d0);
+            d1 = fmaf(g[cc], wr[cc][ch * 8 + 2 * j2 + 1], d1);
+          }
+          const uint32_t r = raw[ch * 4 + j2];
+          d0 *= a.omega_prev * cos_from_signed_half(r & 0xFFFFu);
+          d1 *= a.omega_prev * cos_from_signed_half(r >> 16);
+          o4[j2] = pack_f16x2(d0, d1);
+        }
+        if (on)
+          reinterpret_cast<uint4*>(a.dz + p * W)[ch * 32 + lane] =
+              make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+  if (a.mode == 0) return;
+  // block reduction of the per-warp partial sums (8 warps) through shared memory
+  __shared__ float red[8][kMaxOut + 1];
+  __shared__ float buf[8][32][kMaxOut];
+  float* out = a.part + int64_t(blockIdx.x) * (a.C * W + a.C + 1);
+#pragma unroll
+  for (int j = 0; j < NCH * 8; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < kMaxOut; ++cc) buf[warp][lane][cc] = dwacc[cc][j];
+    __syncthreads();
+    if (warp == 0 && on) {
+#pragma unroll
+      for (int cc = 0; cc < kMaxOut; ++cc) {
+        if (cc < a.C) {
+          float s = 0.f;
+          for (int w8 = 0; w8 < 8; ++w8) s += buf[w8][lane][cc];
+          const int col = (j / 8) * 256 + lane * 8 + (j % 8);
+          out[cc * W + col] = s;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int cc = 0; cc < kMaxOut; ++cc) red[warp][cc] = dbacc[cc];
+    red[warp][kMaxOut] = lsum;
+  }
+  __syncthreads();
+  if (threadIdx.x <= a.C) {
+    const int idx = threadIdx.x < a.C ? threadIdx.x : kMaxOut;
+    float s = 0.f;
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][idx];
+    out[a.C * W + threadIdx.x] = s;  // db[0..C-1], then sum of squared error
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tensor-core path, layer-0 gradients: dW0[j, {h,w}] = sum_p dz0[p, j] * x[p], db0[j] = sum_p dz0
+// ------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) tc_layer0_grad_kernel(CoordSrc c, const __half* __restrict__ dz0,
+                                                             float* __restrict__ part, int64_t npix) {
+  constexpr int TPR = W / 2;      // threads per row (2 columns each)
+  constexpr int RL = 256 / TPR;   // row lanes
+  const int tc = threadIdx.x % TPR, tr = threadIdx.x / TPR;
+  const int64_t per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per_block;
+  const int64_t p1 = min(npix, p0 + per_block);
+  float ah0 = 0, aw0 = 0, ab0 = 0, ah1 = 0, aw1 = 0, ab1 = 0;
+  for (int64_t p = p0 + tr; p < p1; p += RL) {
+    float xh, xw;
+    load_xy(c, p, xh, xw);
+    const float2 g = __half22float2(reinterpret_cast<const __half2*>(dz0 + p * W)[tc]);
+    ah0 = fmaf(g.x, xh, ah0);
+    aw0 = fmaf(g.x, xw, aw0);
+    ab0 += g.x;
+    ah1 = fmaf(g.y, xh, ah1);
+    aw1 = fmaf(g.y, xw, aw1);
+    ab1 += g.y;
+  }
+  __shared__ float red[RL][TPR][6];
+  red[tr][tc][0] = ah0; red[tr][tc][1] = aw0; red[tr][tc][2] = ab0;
+  red[tr][tc][3] = ah1; red[tr][tc][4] = aw1; red[tr][tc][5] = ab1;
+  __syncthreads();
+  if (tr == 0) {
+    float s[6] = {};
+    for (int r = 0; r < RL; ++r)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] += red[r][tc][k];
+    float* out = part + int64_t(blockIdx.x) * (3 * W);
+    const int j0 = 2 * tc;
+    out[j0 * 2 + 0] = s[0];       // dW0[j0, h]
+    out[j0 * 2 + 1] = s[1];       // dW0[j0, w]
+    out[(j0 + 1) * 2 + 0] = s[3];
+    out[(j0 + 1) * 2 + 1] = s[4];
+    out[2 * W + j0] = s[2];       // db0
+    out[2 * W + j0 + 1] = s[5];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight staging for the tensor-core path ("weight load"): fp32 master -> fp16 operands
+//   wh[l]  = fp16(W_l)                [out, in]   forward B operand (K-major)
+//   wth[l] = fp16(omega_{l-1} W_l^T)  [in, out]   dX B operand (omega of the cos factor folded in)
+// ------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const float* w[kMaxLayers];
+  float omega_prev[kMaxLayers];
+  int nlayers;  // hidden layers staged: l = 1 .. nlayers
+  int W;
+  __half* wh;   // [nlayers][W][W]
+  __half* wth;  // [nlayers][W][W]
+  float* stats; // zeroed here (start of a step); may be null
+};
+__global__ void __launch_bounds__(256) tc_prep_weights_kernel(const PrepArgs a) {
+  __shared__ float tile[32][33];
+  if (a.stats && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x < 4)
+    a.stats[threadIdx.x] = 0.f;
+  const int l = blockIdx.z;
+  const float* w = a.w[l];
+  const int W = a.W;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const float v = w[(by + r) * W + bx + tx];
+    tile[r][tx] = v;
+    a.wh[(size_t(l) * W + by + r) * W + bx + tx] = __float2half_rn(v);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    a.wth[(size_t(l) * W + bx + r) * W + by + tx] = __float2half_rn(tile[tx][r] * a.omega_prev[l]);
+}
+
+// ------------------------------------------------------------------------------------------
+// split-K / per-block partial reduction into the gradient tensors (+ non-finite detection)
+// ------------------------------------------------------------------------------------------
+struct ReduceDesc {
+  float* dst;
+  const float* src;
+  int n;             // elements
+  int nsplit;
+  int64_t split_stride;
+};
+struct ReduceArgs {
+  ReduceDesc d[kMaxTensors];
+  int chunk_begin[kMaxTensors + 1];  // prefix sums of ceil(n / 1024)
+  int ndesc;
+  float scale;               // host-known factor
+  const float* gscale;       // device seed scale G (grads are divided by it) or null
+  float* stats;              // stats[2] <- 1 if any non-finite
+};
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
+  int t = 0;
+  while (t + 1 < a.ndesc && int(blockIdx.x) >= a.chunk_begin[t + 1]) ++t;
+  const ReduceDesc d = a.d[t];
+  const float scale = a.gscale ? a.scale / *a.gscale : a.scale;
+  const int base = (blockIdx.x - a.chunk_begin[t]) * 1024;
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = base + k * 256 + threadIdx.x;
+    if (i < d.n) {
+      float s = 0.f;
+      for (int sp = 0; sp < d.nsplit; ++sp) s += d.src[sp * d.split_stride + i];
+      s *= scale;
+      d.dst[i] = s;
+      bad |= !isfinite(s);
+    }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) a.stats[2] = 1.0f;
+}
+
+// loss finalisation + seed-scale policy (one block)
+struct FinalizeArgs {
+  const float* loss_partial;
+  int nparts;
+  int64_t part_stride;  // distance between consecutive partial values
+  float inv_count;      // 1 / (H*W*C)
+  float* stats;         // [0] sum sq err, [1] loss, [2] non-finite flag
+  float* gstate;        // [0] G, [1] G cap  (tensor-core path) or null
+  float* loss_hist;     // optional ring of per-step losses
+  const int* step;      // device step counter (index into loss_hist) or null
+  int hist_len;
+};
+__global__ void __launch_bounds__(256) finalize_loss_kernel(const FinalizeArgs a) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < a.nparts; i += 256) s += a.loss_partial[i * a.part_stride];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float sse = red[0];
+    const float loss = sse * a.inv_count;
+    a.stats[0] = sse;
+    a.stats[1] = loss;
+    if (a.loss_hist && a.step) a.loss_hist[*a.step % a.hist_len] = loss;
+    if (a.gstate) {
+      float cap = a.gstate[1];
+      if (a.stats[2] != 0.f) cap = fmaxf(1.f, a.gstate[0] * (1.f / 16.f));
+      // next seed scale: power of two near 0.125 / rmse, clamped to [1, cap]
+      float g = 1.f;
+      if (loss > 0.f && isfinite(loss)) g = exp2f(floorf(log2f(0.125f * rsqrtf(loss))));
+      g = fminf(fmaxf(g, 1.f), cap);
+      a.gstate[0] = g;
+      a.gstate[1] = cap;
+    }
+  }
+}
+
+// max |x| -> power-of-two seed scale for an external dpred (one block, grid-stride)
+__global__ void __launch_bounds__(1024) absmax_scale_kernel(const float* x, int64_t n, float* gstate) {
+  __shared__ float red[1024];
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(x[i]));
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int k = 512; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + k]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float mx = red[0];
+    float g = 1.f;
+    if (mx > 0.f && isfinite(mx)) g = exp2f(floorf(log2f(4.0f / mx)));
+    gstate[0] = fminf(fmaxf(g, 1.f), 1.0e30f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// eval_epoch metrics (train_helper.py:48-57): mse and mse of the (x*255).int() images
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eval_metrics_kernel(const float* pred, const float* img,
+                                                           int64_t n, double* acc) {
+  double s = 0, s8 = 0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const float p = pred[i], t = img[i];
+    const float d = p - t;
+    s += double(d) * d;
+    const int d8 = int(t * 255.0f) - int(p * 255.0f);  // .int() truncates toward zero
+    s8 += double(d8 * d8);
+  }
+  __shared__ double r0[256], r1[256];
+  r0[threadIdx.x] = s;
+  r1[threadIdx.x] = s8;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) {
+      r0[threadIdx.x] += r0[threadIdx.x + k];
+      r1[threadIdx.x] += r1[threadIdx.x + k];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(&acc[0], r0[0]);
+    atomicAdd(&acc[1], r1[0]);
+  }
+}
+__global__ void eval_metrics_finish_kernel(const double* acc, int64_t n, float* out) {
+  out[0] = float(acc[0] / double(n));
+  out[1] = float(acc[1] / double(n));
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-tensor Adam (+ unscale, skip-on-inf, mask, zero-grad)
+// ------------------------------------------------------------------------------------------
+struct AdamArgs {
+  float* p[kMaxTensors];
+  float* g[kMaxTensors];
+  float* m[kMaxTensors];
+  float* v[kMaxTensors];
+  const float* mask[kMaxTensors];
+  int n[kMaxTensors];
+  int chunk_begin[kMaxTensors + 1];
+  int ntensors;
+  float beta1, beta2, eps;
+  float omb1, omb2;     // float(1 - beta) evaluated in double on the host, as torch does
+  float step_size;     // lr / (1 - beta1^t)
+  float bc2_sqrt;      // sqrt(1 - beta2^t)
+  float inv_scale;
+  const float* skip_flag;
+  int zero_grad;
+  // device-driven schedule (graph replay): when non-null, step_size / bc2_sqrt are read from here
+  const float* dev_sched;  // [0] step_size, [1] bc2_sqrt
+};
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamArgs a) {
+  int t = 0;
+  while (t + 1 < a.ntensors && int(blockIdx.x) >= a.chunk_begin[t + 1]) ++t;
+  const int base = (blockIdx.x - a.chunk_begin[t]) * 1024;
+  const bool skip = a.skip_flag && (*a.skip_flag != 0.f);
+  const float step_size = a.dev_sched ? a.dev_sched[0] : a.step_size;
+  const float bc2_sqrt = a.dev_sched ? a.dev_sched[1] : a.bc2_sqrt;
+  float* P = a.p[t];
+  float* G = a.g[t];
+  float* M = a.m[t];
+  float* V = a.v[t];
+  const float* K = a.mask[t];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = base + k * 256 + threadIdx.x;
+    if (i >= a.n[t]) continue;
+    float p = P[i];
+    if (!skip) {
+      const float g = G[i] * a.inv_scale;
+      float m = M[i], v = V[i];
+      m = m + (g - m) * a.omb1;                                 // exp_avg.lerp_(grad, 1-beta1)
+      v = v * a.beta2 + (a.omb2 * g) * g;                     // mul_(beta2).addcmul_(g, g, 1-beta2)
+      const float denom = sqrtf(v) / bc2_sqrt + a.eps;
+      p = p + (-step_size * m) / denom;                      // addcdiv_(m, denom, -step_size)
+      M[i] = m;
+      V[i] = v;
+    }
+    if (K) p = p * K[i];                                     // Masking.apply_mask
+    P[i] = p;
+    if (a.zero_grad) G[i] = 0.f;
+  }
+}
+
+__global__ void apply_mask_kernel(float* w, const float* mask, int64_t n) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i < n) w[i] = w[i] * mask[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// int8 per-channel symmetric fake quantisation (QAT weights)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fakequant_rows_kernel(const float* w, int rows, int cols,
+                                                             const float* row_min,
+                                                             const float* row_max, float neg_div,
+                                                             float pos_div, int8_t* codes,
+                                                             float* scales, float* w_out) {
+  const int r = blockIdx.x;
+  __shared__ float rlo[256], rhi[256];
+  float lo, hi;
+  if (row_min && row_max) {
+    lo = row_min[r];
+    hi = row_max[r];
+  } else {
+    lo = INFINITY;
+    hi = -INFINITY;
+    for (int c = threadIdx.x; c < cols; c += 256) {
+      const float x = w[int64_t(r) * cols + c];
+      lo = fminf(lo, x);
+      hi = fmaxf(hi, x);
+    }
+    rlo[threadIdx.x] = lo;
+    rhi[threadIdx.x] = hi;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+      if (threadIdx.x < k) {
+        rlo[threadIdx.x] = fminf(rlo[threadIdx.x], rlo[threadIdx.x + k]);
+        rhi[threadIdx.x] = fmaxf(rhi[threadIdx.x], rhi[threadIdx.x + k]);
+      }
+      __syncthreads();
+    }
+    lo = rlo[0];
+    hi = rhi[0];
+  }
+  // symmetric qparams: scale = max(-min(lo,0)/neg_div, max(hi,0)/pos_div), clamped to eps
+  const float s_neg = -fminf(lo, 0.f) / neg_div, s_pos = fmaxf(hi, 0.f) / pos_div;
+  const float scale = fmaxf(fmaxf(s_neg, s_pos), 1.1920928955078125e-07f);
+  if (threadIdx.x == 0 && scales) scales[r] = scale;
+  // torch's fake-quant kernel multiplies by the reciprocal scale: nearbyint(x * (1/scale))
+  const float inv_scale = 1.0f / scale;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float x = w[int64_t(r) * cols + c];
+    float q = nearbyintf(x * inv_scale);  // round half to even
+    q = fminf(fmaxf(q, -128.f), 127.f);
+    if (codes) codes[int64_t(r) * cols + c] = int8_t(q);
+    if (w_out) w_out[int64_t(r) * cols + c] = q * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 1-D k-means (Deep-Compression weight sharing, quant/kmeans.py + kmeans_helper.py)
+// ------------------------------------------------------------------------------------------
+// first-min argmin of (x - c_k)^2 over k (torch.argmin returns the first minimum)
+__device__ __forceinline__ int kmeans_nearest(float x, const float* cent, int k) {
+  float best = INFINITY;
+  int bi = 0;
+  for (int j = 0; j < k; ++j) {
+    const float d = x - cent[j];
+    const float dd = d * d;  // (a - b) ** 2.0
+    if (dd < best) {
+      best = dd;
+      bi = j;
+    }
+  }
+  return bi;
+}
+
+// min / max / count of non-zero weights
+__global__ void __launch_bounds__(256) kmeans_minmax_kernel(const float* w, int64_t n, float* mm) {
+  __shared__ float smin[256], smax[256];
+  float lo = INFINITY, hi = -INFINITY;
+  for (int64_t i = blockIdx.x * int64_t(256) + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
+    const float x = w[i];
+    if (x != 0.f) {
+      lo = fminf(lo, x);
+      hi = fmaxf(hi, x);
+    }
+  }
+  smin[threadIdx.x] = lo;
+  smax[threadIdx.x] = hi;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) {
+      smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + k]);
+      smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + k]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // float atomics via int punning (values may be negative): use CAS loops
+    int* imin = reinterpret_cast<int*>(&mm[0]);
+    int* imax = reinterpret_cast<int*>(&mm[1]);
+    int old = *imin, assumed;
+    do {
+      assumed = old;
+      if (__int_as_float(assumed) <= smin[0]) break;
+      old = atomicCAS(imin, assumed, __float_as_int(smin[0]));
+    } while (old != assumed);
+    old = *imax;
+    do {
+      assumed = old;
+      if (__int_as_float(assumed) >= smax[0]) break;
+      old = atomicCAS(imax, assumed, __float_as_int(smax[0]));
+    } while (old != assumed);
+  }
+}
+
+// Lloyd assignment step for the non-zero weights: label32[i] = nearest centre, -1 for zeros.
+__global__ void __launch_bounds__(256) kmeans_label_kernel(const float* w, int64_t n,
+                                                           const float* cent, const int* k_cur,
+                                                           int* label32) {
+  extern __shared__ float sc[];
+  const int k = *k_cur;
+  for (int j = threadIdx.x; j < k; j += 256) sc[j] = cent[j];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * int64_t(256) + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
+    const float x = w[i];
+    label32[i] = (x == 0.f) ? -1 : kmeans_nearest(x, sc, k);
+  }
+}
+
+// Per-cluster sum and count, one warp per cluster, accumulating in INDEX ORDER in fp32 so the result
+// is bit-identical to the reference's sequential index_add_ (scatter_mean restatement) on the CPU.
+__global__ void __launch_bounds__(256) kmeans_cluster_sum_kernel(const float* w, int64_t n,
+                                                                 const int* label32,
+                                                                 const int* k_cur, float* sums,
+                                                                 unsigned int* cnts) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= *k_cur) return;
+  float sum = 0.f;
+  unsigned int cnt = 0;
+  for (int64_t base = 0; base < n; base += 32) {
+    const int64_t i = base + lane;
+    const bool hit = (i < n) && (label32[i] == c);
+    const float x = hit ? w[i] : 0.f;
+    unsigned int bal = __ballot_sync(0xffffffffu, hit);
+    cnt += __popc(bal);
+    while (bal) {
+      const int b = __ffs(bal) - 1;
+      bal &= bal - 1;
+      sum += __shfl_sync(0xffffffffu, x, b);
+    }
+  }
+  if (lane == 0) {
+    sums[c] = sum;
+    cnts[c] = cnt;
+  }
+}
+
+// one block: new centres (scatter_mean semantics), centre shift, convergence flag
+struct KmeansUpdateArgs {
+  float* cent;        // [k] in/out
+  float* sums;
+  unsigned int* cnts;
+  int* k_cur;         // current number of centres
+  float* shift;       // out: (sum_i |c_i - c'_i|)
+  int* status;        // out: 1 = shape mismatch (reference would raise)
+};
+__global__ void __launch_bounds__(1024) kmeans_update_kernel(const KmeansUpdateArgs a) {
+  __shared__ float red[1024];
+  __shared__ int smax;
+  const int k = *a.k_cur;
+  if (threadIdx.x == 0) smax = -1;
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += 1024)
+    if (a.cnts[j] > 0) atomicMax(&smax, j);
+  __syncthreads();
+  const int nout = smax + 1;  // scatter_mean output length = labels.max() + 1
+  float sh = 0.f;
+  if (nout == k) {
+    for (int j = threadIdx.x; j < k; j += 1024) {
+      const unsigned int c = a.cnts[j];
+      const float nc = a.sums[j] / float(c > 0 ? c : 1u);
+      const float d = a.cent[j] - nc;
+      sh += sqrtf(d * d);
+      a.cent[j] = nc;
+    }
+  }
+  red[threadIdx.x] = sh;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *a.shift = red[0];
+    *a.status = (nout == k) ? 0 : 1;
+  }
+}
+
+// one block: prepend 0, unique, sort by |c| (stable w.r.t. the ascending unique order)
+__global__ void __launch_bounds__(1024) kmeans_codebook_kernel(const float* cent, const int* k_cur,
+                                                               float* codebook, int* n_codes) {
+  __shared__ float v[1024];
+  __shared__ float u[1024];
+  __shared__ int nu;
+  const int k = *k_cur + 1;  // with the prepended zero
+  for (int j = threadIdx.x; j < 1024; j += 1024) v[j] = (j == 0) ? 0.f : (j < k ? cent[j - 1] : INFINITY);
+  __syncthreads();
+  // rank sort ascending (k <= 1024): position = #smaller + #equal-before
+  float mine = v[threadIdx.x];
+  int pos = 0;
+  if (threadIdx.x < k) {
+    for (int j = 0; j < k; ++j) {
+      const float o = v[j];
+      pos += (o < mine) || (o == mine && j < int(threadIdx.x));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < k) u[pos] = mine;
+  __syncthreads();
+  // unique (sorted): keep first of each run; 0.0 == -0.0 collapses like torch.unique
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int j = 0; j < k; ++j)
+      if (j == 0 || u[j] != u[j - 1]) v[m++] = u[j];
+    nu = m;
+  }
+  __syncthreads();
+  const int m = nu;
+  // stable sort by |c|
+  if (threadIdx.x < m) {
+    mine = v[threadIdx.x];
+    const float am = fabsf(mine);
+    pos = 0;
+    for (int j = 0; j < m; ++j) {
+      const float ao = fabsf(v[j]);
+      pos += (ao < am) || (ao == am && j < int(threadIdx.x));
+    }
+    codebook[pos] = mine;
+  }
+  if (threadIdx.x == 0) *n_codes = m;
+}
+
+// assign ALL weights (zeros included) to the codebook and rebuild the weights
+__global__ void __launch_bounds__(256) kmeans_predict_kernel(const float* w, int64_t n,
+                                                             const float* codebook,
+                                                             const int* n_codes, int64_t* labels,
+                                                             float* w_out) {
+  extern __shared__ float sc[];
+  const int k = *n_codes;
+  for (int j = threadIdx.x; j < k; j += 256) sc[j] = codebook[j];
+  __syncthreads();
+  for (int64_t i = blockIdx.x * int64_t(256) + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
+    const int b = kmeans_nearest(w[i], sc, k);
+    if (labels) labels[i] = b;
+    if (w_out) w_out[i] = sc[b];
+  }
+}
+
+__global__ void kmeans_linspace_kernel(const float* mm, int k, float* cent) {
+  // torch.linspace(lo, hi, k): symmetric evaluation, step = (hi - lo) / (k - 1)
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k) return;
+  const float lo = mm[0], hi = mm[1];
+  const float step = (hi - lo) / float(k - 1);
+  cent[j] = (j < k / 2) ? lo + step * float(j) : hi - step * float(k - 1 - j);
+}
+
+}  // namespace sb

@@ -1,0 +1,844 @@
+// libsirenb200.so — C ABI (include/siren_b200.h) over the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/siren_b200.h"
+#include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
+#include "tmap.h"
+
+using namespace sb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(SIRENB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                     \
+  do {                                                                                     \
+    ++g_launches;                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(SIRENB200_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                  \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                            \
+  } while (0)
+
+inline int cdiv(int64_t a, int64_t b) { return int((a + b - 1) / b); }
+
+}  // namespace
+
+struct sirenb200_plan {
+  sirenb200_config_t cfg;
+  int device = 0;
+  int nsm = 0;
+  int D = 0, W = 0, C = 0;
+  int rows = 0;
+  int64_t npix = 0, npix_pad = 0;
+  int ntiles = 0;
+  float inv_count = 0.f;  // 1 / (H*W*C)
+  CoordSrc coord{};
+  bool have_fwd = false;
+  int64_t bytes = 0;
+
+  // device scalars / small buffers
+  float* gstate = nullptr;      // [0] seed scale G, [1] cap
+  float* loss_part = nullptr;   // loss partials
+  double* eval_acc = nullptr;
+
+  // ---- fp32 path ----
+  float* x32 = nullptr;        // [npix, 2]
+  float* z32 = nullptr;        // [(D-1)][npix, W] pre-activations
+  float* a32 = nullptr;        // [(D-1)][npix, W] activations
+  float* y32 = nullptr;        // [npix, C]
+  float* g32 = nullptr;        // [npix, C]
+  float* dz32[2] = {nullptr, nullptr};  // [npix, W] ping-pong
+  float* part32 = nullptr;     // split-K partials for the largest tensor (+ bias sums)
+  int simt_splits = 1;
+  int simt_split_len = 0;
+
+  // ---- tensor-core path ----
+  __half* act = nullptr;  // [(D-1)][npix_pad, W] signed-half activations
+  __half* dz = nullptr;   // [(D-1)][npix_pad, W] fp16 gradients (seed units)
+  __half* wh = nullptr;   // [(D-2)][W, W]
+  __half* wth = nullptr;  // [(D-2)][W, W]
+  CUtensorMap tm_act{}, tm_dz{};
+  std::vector<CUtensorMap> tm_w, tm_wt;
+  float* dw_part = nullptr;  // [splits][D-2][W][W]
+  float* db_part = nullptr;  // [splits][D-2][W]
+  int col_splits = 1;
+  float* last_part = nullptr;  // [last_grid][C*W + C + 1]
+  int last_grid = 0;
+  float* l0_part = nullptr;    // [l0_grid][3*W]
+  int l0_grid = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(sirenb200_plan* p, T** ptr, int64_t count) {
+  if (count <= 0) count = 1;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(ptr), size_t(count) * sizeof(T)));
+  p->bytes += count * int64_t(sizeof(T));
+  return 0;
+}
+
+bool tc_supported(int W) { return W == 128 || W == 256; }
+
+float omega_of(const sirenb200_plan* p, int layer) {
+  return layer == 0 ? p->cfg.first_omega : p->cfg.hidden_omega;
+}
+
+int check_ready(const sirenb200_plan* p) {
+  if (!p) return fail(SIRENB200_ERR_INVALID, "null handle");
+  if (!p->coord.coords && !(p->coord.lin_h && p->coord.lin_w))
+    return fail(SIRENB200_ERR_STATE, "no grid bound: call sirenb200_set_grid_lut/coords first");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// rowgemm / colgemm launch helpers
+// ---------------------------------------------------------------------------------------
+template <int W, int MODE>
+int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                   const CUtensorMap& tmE, const CUtensorMap& tmO, const RowGemmArgs& args,
+                   cudaStream_t st) {
+  using Cfg = RowGemmCfg<W, W, MODE>;
+  auto kfn = rowgemm_kernel<W, W, MODE, false>;
+  static bool attr_set[64] = {};
+  if (!attr_set[p->device & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(Cfg::SMEM_BYTES)));
+    attr_set[p->device & 63] = true;
+  }
+  const int grid = args.num_tiles < p->nsm ? args.num_tiles : p->nsm;
+  const uint32_t idesc = umma_idesc(128, W, 0, 0, 0, 0);
+  kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int W>
+int launch_colgemm(sirenb200_plan* p, const ColGemmJobs& jobs, cudaStream_t st) {
+  using Cfg = ColGemmCfg<W>;
+  auto kfn = colgemm_kernel<W>;
+  static bool attr_set[64] = {};
+  if (!attr_set[p->device & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(Cfg::SMEM_BYTES)));
+    attr_set[p->device & 63] = true;
+  }
+  const int grid = jobs.num_problems * jobs.mblocks * jobs.splits;
+  kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(p->tm_dz, p->tm_act, jobs, umma_idesc(128, W, 0, 0, 1, 1),
+                                          umma_idesc(128, 16, 0, 0, 1, 1));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// tensor-core path
+// ---------------------------------------------------------------------------------------
+template <int W>
+int tc_forward(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* stats_to_zero) {
+  const int D = p->D;
+  const int nh = D - 2;  // hidden (W x W) layers
+  if (nh > 0) {
+    PrepArgs pa{};
+    for (int l = 1; l <= nh; ++l) {
+      pa.w[l - 1] = prm[2 * l];
+      pa.omega_prev[l - 1] = omega_of(p, l - 1);
+    }
+    pa.nlayers = nh;
+    pa.W = W;
+    pa.wh = p->wh;
+    pa.wth = p->wth;
+    pa.stats = stats_to_zero;
+    tc_prep_weights_kernel<<<dim3(W / 32, W / 32, nh), 256, 0, st>>>(pa);
+    LAUNCH_CHECK();
+  } else if (stats_to_zero) {
+    CUDA_TRY(cudaMemsetAsync(stats_to_zero, 0, 4 * sizeof(float), st));
+  }
+  {
+    const int grid = p->nsm * 8;
+    tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(p->coord, prm[0], prm[1], omega_of(p, 0), p->act,
+                                                  p->npix, p->npix_pad);
+    LAUNCH_CHECK();
+  }
+  for (int l = 1; l <= nh; ++l) {
+    RowGemmArgs ra{};
+    ra.num_tiles = p->ntiles;
+    ra.a_row0 = int((l - 1) * p->npix_pad);
+    ra.e_row0 = 0;
+    ra.o_row0 = int(l * p->npix_pad);
+    ra.valid_rows = int(p->npix);
+    ra.omega = omega_of(p, l);
+    ra.bias = prm[2 * l + 1];
+    int rc = launch_rowgemm<W, MODE_FWD>(p, p->tm_act, p->tm_w[l - 1], p->tm_act, p->tm_act, ra, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+template <int W>
+int tc_last(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
+            float* pred, cudaStream_t st) {
+  const int D = p->D;
+  LastArgs la{};
+  la.act = p->act + size_t(D - 2) * p->npix_pad * W;
+  la.dz = p->dz + size_t(D - 2) * p->npix_pad * W;
+  la.w = prm[2 * (D - 1)];
+  la.b = prm[2 * (D - 1) + 1];
+  la.img = img_or_dpred;
+  la.pred = pred;
+  la.part = p->last_part;
+  la.gscale = p->gstate;
+  la.npix = p->npix;
+  la.npix_pad = p->npix_pad;
+  la.C = p->C;
+  la.mode = mode;
+  la.outermost_linear = p->cfg.outermost_linear;
+  la.omega_last = omega_of(p, D - 1);
+  la.omega_prev = omega_of(p, D - 2);
+  tc_last_layer_kernel<W><<<p->last_grid, 256, 0, st>>>(la);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int W>
+int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads, float scale,
+                float* stats, cudaStream_t st) {
+  const int D = p->D, C = p->C;
+  const int nh = D - 2;
+  // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
+  for (int l = nh; l >= 1; --l) {
+    RowGemmArgs ra{};
+    ra.num_tiles = p->ntiles;
+    ra.a_row0 = int(l * p->npix_pad);
+    ra.e_row0 = int((l - 1) * p->npix_pad);
+    ra.o_row0 = int((l - 1) * p->npix_pad);
+    ra.valid_rows = int(p->npix);
+    int rc = launch_rowgemm<W, MODE_DX>(p, p->tm_dz, p->tm_wt[l - 1], p->tm_act, p->tm_dz, ra, st);
+    if (rc) return rc;
+  }
+  // hidden-layer weight / bias gradients: one split-K launch over all layers
+  if (nh > 0) {
+    ColGemmJobs jobs{};
+    jobs.num_problems = nh;
+    jobs.mblocks = W / 128;
+    jobs.splits = p->col_splits;
+    jobs.tiles_total = p->ntiles;
+    jobs.tiles_per_split = cdiv(p->ntiles, p->col_splits);
+    for (int l = 1; l <= nh; ++l) {
+      jobs.x_row0[l - 1] = int(l * p->npix_pad);
+      jobs.y_row0[l - 1] = int((l - 1) * p->npix_pad);
+    }
+    jobs.dw_partial = p->dw_part;
+    jobs.db_partial = p->db_part;
+    jobs.nx = W;
+    int rc = launch_colgemm<W>(p, jobs, st);
+    if (rc) return rc;
+  }
+  tc_layer0_grad_kernel<W><<<p->l0_grid, 256, 0, st>>>(p->coord, p->dz, p->l0_part, p->npix);
+  LAUNCH_CHECK();
+
+  // reduce every partial buffer into the caller's gradient tensors
+  ReduceArgs ra{};
+  int nd = 0;
+  auto add = [&](float* dst, const float* src, int n, int nsplit, int64_t stride) {
+    ra.d[nd].dst = dst;
+    ra.d[nd].src = src;
+    ra.d[nd].n = n;
+    ra.d[nd].nsplit = nsplit;
+    ra.d[nd].split_stride = stride;
+    ++nd;
+  };
+  add(grads[0], p->l0_part, 2 * W, p->l0_grid, 3 * W);
+  add(grads[1], p->l0_part + 2 * W, W, p->l0_grid, 3 * W);
+  for (int l = 1; l <= nh; ++l) {
+    add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, W * W, p->col_splits,
+        int64_t(nh) * W * W);
+    add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, W, p->col_splits, int64_t(nh) * W);
+  }
+  const int64_t lstride = int64_t(C) * W + C + 1;
+  add(grads[2 * (D - 1)], p->last_part, C * W, p->last_grid, lstride);
+  add(grads[2 * (D - 1) + 1], p->last_part + C * W, C, p->last_grid, lstride);
+  ra.ndesc = nd;
+  int chunks = 0;
+  for (int i = 0; i < nd; ++i) {
+    ra.chunk_begin[i] = chunks;
+    chunks += cdiv(ra.d[i].n, 1024);
+  }
+  ra.chunk_begin[nd] = chunks;
+  ra.scale = scale;
+  ra.gscale = p->gstate;
+  ra.stats = stats;
+  reduce_partials_kernel<<<chunks, 256, 0, st>>>(ra);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// fp32 path
+// ---------------------------------------------------------------------------------------
+template <int OP>
+int launch_simt(const SimtGemmArgs& a, int splits, cudaStream_t st) {
+  dim3 grid(cdiv(a.N, 64), cdiv(a.M, 64), splits);
+  simt_gemm_kernel<OP><<<grid, 256, 0, st>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
+                float* pred, cudaStream_t st) {
+  const int D = p->D, W = p->W, C = p->C;
+  const int64_t n = p->npix;
+  simt_coords_kernel<<<cdiv(n, 256), 256, 0, st>>>(p->coord, p->x32, n);
+  LAUNCH_CHECK();
+  const float* in = p->x32;
+  int in_dim = p->cfg.in_features;
+  for (int l = 0; l < D - 1; ++l) {
+    SimtGemmArgs a{};
+    a.A = in;
+    a.B = prm[2 * l];
+    a.bias = prm[2 * l + 1];
+    a.Z = p->z32 + size_t(l) * n * W;
+    a.Out = p->a32 + size_t(l) * n * W;
+    a.M = int(n);
+    a.N = W;
+    a.K = in_dim;
+    a.lda = in_dim;
+    a.ldb = in_dim;
+    a.ldo = W;
+    a.omega = omega_of(p, l);
+    int rc = launch_simt<OP_NT_SINE>(a, 1, st);
+    if (rc) return rc;
+    in = a.Out;
+    in_dim = W;
+  }
+  {
+    SimtGemmArgs a{};
+    a.A = in;
+    a.B = prm[2 * (D - 1)];
+    a.bias = prm[2 * (D - 1) + 1];
+    a.Out = p->y32;
+    a.M = int(n);
+    a.N = C;
+    a.K = in_dim;
+    a.lda = in_dim;
+    a.ldb = in_dim;
+    a.ldo = C;
+    int rc = launch_simt<OP_NT_LIN>(a, 1, st);
+    if (rc) return rc;
+  }
+  LossArgs la{};
+  la.y = p->y32;
+  la.img = img_or_dpred;
+  la.pred = pred;
+  la.g = p->g32;
+  la.loss_partial = p->loss_part;
+  la.n = n * C;
+  la.mode = mode;
+  la.outermost_linear = p->cfg.outermost_linear;
+  la.omega = omega_of(p, D - 1);
+  simt_loss_kernel<<<256, 256, 0, st>>>(la);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads, float scale,
+                 float* stats, cudaStream_t st) {
+  const int D = p->D, W = p->W, C = p->C;
+  const int64_t n = p->npix;
+  const float* g = p->g32;  // dL/dz of layer l (seed units)
+  int gdim = C;
+  int pp = 0;
+  for (int l = D - 1; l >= 0; --l) {
+    const float* xin = (l == 0) ? p->x32 : p->a32 + size_t(l - 1) * n * W;
+    const int xdim = (l == 0) ? p->cfg.in_features : W;
+    // dW_l = g^T xin (split over pixels), db_l = column sums of g
+    SimtGemmArgs a{};
+    a.A = g;
+    a.B = xin;
+    a.Out = p->part32;
+    a.ColSum = p->part32 + size_t(p->simt_splits) * gdim * xdim;
+    a.M = gdim;
+    a.N = xdim;
+    a.K = int(n);
+    a.lda = gdim;
+    a.ldb = xdim;
+    a.ldo = xdim;
+    a.ksplit_len = p->simt_split_len;
+    int rc = launch_simt<OP_TN_PART>(a, p->simt_splits, st);
+    if (rc) return rc;
+    ReduceArgs ra{};
+    ra.d[0] = {grads[2 * l], p->part32, gdim * xdim, p->simt_splits, int64_t(gdim) * xdim};
+    ra.d[1] = {grads[2 * l + 1], a.ColSum, gdim, p->simt_splits, int64_t(gdim)};
+    ra.ndesc = 2;
+    ra.chunk_begin[0] = 0;
+    ra.chunk_begin[1] = cdiv(gdim * xdim, 1024);
+    ra.chunk_begin[2] = ra.chunk_begin[1] + cdiv(gdim, 1024);
+    ra.scale = scale;
+    ra.gscale = nullptr;
+    ra.stats = stats;
+    reduce_partials_kernel<<<ra.chunk_begin[2], 256, 0, st>>>(ra);
+    LAUNCH_CHECK();
+    if (l > 0) {
+      // g_{l-1} = (g_l W_l) .* omega cos(omega z_{l-1})
+      SimtGemmArgs b{};
+      b.A = g;
+      b.B = prm[2 * l];
+      b.Z = p->z32 + size_t(l - 1) * n * W;
+      b.Out = p->dz32[pp];
+      b.M = int(n);
+      b.N = W;
+      b.K = gdim;
+      b.lda = gdim;
+      b.ldb = W;
+      b.ldo = W;
+      b.omega = omega_of(p, l - 1);
+      rc = launch_simt<OP_NN_DCOS>(b, 1, st);
+      if (rc) return rc;
+      g = p->dz32[pp];
+      gdim = W;
+      pp ^= 1;
+    }
+  }
+  return 0;
+}
+
+int finalize(sirenb200_plan* p, const float* parts, int nparts, int64_t stride, float* stats,
+             bool tc, cudaStream_t st) {
+  FinalizeArgs fa{};
+  fa.loss_partial = parts;
+  fa.nparts = nparts;
+  fa.part_stride = stride;
+  fa.inv_count = p->inv_count;
+  fa.stats = stats;
+  fa.gstate = tc ? p->gstate : nullptr;
+  finalize_loss_kernel<<<1, 256, 0, st>>>(fa);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int sirenb200_version(void) { return 100; }
+const char* sirenb200_last_error(void) { return g_err; }
+int64_t sirenb200_launch_count(void) { return g_launches.load(); }
+
+int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
+  if (!cfg || !out) return fail(SIRENB200_ERR_INVALID, "null argument");
+  if (cfg->depth < 2 || cfg->depth > kMaxLayers)
+    return fail(SIRENB200_ERR_INVALID, "depth %d not in [2, %d]", cfg->depth, kMaxLayers);
+  if (cfg->hidden < 1 || cfg->in_features != 2 || cfg->out_features < 1 ||
+      cfg->out_features > kMaxOut)
+    return fail(SIRENB200_ERR_INVALID, "unsupported layer sizes (hidden %d, in %d, out %d)",
+                cfg->hidden, cfg->in_features, cfg->out_features);
+  if (cfg->height < 1 || cfg->width < 1 || cfg->row_begin < 0 || cfg->row_end > cfg->height ||
+      cfg->row_begin >= cfg->row_end)
+    return fail(SIRENB200_ERR_INVALID, "bad image geometry %dx%d rows [%d,%d)", cfg->height,
+                cfg->width, cfg->row_begin, cfg->row_end);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(SIRENB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", dev,
+                prop.major, prop.minor);
+  if (cfg->precision == SIRENB200_PREC_F16TC && !tc_supported(cfg->hidden))
+    return fail(SIRENB200_ERR_INVALID,
+                "tensor-core path supports hidden in {128, 256}; got %d (use SIRENB200_PREC_FP32)",
+                cfg->hidden);
+  if (cfg->precision != SIRENB200_PREC_F16TC && cfg->precision != SIRENB200_PREC_FP32)
+    return fail(SIRENB200_ERR_INVALID, "unknown precision %d", cfg->precision);
+
+  sirenb200_plan* p = new sirenb200_plan();
+  p->cfg = *cfg;
+  p->device = dev;
+  p->nsm = prop.multiProcessorCount;
+  p->D = cfg->depth;
+  p->W = cfg->hidden;
+  p->C = cfg->out_features;
+  p->rows = cfg->row_end - cfg->row_begin;
+  p->npix = int64_t(p->rows) * cfg->width;
+  p->ntiles = cdiv(p->npix, kRowsPerTile);
+  p->npix_pad = int64_t(p->ntiles) * kRowsPerTile;
+  p->inv_count = float(1.0 / (double(cfg->height) * cfg->width * cfg->out_features));
+  p->coord.width = cfg->width;
+  p->coord.row_begin = cfg->row_begin;
+  const int D = p->D, W = p->W, C = p->C;
+  int rc = 0;
+#define ALLOC(ptr, count)                 \
+  if ((rc = dev_alloc(p, &(ptr), (count)))) { \
+    sirenb200_destroy(p);                 \
+    return rc;                            \
+  }
+  ALLOC(p->gstate, 4);
+  ALLOC(p->eval_acc, 2);
+  {
+    const float init[4] = {1.f, 4096.f, 0.f, 0.f};
+    cudaError_t e = cudaMemcpy(p->gstate, init, sizeof(init), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      sirenb200_destroy(p);
+      return fail(SIRENB200_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+    }
+  }
+  if (cfg->precision == SIRENB200_PREC_FP32) {
+    ALLOC(p->loss_part, 256);
+    ALLOC(p->x32, p->npix * 2);
+    ALLOC(p->z32, int64_t(D - 1) * p->npix * W);
+    ALLOC(p->a32, int64_t(D - 1) * p->npix * W);
+    ALLOC(p->y32, p->npix * C);
+    ALLOC(p->g32, p->npix * C);
+    ALLOC(p->dz32[0], p->npix * W);
+    ALLOC(p->dz32[1], p->npix * W);
+    int splits = int((p->npix + 4095) / 4096);
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    p->simt_splits = splits;
+    p->simt_split_len = cdiv(cdiv(p->npix, splits), 16) * 16;
+    int64_t big = int64_t(W) * W;
+    if (big < 2 * int64_t(W)) big = 2 * int64_t(W);
+    if (big < int64_t(C) * W) big = int64_t(C) * W;
+    ALLOC(p->part32, int64_t(splits) * (big + W + 16));
+  } else {
+    const int nh = D - 2;
+    if (int64_t(D - 1) * p->npix_pad >= (int64_t(1) << 31)) {
+      sirenb200_destroy(p);
+      return fail(SIRENB200_ERR_INVALID, "shard too large for 32-bit TMA row coordinates");
+    }
+    ALLOC(p->act, int64_t(D - 1) * p->npix_pad * W);
+    ALLOC(p->dz, int64_t(D - 1) * p->npix_pad * W);
+    ALLOC(p->wh, int64_t(nh > 0 ? nh : 1) * W * W);
+    ALLOC(p->wth, int64_t(nh > 0 ? nh : 1) * W * W);
+    int splits = nh > 0 ? p->nsm / (nh * (W / 128)) : 1;
+    if (splits < 1) splits = 1;
+    if (splits > p->ntiles) splits = p->ntiles;
+    p->col_splits = splits;
+    ALLOC(p->dw_part, int64_t(splits) * (nh > 0 ? nh : 1) * W * W);
+    ALLOC(p->db_part, int64_t(splits) * (nh > 0 ? nh : 1) * W);
+    p->last_grid = p->nsm * 4;
+    if (p->last_grid * 8 > p->npix_pad) p->last_grid = cdiv(p->npix_pad, 8);
+    ALLOC(p->last_part, int64_t(p->last_grid) * (C * W + C + 1));
+    p->l0_grid = p->nsm * 4;
+    if (p->l0_grid > p->ntiles) p->l0_grid = p->ntiles;
+    ALLOC(p->l0_part, int64_t(p->l0_grid) * 3 * W);
+    cudaError_t e = cudaMemset(p->dz, 0, size_t(D - 1) * p->npix_pad * W * sizeof(__half));
+    if (e == cudaSuccess) e = cudaMemset(p->act, 0, size_t(D - 1) * p->npix_pad * W * sizeof(__half));
+    if (e != cudaSuccess) {
+      sirenb200_destroy(p);
+      return fail(SIRENB200_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    int trc = make_tmap_16bit(&p->tm_act, p->act, uint64_t(D - 1) * p->npix_pad, W, 128, false);
+    trc |= make_tmap_16bit(&p->tm_dz, p->dz, uint64_t(D - 1) * p->npix_pad, W, 128, false);
+    p->tm_w.resize(nh > 0 ? nh : 0);
+    p->tm_wt.resize(nh > 0 ? nh : 0);
+    for (int l = 0; l < nh; ++l) {
+      trc |= make_tmap_16bit(&p->tm_w[l], p->wh + size_t(l) * W * W, W, W, W, false);
+      trc |= make_tmap_16bit(&p->tm_wt[l], p->wth + size_t(l) * W * W, W, W, W, false);
+    }
+    if (trc) {
+      sirenb200_destroy(p);
+      return fail(SIRENB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", trc);
+    }
+  }
+#undef ALLOC
+  *out = p;
+  return 0;
+}
+
+int sirenb200_destroy(sirenb200_handle_t p) {
+  if (!p) return 0;
+  void* ptrs[] = {p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
+                  p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
+                  p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
+                  p->l0_part};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  delete p;
+  return 0;
+}
+
+int64_t sirenb200_workspace_bytes(sirenb200_handle_t h) { return h ? h->bytes : 0; }
+
+int sirenb200_set_grid_lut(sirenb200_handle_t h, const float* lin_h, const float* lin_w) {
+  if (!h || !lin_h || !lin_w) return fail(SIRENB200_ERR_INVALID, "null argument");
+  h->coord.lin_h = lin_h;
+  h->coord.lin_w = lin_w;
+  h->coord.coords = nullptr;
+  return 0;
+}
+
+int sirenb200_set_grid_coords(sirenb200_handle_t h, const float* coords) {
+  if (!h || !coords) return fail(SIRENB200_ERR_INVALID, "null argument");
+  h->coord.coords = coords;
+  return 0;
+}
+
+int sirenb200_forward(sirenb200_handle_t h, const float* const* prm, float* pred,
+                      sirenb200_stream_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!prm) return fail(SIRENB200_ERR_INVALID, "null parameter table");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (h->cfg.precision == SIRENB200_PREC_FP32) {
+    rc = f32_forward(h, prm, 0, nullptr, pred, st);
+  } else if (h->W == 256) {
+    rc = tc_forward<256>(h, prm, st, nullptr);
+    if (!rc) rc = tc_last<256>(h, prm, 0, nullptr, pred, st);
+  } else {
+    rc = tc_forward<128>(h, prm, st, nullptr);
+    if (!rc) rc = tc_last<128>(h, prm, 0, nullptr, pred, st);
+  }
+  h->have_fwd = (rc == 0);
+  return rc;
+}
+
+int sirenb200_forward_backward(sirenb200_handle_t h, const float* const* prm, const float* img,
+                               float loss_scale, float* const* grads, float* stats,
+                               sirenb200_stream_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!prm || !img || !grads || !stats) return fail(SIRENB200_ERR_INVALID, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float scale = loss_scale * h->inv_count;
+  if (h->cfg.precision == SIRENB200_PREC_FP32) {
+    CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(float), st));
+    rc = f32_forward(h, prm, 1, img, nullptr, st);
+    if (!rc) rc = f32_backward(h, prm, grads, scale, stats, st);
+    if (!rc) rc = finalize(h, h->loss_part, 256, 1, stats, false, st);
+  } else if (h->W == 256) {
+    rc = tc_forward<256>(h, prm, st, stats);
+    if (!rc) rc = tc_last<256>(h, prm, 1, img, nullptr, st);
+    if (!rc) rc = tc_backward<256>(h, prm, grads, scale, stats, st);
+    if (!rc)
+      rc = finalize(h, h->last_part + h->C * h->W + h->C, h->last_grid,
+                    int64_t(h->C) * h->W + h->C + 1, stats, true, st);
+  } else {
+    rc = tc_forward<128>(h, prm, st, stats);
+    if (!rc) rc = tc_last<128>(h, prm, 1, img, nullptr, st);
+    if (!rc) rc = tc_backward<128>(h, prm, grads, scale, stats, st);
+    if (!rc)
+      rc = finalize(h, h->last_part + h->C * h->W + h->C, h->last_grid,
+                    int64_t(h->C) * h->W + h->C + 1, stats, true, st);
+  }
+  h->have_fwd = (rc == 0);
+  return rc;
+}
+
+int sirenb200_backward(sirenb200_handle_t h, const float* const* prm, const float* dpred,
+                       float* const* grads, sirenb200_stream_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!prm || !dpred || !grads) return fail(SIRENB200_ERR_INVALID, "null argument");
+  if (!h->have_fwd)
+    return fail(SIRENB200_ERR_STATE, "sirenb200_backward needs a preceding sirenb200_forward");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* stats = h->gstate;  // scratch flag lives in gstate[2] (index 2 of a 4-float block)
+  if (h->cfg.precision == SIRENB200_PREC_FP32) {
+    // re-run the loss stage on the stashed last-layer output to seed the gradient
+    LossArgs la{};
+    la.y = h->y32;
+    la.img = dpred;
+    la.g = h->g32;
+    la.n = h->npix * h->C;
+    la.mode = 2;
+    la.outermost_linear = h->cfg.outermost_linear;
+    la.omega = omega_of(h, h->D - 1);
+    simt_loss_kernel<<<256, 256, 0, st>>>(la);
+    LAUNCH_CHECK();
+    rc = f32_backward(h, prm, grads, 1.0f, stats, st);
+  } else {
+    absmax_scale_kernel<<<1, 1024, 0, st>>>(dpred, h->npix * h->C, h->gstate);
+    LAUNCH_CHECK();
+    if (h->W == 256) {
+      rc = tc_last<256>(h, prm, 2, dpred, nullptr, st);
+      if (!rc) rc = tc_backward<256>(h, prm, grads, 1.0f, stats, st);
+    } else {
+      rc = tc_last<128>(h, prm, 2, dpred, nullptr, st);
+      if (!rc) rc = tc_backward<128>(h, prm, grads, 1.0f, stats, st);
+    }
+  }
+  return rc;
+}
+
+int sirenb200_eval_metrics(const float* pred, const float* img, int64_t n, float* out,
+                           sirenb200_stream_t stream) {
+  if (!pred || !img || !out || n <= 0) return fail(SIRENB200_ERR_INVALID, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* acc = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&acc), 2 * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+  int grid = cdiv(n, 256 * 8);
+  if (grid > 1184) grid = 1184;
+  eval_metrics_kernel<<<grid, 256, 0, st>>>(pred, img, n, acc);
+  LAUNCH_CHECK();
+  eval_metrics_finish_kernel<<<1, 1, 0, st>>>(acc, n, out);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaFreeAsync(acc, st));
+  return 0;
+}
+
+int sirenb200_adam_step(int32_t nt, float* const* prm, float* const* grads, float* const* m,
+                        float* const* v, const float* const* mask, const int64_t* numel, float lr,
+                        float beta1, float beta2, float eps, int32_t step, float inv_scale,
+                        const float* skip_flag, int32_t zero_grad, sirenb200_stream_t stream) {
+  if (nt < 1 || nt > kMaxTensors) return fail(SIRENB200_ERR_INVALID, "tensor count %d", nt);
+  if (!prm || !grads || !m || !v || !numel || step < 1)
+    return fail(SIRENB200_ERR_INVALID, "bad argument");
+  AdamArgs a{};
+  int chunks = 0;
+  for (int i = 0; i < nt; ++i) {
+    a.p[i] = prm[i];
+    a.g[i] = grads[i];
+    a.m[i] = m[i];
+    a.v[i] = v[i];
+    a.mask[i] = mask ? mask[i] : nullptr;
+    if (numel[i] < 0 || numel[i] > 0x7fffffff) return fail(SIRENB200_ERR_INVALID, "numel");
+    a.n[i] = int(numel[i]);
+    a.chunk_begin[i] = chunks;
+    chunks += cdiv(numel[i], 1024);
+  }
+  a.chunk_begin[nt] = chunks;
+  a.ntensors = nt;
+  a.beta1 = beta1;
+  a.beta2 = beta2;
+  a.eps = eps;
+  a.omb1 = float(1.0 - double(beta1));
+  a.omb2 = float(1.0 - double(beta2));
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  a.step_size = float(double(lr) / bc1);
+  a.bc2_sqrt = float(sqrt(bc2));
+  a.inv_scale = inv_scale;
+  a.skip_flag = skip_flag;
+  a.zero_grad = zero_grad;
+  a.dev_sched = nullptr;
+  if (chunks == 0) return 0;
+  adam_multi_kernel<<<chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int sirenb200_apply_mask(float* w, const float* mask, int64_t n, sirenb200_stream_t stream) {
+  if (!w || !mask || n < 0) return fail(SIRENB200_ERR_INVALID, "bad argument");
+  if (n == 0) return 0;
+  apply_mask_kernel<<<cdiv(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(w, mask, n);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int sirenb200_fakequant_per_channel(const float* w, int32_t rows, int32_t cols,
+                                    const float* row_min, const float* row_max, float neg_div,
+                                    float pos_div, int8_t* codes, float* scales, float* w_out,
+                                    sirenb200_stream_t stream) {
+  if (!w || rows < 1 || cols < 1 || !(neg_div > 0.f) || !(pos_div > 0.f))
+    return fail(SIRENB200_ERR_INVALID, "bad argument");
+  fakequant_rows_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, rows, cols, row_min, row_max, neg_div, pos_div, codes, scales, w_out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int sirenb200_kmeans_quantize(const float* w, int64_t n, int32_t bits, int32_t iter_limit, float tol,
+                              const float* init_centers, float* centroids, int32_t* n_centroids, int64_t* labels, float* w_out,
+                              sirenb200_stream_t stream) {
+  if (!w || n < 1 || bits < 1 || bits > 10 || !centroids || !n_centroids)
+    return fail(SIRENB200_ERR_INVALID, "bad argument (bits must be in [1, 10])");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int k = (1 << bits) - 1;
+  // scratch: centres[k] | minmax[2] | shift | sums[k] | cnts[k] | k_cur | status | label32[n]
+  const size_t fbytes = (size_t(k) * 2 + 8) * sizeof(float);
+  const size_t ibytes = (size_t(k) + 8 + size_t(n)) * sizeof(int);
+  char* scratch = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), fbytes + ibytes, st));
+  float* cent = reinterpret_cast<float*>(scratch);
+  float* mm = cent + k;
+  float* shift = mm + 2;
+  float* sums = mm + 8;
+  unsigned int* cnts = reinterpret_cast<unsigned int*>(scratch + fbytes);
+  int* k_cur = reinterpret_cast<int*>(cnts + k);
+  int* status = k_cur + 1;
+  int* label32 = k_cur + 8;
+  const float inf_init[2] = {INFINITY, -INFINITY};
+  CUDA_TRY(cudaMemcpyAsync(mm, inf_init, sizeof(inf_init), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(k_cur, &k, sizeof(int), cudaMemcpyHostToDevice, st));
+  int grid = cdiv(n, 256);
+  if (grid > 592) grid = 592;
+  int rc = 0;
+  auto cleanup = [&](int code) {
+    cudaFreeAsync(scratch, st);
+    return code;
+  };
+  kmeans_minmax_kernel<<<grid, 256, 0, st>>>(w, n, mm);
+  ++g_launches;
+  if (init_centers) {
+    CUDA_TRY(cudaMemcpyAsync(cent, init_centers, k * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    kmeans_linspace_kernel<<<cdiv(k, 256), 256, 0, st>>>(mm, k, cent);
+    ++g_launches;
+  }
+  for (int it = 0; it < iter_limit; ++it) {
+    kmeans_label_kernel<<<grid, 256, k * sizeof(float), st>>>(w, n, cent, k_cur, label32);
+    ++g_launches;
+    kmeans_cluster_sum_kernel<<<cdiv(k, 8), 256, 0, st>>>(w, n, label32, k_cur, sums, cnts);
+    ++g_launches;
+    KmeansUpdateArgs ua{cent, sums, cnts, k_cur, shift, status};
+    kmeans_update_kernel<<<1, 1024, 0, st>>>(ua);
+    ++g_launches;
+    float hs[1];
+    int hstat[1];
+    if (cudaMemcpyAsync(hs, shift, sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(hstat, status, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = fail(SIRENB200_ERR_CUDA, "k-means iteration failed: %s",
+                cudaGetErrorString(cudaGetLastError()));
+      return cleanup(rc);
+    }
+    if (hstat[0] != 0) {
+      rc = fail(SIRENB200_ERR_INVALID,
+                "k-means: top clusters are empty (the reference raises a shape mismatch here, "
+                "quant/kmeans_helper.py:91)");
+      return cleanup(rc);
+    }
+    if (hs[0] * hs[0] < tol) break;  // center_shift ** 2 < tolerance
+  }
+  kmeans_codebook_kernel<<<1, 1024, 0, st>>>(cent, k_cur, centroids, n_centroids);
+  ++g_launches;
+  kmeans_predict_kernel<<<grid, 256, (k + 1) * sizeof(float), st>>>(w, n, centroids, n_centroids,
+                                                                   labels, w_out);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return cleanup(fail(SIRENB200_ERR_CUDA, "k-means launch failed: %s", cudaGetErrorString(e)));
+  return cleanup(0);
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+/* siren_b200.h — C ABI of libsirenb200.so: the B200 (sm_100a) implementation of the per-image SIREN fit
+ * hot path of varun19299/implicit-image-compression.
+ *
+ * The reference has no FFI: its boundary is a Python call surface.  Each entry point below
+ * names the reference call it replaces (paths relative to the reference root, implicit_image/...).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative sirenb200_status on failure; it never throws and
+ *     never exits.  sirenb200_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers unless the parameter name starts with `h_` (host array).
+ *   - parameter tensors are fp32, row-major [out, in] weights and [out] biases, ordered as
+ *     model.parameters(): w0, b0, w1, b1, ... (2*depth entries).  Pointer arrays are read on every call and
+ *     never cached (the reference rebinds weight.data: pipeline/masking/core.py:279, quant/kmeans.py:71).
+ *   - calls are asynchronous on `stream`; no hidden host synchronisation unless stated.
+ *   - a handle is bound to the device that was current at create time and is not re-entrant.
+ */
+#ifndef SIREN_B200_H_
+#define SIREN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* sirenb200_stream_t;
+typedef struct sirenb200_plan* sirenb200_handle_t;
+
+typedef enum {
+  SIRENB200_OK = 0,
+  SIRENB200_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  SIRENB200_ERR_CUDA = -2,        /* CUDA runtime error (message has the details) */
+  SIRENB200_ERR_NO_DEVICE = -3,   /* no sm_100 device */
+  SIRENB200_ERR_STATE = -4        /* call sequence error (e.g. backward without grid) */
+} sirenb200_status;
+
+typedef enum {
+  SIRENB200_PREC_FP32 = 0,  /* fp32 CUDA-core path, any shape */
+  SIRENB200_PREC_F16TC = 1  /* fp16 operands / fp32 accumulate on tcgen05 tensor cores (hidden in {128,256}) */
+} sirenb200_precision;
+
+/* Siren(...) constructor arguments (models/siren.py:71-121) + the image geometry of compress.py:64-67. */
+typedef struct {
+  int32_t depth;            /* number of SineLayers including first and last (mlp.depth) */
+  int32_t hidden;           /* effective hidden width (after small_dense_density) */
+  int32_t in_features;      /* 2 */
+  int32_t out_features;     /* 3 (<= 4) */
+  float first_omega;        /* mlp.first_omega_0 */
+  float hidden_omega;       /* mlp.hidden_omega_0 */
+  int32_t outermost_linear; /* mlp.outermost_linear */
+  int32_t height, width;    /* full image size H x W: the loss is a mean over H*W*out_features */
+  int32_t row_begin;        /* this handle processes image rows [row_begin, row_end) (pixel sharding) */
+  int32_t row_end;
+  int32_t precision;        /* sirenb200_precision */
+  int32_t reserved[4];
+} sirenb200_config_t;
+
+int sirenb200_version(void);
+const char* sirenb200_last_error(void);
+
+int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out);
+int sirenb200_destroy(sirenb200_handle_t h);
+int64_t sirenb200_workspace_bytes(sirenb200_handle_t h);
+
+/* Input coordinates (data.py:78-88 get_grid + siren.py:125-128).  Either the two 1-D linspace tables
+ * (the grid is their outer product and is generated in-kernel from the pixel index), or an explicit
+ * [rows*width, 2] coordinate tensor (values in [0,1], (h, w) order) for arbitrary grids. */
+int sirenb200_set_grid_lut(sirenb200_handle_t h, const float* lin_h, const float* lin_w);
+int sirenb200_set_grid_coords(sirenb200_handle_t h, const float* coords);
+
+/* Siren.forward (models/siren.py:123-134): pred[rows, width, out_features] fp32 in [0,1] space. */
+int sirenb200_forward(sirenb200_handle_t h, const float* const* h_params, float* pred,
+                      sirenb200_stream_t stream);
+
+/* train_epoch's forward + F.mse_loss + backward (utils/train_helper.py:148-161).
+ * grads: h_grads[i] receives d(loss*loss_scale)/d(param i) summed over this handle's rows and divided
+ * by the FULL image element count (so that ranks can be summed); stats (device, 4 floats):
+ *   [0] sum of squared error over this handle's rows, [1] loss (= [0] / (H*W*out)) valid when the handle
+ *   covers the whole image, [2] 1.0 if any gradient is non-finite, [3] reserved. */
+int sirenb200_forward_backward(sirenb200_handle_t h, const float* const* h_params, const float* img,
+                               float loss_scale, float* const* h_grads, float* stats,
+                               sirenb200_stream_t stream);
+
+/* Backward for an arbitrary upstream gradient dpred[rows, width, out] (autograd of Siren.forward); uses
+ * the activations stashed by the last sirenb200_forward(_backward) call on this handle. */
+int sirenb200_backward(sirenb200_handle_t h, const float* const* h_params, const float* dpred,
+                       float* const* h_grads, sirenb200_stream_t stream);
+
+/* eval_epoch's metrics (utils/train_helper.py:48-57) from pred/img of n elements:
+ * out (device, 2 floats) = [mse, mse of the (x*255).int() images]. */
+int sirenb200_eval_metrics(const float* pred, const float* img, int64_t n, float* out,
+                           sirenb200_stream_t stream);
+
+/* torch.optim.Adam.step for a list of tensors (train_helper.py:72-78, stepped at :177 / core.py:687),
+ * fused with GradScaler's unscale + inf check (compress.py:131-135), Masking.apply_mask (core.py:272-279)
+ * and optim.zero_grad (train_helper.py:145).
+ *   h_mask[i] may be NULL (no mask).  step = 1-based step count after increment.
+ *   grads are multiplied by inv_scale before use; if skip_flag != NULL and *skip_flag != 0 (device float,
+ *   e.g. stats[2]) the update is skipped (GradScaler.step semantics) but masks are still applied. */
+int sirenb200_adam_step(int32_t n_tensors, float* const* h_params, float* const* h_grads,
+                        float* const* h_exp_avg, float* const* h_exp_avg_sq,
+                        const float* const* h_mask, const int64_t* h_numel, float lr, float beta1,
+                        float beta2, float eps, int32_t step, float inv_scale, const float* skip_flag,
+                        int32_t zero_grad, sirenb200_stream_t stream);
+
+/* Masking.apply_mask for one tensor (pipeline/masking/core.py:272-279): w <- w * mask (bit-exact). */
+int sirenb200_apply_mask(float* w, const float* mask, int64_t n, sirenb200_stream_t stream);
+
+/* KmeansQuant.find_centroids (pipeline/quant/kmeans.py:110-150 + kmeans_helper.py:59-116) on n weights.
+ * init_centers: optional [2^bits - 1] initial guess (kmeans.py:123-129 builds it with torch.linspace on the
+ * weights' device; NULL = linspace(min, max) of the non-zero weights evaluated in-kernel with CUDA
+ * torch.linspace's symmetric formula).
+ * Outputs: centroids[2^bits] (sorted by |c|, first n_centroids valid), n_centroids (device int32),
+ * labels[n] int64, w_out[n] = centroids[labels].  Synchronises `stream` internally (convergence test). */
+int sirenb200_kmeans_quantize(const float* w, int64_t n, int32_t bits, int32_t iter_limit, float tol,
+                              const float* init_centers, float* centroids, int32_t* n_centroids, int64_t* labels, float* w_out,
+                              sirenb200_stream_t stream);
+
+/* QAT weight fake-quant (torch per-channel weight fake-quant via quant/context.py:35-47): per-output-row
+ * symmetric int8, zero point 0:
+ *   scale = max(-min(lo,0) / neg_div, max(hi,0) / pos_div, eps);  q = clamp(rne(w * (1/scale)), -128, 127)
+ * row_min / row_max (device, [rows], the observer's running min / max) may both be NULL (use the row's own
+ * extrema).  (neg_div, pos_div) = (127.5, 127.5) is torch 1.7's observer formula (the reference's pin);
+ * (128, 127) is what torch >= 1.13's fused observer kernel computes. */
+int sirenb200_fakequant_per_channel(const float* w, int32_t rows, int32_t cols, const float* row_min,
+                                    const float* row_max, float neg_div, float pos_div, int8_t* codes,
+                                    float* scales, float* w_out, sirenb200_stream_t stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t sirenb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIREN_B200_H_ */

@@ -326,15 +326,18 @@ def kmeans_quantize(weight, bits, iter_limit=5, tolerance=1e-4):
     return cent, labels, cent[labels]
 
 
-def fake_quant_per_channel_weight(weight, max_abs=None):
-    """torch default_per_channel_weight_fake_quant as used by get_default_qat_qconfig('fbgemm')
-    (pipeline/quant/context.py:35-47): per-output-channel symmetric qint8, quant range [-128,127],
-    scale = max(|min_c|,|max_c|) / 127.5 (clamped to >= eps), zero point 0,
-    q = clamp(rne(w/scale), -128, 127).  Returns (codes int8, scale[out], dequantised weight)."""
-    if max_abs is None:
-        mn = torch.minimum(weight.min(dim=1).values, torch.zeros(weight.shape[0]))
-        mx = torch.maximum(weight.max(dim=1).values, torch.zeros(weight.shape[0]))
-        max_abs = torch.maximum(-mn, mx)
-    scale = (max_abs / (float(127 - (-128)) / 2)).clamp(min=torch.finfo(torch.float32).eps)
-    q = torch.clamp(torch.round(weight / scale[:, None]), -128, 127)  # torch.round = RNE
+def fake_quant_per_channel_weight(weight, row_min=None, row_max=None, neg_div=128.0, pos_div=127.0):
+    """Per-channel weight fake-quant used by get_default_qat_qconfig('fbgemm') (pipeline/quant/context.py:
+    35-47): per-output-channel symmetric qint8, quant range [-128, 127], zero point 0,
+      scale = max(-min(lo,0)/neg_div, max(hi,0)/pos_div, eps), q = clamp(rne(w * (1/scale)), -128, 127).
+    The installed torch (2.11) runs the FUSED observer kernel (fbgemm ChooseQuantizationParams with
+    preserve_sparsity): (neg_div, pos_div) = (128, 127).  torch 1.7 (the reference's pin) used the Python
+    observer formula max(|lo|, hi) / 127.5, i.e. (127.5, 127.5).
+    Returns (codes int8, scale[out], dequantised weight)."""
+    lo = weight.min(dim=1).values if row_min is None else row_min
+    hi = weight.max(dim=1).values if row_max is None else row_max
+    zero = torch.zeros_like(lo)
+    scale = torch.maximum(-torch.minimum(lo, zero) / neg_div, torch.maximum(hi, zero) / pos_div)
+    scale = scale.clamp(min=torch.finfo(torch.float32).eps)
+    q = torch.clamp(torch.round(weight * (1.0 / scale)[:, None]), -128, 127)  # torch.round = RNE
     return q.to(torch.int8), scale, q * scale[:, None]
