@@ -1,0 +1,85 @@
+"""Fit driver mirroring the reference entry point (implicit_image/compress.py:54-269) for the hot path:
+build image / grid / model, main fit loop (:137-170), quantisation fine-tune loop (:172-216).
+Saving weights and entropy coding (:242-263) stay on the host and are out of scope, as are W&B and hydra
+(`config.load_config` reads the same keys).  Usage:
+    python -m implicit_image_compression_b200.compress mlp.hidden_size=256 mlp.depth=6 masking=none quant=none
+"""
+import logging
+import sys
+from copy import deepcopy
+
+import torch
+
+from .config import load_config
+from .data import get_grid, synth_image
+from .fit import Fitter
+from .models import registry as model_registry
+from .pipeline.quant import context as quant_context
+from .utils.train_helper import eval_epoch, get_device, get_optimizer_lr_scheduler, setup_mask, train_epoch
+
+
+def main(cfg, fast=True):
+    """Returns a dict of the numbers the reference logs (PSNR, Quant PSNR, Density, ...)."""
+    torch.manual_seed(cfg.seed)
+    device = get_device(cfg.device)
+    img = synth_image(cfg.img.height, cfg.img.width, cfg.img.get("index", 0), cfg.img.get("bits", 16))
+    grid = get_grid(cfg.img.height, cfg.img.width)
+
+    small_density = 1.0
+    if cfg.get("masking") and cfg.masking.get("name") == "Small_Dense":
+        small_density = cfg.masking.density
+    model = model_registry[cfg.mlp.name](**cfg.mlp, small_dense_density=small_density)
+    model, grid, img = model.to(device), grid.to(device), img.to(device)
+
+    model.train()
+    optim, lr_scheduler = get_optimizer_lr_scheduler(model, cfg.optim)
+    mult = cfg.train.multiplier
+    num_steps = cfg.train.num_steps * mult
+    masking_cfg = cfg.get("masking") or None
+    if masking_cfg:
+        if masking_cfg.get("end_when"):
+            masking_cfg["end_when"] = int(masking_cfg["end_when"] * mult)
+        if masking_cfg.get("interval"):
+            masking_cfg["interval"] = int(masking_cfg["interval"] * mult)
+    mask = setup_mask(model, optim, masking_cfg)
+    out = {}
+
+    if fast:
+        fitter = Fitter(model, optim, grid, img, lr_scheduler, mask, masking_cfg if mask else None)
+        done = 0
+        while done < num_steps:
+            k = min(cfg.train.log_steps, num_steps - done)
+            fitter.steps(k)
+            done += k
+            _, loss, psnr, psnr8 = eval_epoch(model, grid, img)
+            out.update(loss=loss, PSNR=psnr, PSNR_8bit=psnr8)
+            logging.info(f"Train | Step: {done} | loss: {loss:.6f} | PSNR: {psnr:.4f} | PSNR_8bit: {psnr8:.4f}")
+    else:
+        for i in range(num_steps):
+            train_epoch(model, optim, grid, img, lr_scheduler=lr_scheduler, mask=mask)
+            if mask and i <= masking_cfg["end_when"] and i % masking_cfg["interval"] == 0:
+                mask.update_connections()
+            if (i + 1) % cfg.train.log_steps == 0:
+                _, loss, psnr, psnr8 = eval_epoch(model, grid, img)
+                out.update(loss=loss, PSNR=psnr, PSNR_8bit=psnr8)
+    if mask:
+        out.update({"Prune Rate": mask.prune_rate, "Density": mask.stats.total_density})
+
+    if cfg.get("quant"):
+        quantized_model = deepcopy(model)
+        optim_q, sched_q = get_optimizer_lr_scheduler(quantized_model, cfg.optim, quantize_mode=True)
+        quantized_model.train()
+        with quant_context.Quantize(quantized_model, optim_q, cfg.quant) as q:
+            for i in range(cfg.quant.num_steps):
+                # the reference passes the ORIGINAL model's mask here (App. A.2), which steps the old
+                # optimizer; the fixed behaviour (fine-tune the quantised copy) is what runs here.
+                train_epoch(quantized_model, optim_q, grid, img, lr_scheduler=sched_q)
+        quantized_model = q.convert()
+        _, loss, psnr, psnr8 = eval_epoch(quantized_model, grid, img)
+        out.update({"Quant loss": loss, "Quant PSNR": psnr, "Quant PSNR 8bit": psnr8})
+    return out
+
+
+if __name__ == "__main__":
+    logging.basicConfig(level=logging.INFO)
+    print(main(load_config(sys.argv[1:])))

@@ -47,8 +47,9 @@ class _SirenFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, grid, *params):
         engine = model.engine_for(grid)
-        pred = engine.forward([p.detach() for p in params])
-        ctx.engine, ctx.generation = engine, engine.generation
+        kparams = model.kernel_parameters()
+        pred = engine.forward(kparams)
+        ctx.engine, ctx.generation, ctx.kparams = engine, engine.generation, kparams
         ctx.save_for_backward(*params)
         return pred
 
@@ -57,9 +58,8 @@ class _SirenFunction(torch.autograd.Function):
         engine = ctx.engine
         if engine.generation != ctx.generation:
             raise _lib.SirenB200Error("stale activations: another forward ran on this model before backward")
-        params = [p.detach() for p in ctx.saved_tensors]
-        grads = [torch.empty_like(p) for p in params]
-        engine.backward(params, dpred.contiguous(), grads)
+        grads = [torch.empty_like(p) for p in ctx.kparams]
+        engine.backward(ctx.kparams, dpred.contiguous(), grads)
         return (None, None, *grads)
 
 
@@ -89,6 +89,8 @@ class Siren(nn.Module):
         self.precision = precision  # None = automatic ("f16tc" when hidden in {128, 256}, else "fp32")
         self._engines = {}
         self._weight_transforms = []  # callables run before every forward ("weight load" hooks)
+        self._param_override = {}     # param -> tensor the kernels read instead (fake-quantised weights)
+        self._post_backward = []      # callables run after the fused backward filled param.grad
 
     # --------------------------------------------------------------------------------------------
     def hot_parameters(self):
@@ -97,6 +99,10 @@ class Siren(nn.Module):
         for layer in self.layers:
             out += [layer.linear.weight, layer.linear.bias]
         return out
+
+    def kernel_parameters(self):
+        """Tensors whose pointers go to the kernels: the parameters, or their weight-load overrides."""
+        return [self._param_override.get(p, p.data) for p in self.hot_parameters()]
 
     def _precision_code(self):
         if self.precision in (None, "auto"):
@@ -132,7 +138,7 @@ class Siren(nn.Module):
         params = self.hot_parameters()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _SirenFunction.apply(self, grid, *params)
-        return self.engine_for(grid).forward([p.detach() for p in params])
+        return self.engine_for(grid).forward(self.kernel_parameters())
 
     def __deepcopy__(self, memo):
         # engines own device workspaces and ctypes handles: never copy them (compress.py:174 deepcopy)
@@ -144,6 +150,10 @@ class Siren(nn.Module):
             if k == "_engines":
                 new.__dict__[k] = {}
             elif k == "_weight_transforms":
+                new.__dict__[k] = []
+            elif k == "_param_override":
+                new.__dict__[k] = {}
+            elif k == "_post_backward":
                 new.__dict__[k] = []
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)

@@ -134,7 +134,9 @@ def _fused_loss_and_grads(model, grid, img):
         if p.grad is None or p.grad.shape != p.shape:
             p.grad = torch.empty_like(p)
     eng = model.engine_for(grid)
-    stats = eng.forward_backward([p.data for p in params], img.contiguous(), [p.grad for p in params])
+    stats = eng.forward_backward(model.kernel_parameters(), img.contiguous(), [p.grad for p in params])
+    for fn in model._post_backward:
+        fn(model)
     return stats
 
 
