@@ -32,7 +32,8 @@ __device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh,
     gh = v.x;
     gw = v.y;
   } else {
-    const int r = int(p / c.width), col = int(p - int64_t(r) * c.width);
+    const unsigned pu = unsigned(p);  // npix < 2^31 (checked at create)
+    const int r = int(pu / unsigned(c.width)), col = int(pu - unsigned(r) * unsigned(c.width));
     gh = __ldg(c.lin_h + c.row_begin + r);
     gw = __ldg(c.lin_w + col);
   }
@@ -286,7 +287,33 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
     }
   const float G = (a.mode != 0) ? *a.gscale : 1.f;
   const int64_t nwarps = int64_t(gridDim.x) * 8;
-  for (int64_t p = int64_t(blockIdx.x) * 8 + warp; p < a.npix_pad; p += nwarps) {
+  // software pipeline: the activation rows of the next PF iterations are already in flight
+  constexpr int PF = 3;
+  uint4 q[PF][NCH];
+  auto fetch = [&](int64_t row, uint4 (&dst)[NCH]) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      dst[ch] = make_uint4(0, 0, 0, 0);
+      if (on && row < a.npix) dst[ch] = reinterpret_cast<const uint4*>(a.act + row * W)[ch * 32 + lane];
+    }
+  };
+  const int64_t pstart = int64_t(blockIdx.x) * 8 + warp;
+#pragma unroll
+  for (int i = 0; i < PF; ++i) fetch(pstart + i * nwarps, q[i]);
+  for (int64_t p = pstart; p < a.npix_pad; p += nwarps) {
+    uint32_t raw[NCH * 4];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      raw[ch * 4 + 0] = q[0][ch].x;
+      raw[ch * 4 + 1] = q[0][ch].y;
+      raw[ch * 4 + 2] = q[0][ch].z;
+      raw[ch * 4 + 3] = q[0][ch].w;
+    }
+#pragma unroll
+    for (int i = 0; i + 1 < PF; ++i)
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) q[i][ch] = q[i + 1][ch];
+    fetch(p + PF * nwarps, q[PF - 1]);
     if (p >= a.npix) {  // padding rows: zero gradient so the dW reduction ignores them
       if (a.mode != 0 && on)
 #pragma unroll
@@ -294,17 +321,7 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
           reinterpret_cast<uint4*>(a.dz + p * W)[ch * 32 + lane] = make_uint4(0, 0, 0, 0);
       continue;
     }
-    uint32_t raw[NCH * 4];
     float av[NCH * 8];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (on) v = reinterpret_cast<const uint4*>(a.act + p * W)[ch * 32 + lane];
-      raw[ch * 4 + 0] = v.x;
-      raw[ch * 4 + 1] = v.y;
-      raw[ch * 4 + 2] = v.z;
-      raw[ch * 4 + 3] = v.w;
-    }
 #pragma unroll
     for (int j = 0; j < NCH * 4; ++j) {
       const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw[j]));
@@ -413,41 +430,60 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
 template <int W>
 __global__ void __launch_bounds__(256) tc_layer0_grad_kernel(CoordSrc c, const __half* __restrict__ dz0,
                                                              float* __restrict__ part, int64_t npix) {
-  constexpr int TPR = W / 2;      // threads per row (2 columns each)
+  constexpr int TPR = W / 8;      // threads per row (8 columns = 16 bytes each)
   constexpr int RL = 256 / TPR;   // row lanes
+  constexpr int UN = 4;           // rows in flight per thread
   const int tc = threadIdx.x % TPR, tr = threadIdx.x / TPR;
   const int64_t per_block = (npix + gridDim.x - 1) / gridDim.x;
   const int64_t p0 = blockIdx.x * per_block;
   const int64_t p1 = min(npix, p0 + per_block);
-  float ah0 = 0, aw0 = 0, ab0 = 0, ah1 = 0, aw1 = 0, ab1 = 0;
-  for (int64_t p = p0 + tr; p < p1; p += RL) {
-    float xh, xw;
-    load_xy(c, p, xh, xw);
-    const float2 g = __half22float2(reinterpret_cast<const __half2*>(dz0 + p * W)[tc]);
-    ah0 = fmaf(g.x, xh, ah0);
-    aw0 = fmaf(g.x, xw, aw0);
-    ab0 += g.x;
-    ah1 = fmaf(g.y, xh, ah1);
-    aw1 = fmaf(g.y, xw, aw1);
-    ab1 += g.y;
-  }
-  __shared__ float red[RL][TPR][6];
-  red[tr][tc][0] = ah0; red[tr][tc][1] = aw0; red[tr][tc][2] = ab0;
-  red[tr][tc][3] = ah1; red[tr][tc][4] = aw1; red[tr][tc][5] = ab1;
-  __syncthreads();
-  if (tr == 0) {
-    float s[6] = {};
-    for (int r = 0; r < RL; ++r)
+  float ah[8] = {}, aw[8] = {}, ab[8] = {};
+  for (int64_t p = p0 + tr; p < p1; p += RL * UN) {
+    uint4 v[UN];
+    float xh[UN], xw[UN];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s[k] += red[r][tc][k];
-    float* out = part + int64_t(blockIdx.x) * (3 * W);
-    const int j0 = 2 * tc;
-    out[j0 * 2 + 0] = s[0];       // dW0[j0, h]
-    out[j0 * 2 + 1] = s[1];       // dW0[j0, w]
-    out[(j0 + 1) * 2 + 0] = s[3];
-    out[(j0 + 1) * 2 + 1] = s[4];
-    out[2 * W + j0] = s[2];       // db0
-    out[2 * W + j0 + 1] = s[5];
+    for (int u = 0; u < UN; ++u) {
+      const int64_t q = p + u * RL;
+      v[u] = make_uint4(0, 0, 0, 0);
+      xh[u] = xw[u] = 0.f;
+      if (q < p1) {
+        v[u] = reinterpret_cast<const uint4*>(dz0 + q * W)[tc];
+        load_xy(c, q, xh[u], xw[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
+        ah[2 * j] = fmaf(g.x, xh[u], ah[2 * j]);
+        aw[2 * j] = fmaf(g.x, xw[u], aw[2 * j]);
+        ab[2 * j] += g.x;
+        ah[2 * j + 1] = fmaf(g.y, xh[u], ah[2 * j + 1]);
+        aw[2 * j + 1] = fmaf(g.y, xw[u], aw[2 * j + 1]);
+        ab[2 * j + 1] += g.y;
+      }
+    }
+  }
+  __shared__ float red[RL][3][W + 8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[tr][0][tc * 8 + j] = ah[j];
+    red[tr][1][tc * 8 + j] = aw[j];
+    red[tr][2][tc * 8 + j] = ab[j];
+  }
+  __syncthreads();
+  float* out = part + int64_t(blockIdx.x) * (3 * W);
+  for (int i = threadIdx.x; i < 3 * W; i += 256) {
+    const int k = i / W, col = i % W;
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < RL; ++r) sum += red[r][k][col];
+    if (k < 2)
+      out[col * 2 + k] = sum;  // dW0[col, {h, w}]
+    else
+      out[2 * W + col] = sum;  // db0[col]
   }
 }
 
@@ -496,29 +532,43 @@ struct ReduceDesc {
 };
 struct ReduceArgs {
   ReduceDesc d[kMaxTensors];
-  int chunk_begin[kMaxTensors + 1];  // prefix sums of ceil(n / 1024)
+  int chunk_begin[kMaxTensors + 1];  // prefix sums of ceil(n / 32)
   int ndesc;
   float scale;               // host-known factor
   const float* gscale;       // device seed scale G (grads are divided by it) or null
   float* stats;              // stats[2] <- 1 if any non-finite
 };
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
+  // block = 32 consecutive elements x 8 split lanes (one warp per lane: 128-byte coalesced rows)
   int t = 0;
   while (t + 1 < a.ndesc && int(blockIdx.x) >= a.chunk_begin[t + 1]) ++t;
   const ReduceDesc d = a.d[t];
   const float scale = a.gscale ? a.scale / *a.gscale : a.scale;
-  const int base = (blockIdx.x - a.chunk_begin[t]) * 1024;
-  bool bad = false;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = base + k * 256 + threadIdx.x;
-    if (i < d.n) {
-      float s = 0.f;
-      for (int sp = 0; sp < d.nsplit; ++sp) s += d.src[sp * d.split_stride + i];
-      s *= scale;
-      d.dst[i] = s;
-      bad |= !isfinite(s);
+  const int e = (blockIdx.x - a.chunk_begin[t]) * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x >> 5;
+  float s = 0.f;
+  if (e < d.n) {
+    int sp = lane;
+    for (; sp + 24 < d.nsplit; sp += 32) {  // 4 independent loads in flight
+      const float v0 = d.src[int64_t(sp) * d.split_stride + e];
+      const float v1 = d.src[int64_t(sp + 8) * d.split_stride + e];
+      const float v2 = d.src[int64_t(sp + 16) * d.split_stride + e];
+      const float v3 = d.src[int64_t(sp + 24) * d.split_stride + e];
+      s += (v0 + v1) + (v2 + v3);
     }
+    for (; sp < d.nsplit; sp += 8) s += d.src[int64_t(sp) * d.split_stride + e];
+  }
+  __shared__ float red[8][32];
+  red[lane][threadIdx.x & 31] = s;
+  __syncthreads();
+  bool bad = false;
+  if (lane == 0 && e < d.n) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[k][threadIdx.x];
+    r *= scale;
+    d.dst[e] = r;
+    bad = !isfinite(r);
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) a.stats[2] = 1.0f;
 }

@@ -93,7 +93,44 @@ struct sirenb200_plan {
   int last_grid = 0;
   float* l0_part = nullptr;    // [l0_grid][3*W]
   int l0_grid = 0;
+
+  // ---- optional per-kernel timing (cudaEvent pairs recorded around tagged launches) ----
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+  std::vector<int> prof_kind;         // kind of pair i
+  size_t prof_used = 0;
 };
+
+enum ProfKind {
+  PK_PREP = 0, PK_FIRST = 1, PK_FWD_GEMM = 2, PK_LAST = 3, PK_DX_GEMM = 4, PK_DW_GEMM = 5,
+  PK_L0_GRAD = 6, PK_REDUCE = 7, PK_FINALIZE = 8, PK_COUNT = 9
+};
+
+namespace {
+struct ProfScope {
+  sirenb200_plan* p;
+  cudaStream_t st;
+  cudaEvent_t stop = nullptr;
+  ProfScope(sirenb200_plan* plan, int kind, cudaStream_t s) : p(plan), st(s) {
+    if (!p->prof_on) return;
+    if (p->prof_used + 2 > p->prof_ev.size()) {
+      for (int i = 0; i < 512; ++i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        p->prof_ev.push_back(e);
+      }
+    }
+    cudaEvent_t start = p->prof_ev[p->prof_used];
+    stop = p->prof_ev[p->prof_used + 1];
+    p->prof_used += 2;
+    p->prof_kind.push_back(kind);
+    cudaEventRecord(start, st);
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, st);
+  }
+};
+}  // namespace
 
 namespace {
 
@@ -135,7 +172,10 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   }
   const int grid = args.num_tiles < p->nsm ? args.num_tiles : p->nsm;
   const uint32_t idesc = umma_idesc(128, W, 0, 0, 0, 0);
-  kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
+  {
+    ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
+    kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -151,8 +191,12 @@ int launch_colgemm(sirenb200_plan* p, const ColGemmJobs& jobs, cudaStream_t st) 
     attr_set[p->device & 63] = true;
   }
   const int grid = jobs.num_problems * jobs.mblocks * jobs.splits;
-  kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(p->tm_dz, p->tm_act, jobs, umma_idesc(128, W, 0, 0, 1, 1),
-                                          umma_idesc(128, 16, 0, 0, 1, 1));
+  {
+    ProfScope ps(p, PK_DW_GEMM, st);
+    kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(p->tm_dz, p->tm_act, jobs,
+                                            umma_idesc(128, W, 0, 0, 1, 1),
+                                            umma_idesc(128, 16, 0, 0, 1, 1));
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -175,15 +219,21 @@ int tc_forward(sirenb200_plan* p, const float* const* prm, cudaStream_t st, floa
     pa.wh = p->wh;
     pa.wth = p->wth;
     pa.stats = stats_to_zero;
-    tc_prep_weights_kernel<<<dim3(W / 32, W / 32, nh), 256, 0, st>>>(pa);
+    {
+      ProfScope ps(p, PK_PREP, st);
+      tc_prep_weights_kernel<<<dim3(W / 32, W / 32, nh), 256, 0, st>>>(pa);
+    }
     LAUNCH_CHECK();
   } else if (stats_to_zero) {
     CUDA_TRY(cudaMemsetAsync(stats_to_zero, 0, 4 * sizeof(float), st));
   }
   {
     const int grid = p->nsm * 8;
-    tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(p->coord, prm[0], prm[1], omega_of(p, 0), p->act,
-                                                  p->npix, p->npix_pad);
+    {
+      ProfScope ps(p, PK_FIRST, st);
+      tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(p->coord, prm[0], prm[1], omega_of(p, 0), p->act,
+                                                    p->npix, p->npix_pad);
+    }
     LAUNCH_CHECK();
   }
   for (int l = 1; l <= nh; ++l) {
@@ -221,7 +271,10 @@ int tc_last(sirenb200_plan* p, const float* const* prm, int mode, const float* i
   la.outermost_linear = p->cfg.outermost_linear;
   la.omega_last = omega_of(p, D - 1);
   la.omega_prev = omega_of(p, D - 2);
-  tc_last_layer_kernel<W><<<p->last_grid, 256, 0, st>>>(la);
+  {
+    ProfScope ps(p, PK_LAST, st);
+    tc_last_layer_kernel<W><<<p->last_grid, 256, 0, st>>>(la);
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -260,7 +313,10 @@ int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads,
     int rc = launch_colgemm<W>(p, jobs, st);
     if (rc) return rc;
   }
-  tc_layer0_grad_kernel<W><<<p->l0_grid, 256, 0, st>>>(p->coord, p->dz, p->l0_part, p->npix);
+  {
+    ProfScope ps(p, PK_L0_GRAD, st);
+    tc_layer0_grad_kernel<W><<<p->l0_grid, 256, 0, st>>>(p->coord, p->dz, p->l0_part, p->npix);
+  }
   LAUNCH_CHECK();
 
   // reduce every partial buffer into the caller's gradient tensors
@@ -288,13 +344,16 @@ int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads,
   int chunks = 0;
   for (int i = 0; i < nd; ++i) {
     ra.chunk_begin[i] = chunks;
-    chunks += cdiv(ra.d[i].n, 1024);
+    chunks += cdiv(ra.d[i].n, 32);
   }
   ra.chunk_begin[nd] = chunks;
   ra.scale = scale;
   ra.gscale = p->gstate;
   ra.stats = stats;
-  reduce_partials_kernel<<<chunks, 256, 0, st>>>(ra);
+  {
+    ProfScope ps(p, PK_REDUCE, st);
+    reduce_partials_kernel<<<chunks, 256, 0, st>>>(ra);
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -397,8 +456,8 @@ int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads
     ra.d[1] = {grads[2 * l + 1], a.ColSum, gdim, p->simt_splits, int64_t(gdim)};
     ra.ndesc = 2;
     ra.chunk_begin[0] = 0;
-    ra.chunk_begin[1] = cdiv(gdim * xdim, 1024);
-    ra.chunk_begin[2] = ra.chunk_begin[1] + cdiv(gdim, 1024);
+    ra.chunk_begin[1] = cdiv(gdim * xdim, 32);
+    ra.chunk_begin[2] = ra.chunk_begin[1] + cdiv(gdim, 32);
     ra.scale = scale;
     ra.gscale = nullptr;
     ra.stats = stats;
@@ -437,7 +496,10 @@ int finalize(sirenb200_plan* p, const float* parts, int nparts, int64_t stride, 
   fa.inv_count = p->inv_count;
   fa.stats = stats;
   fa.gstate = tc ? p->gstate : nullptr;
-  finalize_loss_kernel<<<1, 256, 0, st>>>(fa);
+  {
+    ProfScope ps(p, PK_FINALIZE, st);
+    finalize_loss_kernel<<<1, 256, 0, st>>>(fa);
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -544,7 +606,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     p->col_splits = splits;
     ALLOC(p->dw_part, int64_t(splits) * (nh > 0 ? nh : 1) * W * W);
     ALLOC(p->db_part, int64_t(splits) * (nh > 0 ? nh : 1) * W);
-    p->last_grid = p->nsm * 4;
+    p->last_grid = p->nsm * 2;
     if (p->last_grid * 8 > p->npix_pad) p->last_grid = cdiv(p->npix_pad, 8);
     ALLOC(p->last_part, int64_t(p->last_grid) * (C * W + C + 1));
     p->l0_grid = p->nsm * 4;
@@ -582,11 +644,40 @@ int sirenb200_destroy(sirenb200_handle_t p) {
                   p->l0_part};
   for (void* q : ptrs)
     if (q) cudaFree(q);
+  for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
   delete p;
   return 0;
 }
 
 int64_t sirenb200_workspace_bytes(sirenb200_handle_t h) { return h ? h->bytes : 0; }
+
+int sirenb200_profile_enable(sirenb200_handle_t h, int32_t enable) {
+  if (!h) return fail(SIRENB200_ERR_INVALID, "null handle");
+  h->prof_on = enable != 0;
+  h->prof_used = 0;
+  h->prof_kind.clear();
+  return 0;
+}
+
+int sirenb200_profile_read(sirenb200_handle_t h, float* h_total_ms, int32_t* h_count, int32_t n_kinds) {
+  if (!h || !h_total_ms || !h_count) return fail(SIRENB200_ERR_INVALID, "null argument");
+  for (int k = 0; k < n_kinds; ++k) {
+    h_total_ms[k] = 0.f;
+    h_count[k] = 0;
+  }
+  for (size_t i = 0; i < h->prof_kind.size(); ++i) {
+    cudaEvent_t a = h->prof_ev[2 * i], b = h->prof_ev[2 * i + 1];
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    const int k = h->prof_kind[i];
+    if (k < n_kinds) {
+      h_total_ms[k] += ms;
+      h_count[k] += 1;
+    }
+  }
+  return 0;
+}
 
 int sirenb200_set_grid_lut(sirenb200_handle_t h, const float* lin_h, const float* lin_w) {
   if (!h || !lin_h || !lin_w) return fail(SIRENB200_ERR_INVALID, "null argument");

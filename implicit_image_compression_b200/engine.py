@@ -126,6 +126,17 @@ class SirenEngine:
     def workspace_bytes(self):
         return int(self.lib.sirenb200_workspace_bytes(self.handle))
 
+    def profile(self, enable):
+        _lib.check(self.lib.sirenb200_profile_enable(self.handle, int(bool(enable))))
+
+    def profile_read(self):
+        """{kind: (total_ms, launches)} of the tagged kernels since profile(True)."""
+        n = len(_lib.PROFILE_KINDS)
+        ms = (ctypes.c_float * n)()
+        cnt = (ctypes.c_int32 * n)()
+        _lib.check(self.lib.sirenb200_profile_read(self.handle, ms, cnt, n))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.PROFILE_KINDS)}
+
 
 def eval_metrics(pred, img):
     """Device tensor [mse, mse_8bit] (train_helper.py:48-57)."""

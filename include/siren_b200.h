@@ -127,6 +127,14 @@ int sirenb200_fakequant_per_channel(const float* w, int32_t rows, int32_t cols, 
                                     const float* row_max, float neg_div, float pos_div, int8_t* codes,
                                     float* scales, float* w_out, sirenb200_stream_t stream);
 
+/* Optional per-kernel timing for bench.py's roofline: while enabled, tagged launches of this handle are
+ * bracketed by cudaEvent pairs on the launching stream.  profile_read synchronises the recorded events and
+ * returns, per kind, the summed device time (ms) and the launch count into HOST arrays of n_kinds entries.
+ * Kinds: 0 weight staging, 1 first layer, 2 forward GEMM, 3 last layer + loss, 4 dX GEMM, 5 dW GEMM,
+ *        6 layer-0 gradient, 7 partial reduction, 8 loss finalise. */
+int sirenb200_profile_enable(sirenb200_handle_t h, int32_t enable);
+int sirenb200_profile_read(sirenb200_handle_t h, float* h_total_ms, int32_t* h_count, int32_t n_kinds);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t sirenb200_launch_count(void);
 
