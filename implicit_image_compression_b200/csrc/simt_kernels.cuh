@@ -22,11 +22,13 @@ struct CoordSrc {
   const float* coords;  // [npix, 2] or null
   int width;            // image width
   int row_begin;        // first image row of this handle
+  int64_t p_offset;     // pixel offset of the current launch inside the handle's rows (row chunks)
 };
 
 // siren.py:125-128: x = (grid - 0.5) * 2, features ordered (h, w) (data.py:82-86, 'ij' meshgrid)
 __device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh, float& xw) {
   float gh, gw;
+  p += c.p_offset;
   if (c.coords) {
     const float2 v = reinterpret_cast<const float2*>(c.coords)[p];
     gh = v.x;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -91,8 +92,10 @@ struct sirenb200_plan {
   int col_splits = 1;
   float* last_part = nullptr;  // [last_grid][C*W + C + 1]
   int last_grid = 0;
-  float* l0_part = nullptr;    // [l0_grid][3*W]
+  float* l0_part = nullptr;    // [nchunks][l0_grid][3*W]
   int l0_grid = 0;
+  int chunk_tiles = 0;         // 128-row tiles per L2-resident chunk (0 = whole shard)
+  int nchunks = 1;
 
   // ---- optional per-kernel timing (cudaEvent pairs recorded around tagged launches) ----
   bool prof_on = false;
@@ -202,12 +205,37 @@ int launch_colgemm(sirenb200_plan* p, const ColGemmJobs& jobs, cudaStream_t st) 
 }
 
 // ---------------------------------------------------------------------------------------
-// tensor-core path
+// tensor-core path.  The pixel rows are processed in chunks of `chunk_tiles` 128-row tiles: for each
+// chunk the whole layer chain runs forward and then backward before the next chunk starts, so the
+// activations / gradients of a chunk are re-read from L2 instead of HBM (the 126 MB L2 holds one
+// chunk's working set); weight-gradient partials accumulate across chunks.
 // ---------------------------------------------------------------------------------------
+struct Chunk {
+  int index;
+  int t0, ntiles;          // 128-row tiles
+  int64_t p0;              // first pixel
+  int64_t npix, npix_pad;  // valid / padded pixels of this chunk
+};
+
+std::vector<Chunk> make_chunks(const sirenb200_plan* p) {
+  std::vector<Chunk> v;
+  const int ct = p->chunk_tiles > 0 ? p->chunk_tiles : p->ntiles;
+  for (int t0 = 0, i = 0; t0 < p->ntiles; t0 += ct, ++i) {
+    Chunk c;
+    c.index = i;
+    c.t0 = t0;
+    c.ntiles = (t0 + ct <= p->ntiles) ? ct : p->ntiles - t0;
+    c.p0 = int64_t(t0) * kRowsPerTile;
+    c.npix_pad = int64_t(c.ntiles) * kRowsPerTile;
+    c.npix = (c.p0 + c.npix_pad <= p->npix) ? c.npix_pad : p->npix - c.p0;
+    v.push_back(c);
+  }
+  return v;
+}
+
 template <int W>
-int tc_forward(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* stats_to_zero) {
-  const int D = p->D;
-  const int nh = D - 2;  // hidden (W x W) layers
+int tc_prep(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* stats_to_zero) {
+  const int nh = p->D - 2;  // hidden (W x W) layers
   if (nh > 0) {
     PrepArgs pa{};
     for (int l = 1; l <= nh; ++l) {
@@ -227,22 +255,30 @@ int tc_forward(sirenb200_plan* p, const float* const* prm, cudaStream_t st, floa
   } else if (stats_to_zero) {
     CUDA_TRY(cudaMemsetAsync(stats_to_zero, 0, 4 * sizeof(float), st));
   }
+  return 0;
+}
+
+template <int W>
+int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
+  const int nh = p->D - 2;
   {
-    const int grid = p->nsm * 8;
-    {
-      ProfScope ps(p, PK_FIRST, st);
-      tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(p->coord, prm[0], prm[1], omega_of(p, 0), p->act,
-                                                    p->npix, p->npix_pad);
-    }
-    LAUNCH_CHECK();
+    int grid = p->nsm * 8;
+    const int need = cdiv(ch.npix_pad, 256 / (W / 8));
+    if (grid > need) grid = need;
+    CoordSrc cs = p->coord;
+    cs.p_offset = ch.p0;
+    ProfScope ps(p, PK_FIRST, st);
+    tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(cs, prm[0], prm[1], omega_of(p, 0),
+                                                  p->act + ch.p0 * W, ch.npix, ch.npix_pad);
   }
+  LAUNCH_CHECK();
   for (int l = 1; l <= nh; ++l) {
     RowGemmArgs ra{};
-    ra.num_tiles = p->ntiles;
-    ra.a_row0 = int((l - 1) * p->npix_pad);
+    ra.num_tiles = ch.ntiles;
+    ra.a_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.e_row0 = 0;
-    ra.o_row0 = int(l * p->npix_pad);
-    ra.valid_rows = int(p->npix);
+    ra.o_row0 = int(l * p->npix_pad + ch.p0);
+    ra.valid_rows = int(ch.npix);
     ra.omega = omega_of(p, l);
     ra.bias = prm[2 * l + 1];
     int rc = launch_rowgemm<W, MODE_FWD>(p, p->tm_act, p->tm_w[l - 1], p->tm_act, p->tm_act, ra, st);
@@ -252,21 +288,21 @@ int tc_forward(sirenb200_plan* p, const float* const* prm, cudaStream_t st, floa
 }
 
 template <int W>
-int tc_last(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
-            float* pred, cudaStream_t st) {
-  const int D = p->D;
+int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
+                  float* pred, const Chunk& ch, cudaStream_t st) {
+  const int D = p->D, C = p->C;
   LastArgs la{};
-  la.act = p->act + size_t(D - 2) * p->npix_pad * W;
-  la.dz = p->dz + size_t(D - 2) * p->npix_pad * W;
+  la.act = p->act + (size_t(D - 2) * p->npix_pad + ch.p0) * W;
+  la.dz = p->dz + (size_t(D - 2) * p->npix_pad + ch.p0) * W;
   la.w = prm[2 * (D - 1)];
   la.b = prm[2 * (D - 1) + 1];
-  la.img = img_or_dpred;
-  la.pred = pred;
-  la.part = p->last_part;
+  la.img = img_or_dpred ? img_or_dpred + ch.p0 * C : nullptr;
+  la.pred = pred ? pred + ch.p0 * C : nullptr;
+  la.part = p->last_part + size_t(ch.index) * p->last_grid * (C * W + C + 1);
   la.gscale = p->gstate;
-  la.npix = p->npix;
-  la.npix_pad = p->npix_pad;
-  la.C = p->C;
+  la.npix = ch.npix;
+  la.npix_pad = ch.npix_pad;
+  la.C = C;
   la.mode = mode;
   la.outermost_linear = p->cfg.outermost_linear;
   la.omega_last = omega_of(p, D - 1);
@@ -280,18 +316,16 @@ int tc_last(sirenb200_plan* p, const float* const* prm, int mode, const float* i
 }
 
 template <int W>
-int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads, float scale,
-                float* stats, cudaStream_t st) {
-  const int D = p->D, C = p->C;
-  const int nh = D - 2;
+int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
+  const int nh = p->D - 2;
   // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
   for (int l = nh; l >= 1; --l) {
     RowGemmArgs ra{};
-    ra.num_tiles = p->ntiles;
-    ra.a_row0 = int(l * p->npix_pad);
-    ra.e_row0 = int((l - 1) * p->npix_pad);
-    ra.o_row0 = int((l - 1) * p->npix_pad);
-    ra.valid_rows = int(p->npix);
+    ra.num_tiles = ch.ntiles;
+    ra.a_row0 = int(l * p->npix_pad + ch.p0);
+    ra.e_row0 = int((l - 1) * p->npix_pad + ch.p0);
+    ra.o_row0 = int((l - 1) * p->npix_pad + ch.p0);
+    ra.valid_rows = int(ch.npix);
     int rc = launch_rowgemm<W, MODE_DX>(p, p->tm_dz, p->tm_wt[l - 1], p->tm_act, p->tm_dz, ra, st);
     if (rc) return rc;
   }
@@ -301,8 +335,10 @@ int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads,
     jobs.num_problems = nh;
     jobs.mblocks = W / 128;
     jobs.splits = p->col_splits;
-    jobs.tiles_total = p->ntiles;
-    jobs.tiles_per_split = cdiv(p->ntiles, p->col_splits);
+    jobs.tile0 = ch.t0;
+    jobs.tiles_total = ch.ntiles;
+    jobs.tiles_per_split = cdiv(ch.ntiles, p->col_splits);
+    jobs.accumulate = ch.index > 0 ? 1 : 0;
     for (int l = 1; l <= nh; ++l) {
       jobs.x_row0[l - 1] = int(l * p->npix_pad);
       jobs.y_row0[l - 1] = int((l - 1) * p->npix_pad);
@@ -314,12 +350,23 @@ int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads,
     if (rc) return rc;
   }
   {
+    CoordSrc cs = p->coord;
+    cs.p_offset = ch.p0;
+    int grid = p->l0_grid;
     ProfScope ps(p, PK_L0_GRAD, st);
-    tc_layer0_grad_kernel<W><<<p->l0_grid, 256, 0, st>>>(p->coord, p->dz, p->l0_part, p->npix);
+    tc_layer0_grad_kernel<W><<<grid, 256, 0, st>>>(cs, p->dz + ch.p0 * W,
+                                                  p->l0_part + size_t(ch.index) * p->l0_grid * 3 * W,
+                                                  ch.npix);
   }
   LAUNCH_CHECK();
+  return 0;
+}
 
-  // reduce every partial buffer into the caller's gradient tensors
+// reduce every partial buffer into the caller's gradient tensors
+template <int W>
+int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats, int nchunks,
+              cudaStream_t st) {
+  const int D = p->D, C = p->C, nh = D - 2;
   ReduceArgs ra{};
   int nd = 0;
   auto add = [&](float* dst, const float* src, int n, int nsplit, int64_t stride) {
@@ -330,16 +377,16 @@ int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads,
     ra.d[nd].split_stride = stride;
     ++nd;
   };
-  add(grads[0], p->l0_part, 2 * W, p->l0_grid, 3 * W);
-  add(grads[1], p->l0_part + 2 * W, W, p->l0_grid, 3 * W);
+  add(grads[0], p->l0_part, 2 * W, p->l0_grid * nchunks, 3 * W);
+  add(grads[1], p->l0_part + 2 * W, W, p->l0_grid * nchunks, 3 * W);
   for (int l = 1; l <= nh; ++l) {
     add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, W * W, p->col_splits,
         int64_t(nh) * W * W);
     add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, W, p->col_splits, int64_t(nh) * W);
   }
   const int64_t lstride = int64_t(C) * W + C + 1;
-  add(grads[2 * (D - 1)], p->last_part, C * W, p->last_grid, lstride);
-  add(grads[2 * (D - 1) + 1], p->last_part + C * W, C, p->last_grid, lstride);
+  add(grads[2 * (D - 1)], p->last_part, C * W, p->last_grid * nchunks, lstride);
+  add(grads[2 * (D - 1) + 1], p->last_part + C * W, C, p->last_grid * nchunks, lstride);
   ra.ndesc = nd;
   int chunks = 0;
   for (int i = 0; i < nd; ++i) {
@@ -356,6 +403,23 @@ int tc_backward(sirenb200_plan* p, const float* const* prm, float* const* grads,
   }
   LAUNCH_CHECK();
   return 0;
+}
+
+// forward only (pred), forward + MSE + backward (mode 1), or backward from dpred (mode 2, no forward)
+template <int W>
+int tc_run(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
+           float* pred, float* const* grads, float scale, float* stats, cudaStream_t st) {
+  const std::vector<Chunk> chunks = make_chunks(p);
+  int rc = 0;
+  if (mode != 2) rc = tc_prep<W>(p, prm, st, mode == 1 ? stats : nullptr);
+  for (const Chunk& ch : chunks) {
+    if (rc) return rc;
+    if (mode != 2) rc = tc_forward_chunk<W>(p, prm, ch, st);
+    if (!rc) rc = tc_last_chunk<W>(p, prm, mode, img_or_dpred, pred, ch, st);
+    if (!rc && mode != 0) rc = tc_backward_chunk<W>(p, prm, ch, st);
+  }
+  if (!rc && mode != 0) rc = tc_reduce<W>(p, grads, scale, stats, int(chunks.size()), st);
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -603,15 +667,29 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     int splits = nh > 0 ? p->nsm / (nh * (W / 128)) : 1;
     if (splits < 1) splits = 1;
     if (splits > p->ntiles) splits = p->ntiles;
-    p->col_splits = splits;
+    p->col_splits = splits;  // (re-clamped to the chunk size below)
     ALLOC(p->dw_part, int64_t(splits) * (nh > 0 ? nh : 1) * W * W);
     ALLOC(p->db_part, int64_t(splits) * (nh > 0 ? nh : 1) * W);
+    {
+      // Row chunking (forward+backward per chunk so a chunk's stash is re-read from L2) is OFF by
+      // default: measured on B200 at config 2 it loses (1.56 ms/step unchunked vs 2.0 ms with two
+      // chunks, 5.9 ms with 21) because every tcgen05 kernel launch pays ~10 us of fixed cost (TMEM
+      // alloc, 128 KB weight load, pipeline fill/drain).  SIRENB200_CHUNK_TILES=<n> enables it.
+      int ct = 0;
+      const char* env = getenv("SIRENB200_CHUNK_TILES");
+      if (env) ct = atoi(env);
+      if (ct <= 0 || ct >= p->ntiles) ct = p->ntiles;
+      p->chunk_tiles = ct;
+      p->nchunks = cdiv(p->ntiles, ct);
+    }
+    if (p->col_splits > p->chunk_tiles) p->col_splits = p->chunk_tiles;
+    const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
     p->last_grid = p->nsm * 2;
-    if (p->last_grid * 8 > p->npix_pad) p->last_grid = cdiv(p->npix_pad, 8);
-    ALLOC(p->last_part, int64_t(p->last_grid) * (C * W + C + 1));
+    if (int64_t(p->last_grid) * 8 > chunk_pad) p->last_grid = cdiv(chunk_pad, 8);
+    ALLOC(p->last_part, int64_t(p->nchunks) * p->last_grid * (C * W + C + 1));
     p->l0_grid = p->nsm * 4;
-    if (p->l0_grid > p->ntiles) p->l0_grid = p->ntiles;
-    ALLOC(p->l0_part, int64_t(p->l0_grid) * 3 * W);
+    if (p->l0_grid > p->chunk_tiles) p->l0_grid = p->chunk_tiles;
+    ALLOC(p->l0_part, int64_t(p->nchunks) * p->l0_grid * 3 * W);
     cudaError_t e = cudaMemset(p->dz, 0, size_t(D - 1) * p->npix_pad * W * sizeof(__half));
     if (e == cudaSuccess) e = cudaMemset(p->act, 0, size_t(D - 1) * p->npix_pad * W * sizeof(__half));
     if (e != cudaSuccess) {
@@ -702,11 +780,9 @@ int sirenb200_forward(sirenb200_handle_t h, const float* const* prm, float* pred
   if (h->cfg.precision == SIRENB200_PREC_FP32) {
     rc = f32_forward(h, prm, 0, nullptr, pred, st);
   } else if (h->W == 256) {
-    rc = tc_forward<256>(h, prm, st, nullptr);
-    if (!rc) rc = tc_last<256>(h, prm, 0, nullptr, pred, st);
+    rc = tc_run<256>(h, prm, 0, nullptr, pred, nullptr, 0.f, nullptr, st);
   } else {
-    rc = tc_forward<128>(h, prm, st, nullptr);
-    if (!rc) rc = tc_last<128>(h, prm, 0, nullptr, pred, st);
+    rc = tc_run<128>(h, prm, 0, nullptr, pred, nullptr, 0.f, nullptr, st);
   }
   h->have_fwd = (rc == 0);
   return rc;
@@ -725,19 +801,11 @@ int sirenb200_forward_backward(sirenb200_handle_t h, const float* const* prm, co
     rc = f32_forward(h, prm, 1, img, nullptr, st);
     if (!rc) rc = f32_backward(h, prm, grads, scale, stats, st);
     if (!rc) rc = finalize(h, h->loss_part, 256, 1, stats, false, st);
-  } else if (h->W == 256) {
-    rc = tc_forward<256>(h, prm, st, stats);
-    if (!rc) rc = tc_last<256>(h, prm, 1, img, nullptr, st);
-    if (!rc) rc = tc_backward<256>(h, prm, grads, scale, stats, st);
-    if (!rc)
-      rc = finalize(h, h->last_part + h->C * h->W + h->C, h->last_grid,
-                    int64_t(h->C) * h->W + h->C + 1, stats, true, st);
   } else {
-    rc = tc_forward<128>(h, prm, st, stats);
-    if (!rc) rc = tc_last<128>(h, prm, 1, img, nullptr, st);
-    if (!rc) rc = tc_backward<128>(h, prm, grads, scale, stats, st);
+    rc = (h->W == 256) ? tc_run<256>(h, prm, 1, img, nullptr, grads, scale, stats, st)
+                       : tc_run<128>(h, prm, 1, img, nullptr, grads, scale, stats, st);
     if (!rc)
-      rc = finalize(h, h->last_part + h->C * h->W + h->C, h->last_grid,
+      rc = finalize(h, h->last_part + h->C * h->W + h->C, h->last_grid * h->nchunks,
                     int64_t(h->C) * h->W + h->C + 1, stats, true, st);
   }
   h->have_fwd = (rc == 0);
@@ -769,13 +837,8 @@ int sirenb200_backward(sirenb200_handle_t h, const float* const* prm, const floa
   } else {
     absmax_scale_kernel<<<1, 1024, 0, st>>>(dpred, h->npix * h->C, h->gstate);
     LAUNCH_CHECK();
-    if (h->W == 256) {
-      rc = tc_last<256>(h, prm, 2, dpred, nullptr, st);
-      if (!rc) rc = tc_backward<256>(h, prm, grads, 1.0f, stats, st);
-    } else {
-      rc = tc_last<128>(h, prm, 2, dpred, nullptr, st);
-      if (!rc) rc = tc_backward<128>(h, prm, grads, 1.0f, stats, st);
-    }
+    rc = (h->W == 256) ? tc_run<256>(h, prm, 2, dpred, nullptr, grads, 1.0f, stats, st)
+                       : tc_run<128>(h, prm, 2, dpred, nullptr, grads, 1.0f, stats, st);
   }
   return rc;
 }

@@ -329,8 +329,10 @@ struct ColGemmJobs {
   int num_problems;     // e.g. hidden layers 1..D-2
   int mblocks;          // output row blocks per problem (NX / 128)
   int splits;           // pixel splits per (problem, mblock)
+  int tile0;            // first 128-pixel tile of this launch (row chunks)
   int tiles_total;      // 128-pixel tiles in the launch's row range
   int tiles_per_split;  // ceil(tiles_total / splits)
+  int accumulate;       // add to the existing partials instead of overwriting them
   int x_row0[8];        // first row of problem p in the X (dZ) tensor map
   int y_row0[8];        // first row of problem p in the Y (activation) tensor map
   float* dw_partial;    // [splits][num_problems][NX][NY] fp32
@@ -393,7 +395,7 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       for (int i = 0; i < ntiles; ++i) {
         const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
-        const int prow = (tile_begin + i) * kRowsPerTile;
+        const int prow = (jobs.tile0 + tile_begin + i) * kRowsPerTile;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], C::STAGE_BYTES);
         uint8_t* st = smem + s * C::STAGE_BYTES;
@@ -441,15 +443,25 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + cb * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<uint4*>(dw + cb * 32)[j] =
-              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          float4* dst = reinterpret_cast<float4*>(dw + cb * 32) + j;
+          if (jobs.accumulate) {
+            const float4 old = *dst;
+            o.x += old.x;
+            o.y += old.y;
+            o.z += old.z;
+            o.w += old.w;
+          }
+          *dst = o;
+        }
       }
       uint32_t b8[8];
       tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + NY, b8);
       tmem_ld_wait();
-      *dbp = __uint_as_float(b8[0]);
-    } else {
+      *dbp = __uint_as_float(b8[0]) + (jobs.accumulate ? *dbp : 0.f);
+    } else if (!jobs.accumulate) {
       for (int j = 0; j < NY / 4; ++j) reinterpret_cast<uint4*>(dw)[j] = make_uint4(0, 0, 0, 0);
       *dbp = 0.0f;
     }
