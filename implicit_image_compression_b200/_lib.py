@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = [
     "sirenb200_forward", "sirenb200_forward_backward", "sirenb200_backward", "sirenb200_eval_metrics",
     "sirenb200_adam_step", "sirenb200_apply_mask", "sirenb200_kmeans_quantize",
     "sirenb200_fakequant_per_channel", "sirenb200_launch_count", "sirenb200_profile_enable",
-    "sirenb200_profile_read",
+    "sirenb200_profile_read", "sirenb200_debug_timeline",
 ]
 
 PROFILE_KINDS = ["weight_staging", "first_layer", "fwd_gemm", "last_layer_loss", "dx_gemm", "dw_gemm",
@@ -74,6 +74,7 @@ def load():
                                               vp, vp]
     lib.sirenb200_fakequant_per_channel.argtypes = [vp, c_int32, c_int32, vp, vp, c_float, c_float, vp, vp,
                                                     vp, vp]
+    lib.sirenb200_debug_timeline.argtypes = [vp, POINTER(c_int64), c_int32]
     lib.sirenb200_profile_enable.argtypes = [vp, c_int32]
     lib.sirenb200_profile_read.argtypes = [vp, POINTER(c_float), POINTER(c_int32), c_int32]
     _lib = lib

@@ -269,18 +269,19 @@ struct LastArgs {
   float omega_prev;      // omega of the layer that produced `act`
 };
 
-template <int W>
+// CT = compile-time bound on the output channels (3 for RGB; 4 = generic up to CT)
+template <int W, int CT>
 __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
   constexpr int NCH = (W + 255) / 256;            // 8-column chunks per lane
   constexpr int ACTIVE = (W / 8) < 32 ? (W / 8) : 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool on = lane < ACTIVE;
-  float wr[kMaxOut][NCH * 8];
-  float dwacc[kMaxOut][NCH * 8];
-  float dbacc[kMaxOut] = {};
+  float wr[CT][NCH * 8];
+  float dwacc[CT][NCH * 8];
+  float dbacc[CT] = {};
   float lsum = 0.f;
 #pragma unroll
-  for (int cc = 0; cc < kMaxOut; ++cc)
+  for (int cc = 0; cc < CT; ++cc)
 #pragma unroll
     for (int j = 0; j < NCH * 8; ++j) {
       const int col = (j / 8) * 256 + lane * 8 + (j % 8);
@@ -292,16 +293,19 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
   // software pipeline: the activation rows of the next PF iterations are already in flight
   constexpr int PF = 3;
   uint4 q[PF][NCH];
-  auto fetch = [&](int64_t row, uint4 (&dst)[NCH]) {
+  float qi[PF];  // lane cc < C prefetches img[row, cc] (target or upstream gradient)
+  auto fetch = [&](int64_t row, uint4 (&dst)[NCH], float& dimg) {
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       dst[ch] = make_uint4(0, 0, 0, 0);
       if (on && row < a.npix) dst[ch] = reinterpret_cast<const uint4*>(a.act + row * W)[ch * 32 + lane];
     }
+    dimg = 0.f;
+    if (a.mode != 0 && lane < a.C && row < a.npix) dimg = a.img[row * a.C + lane];
   };
   const int64_t pstart = int64_t(blockIdx.x) * 8 + warp;
 #pragma unroll
-  for (int i = 0; i < PF; ++i) fetch(pstart + i * nwarps, q[i]);
+  for (int i = 0; i < PF; ++i) fetch(pstart + i * nwarps, q[i], qi[i]);
   for (int64_t p = pstart; p < a.npix_pad; p += nwarps) {
     uint32_t raw[NCH * 4];
 #pragma unroll
@@ -311,11 +315,14 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
       raw[ch * 4 + 2] = q[0][ch].z;
       raw[ch * 4 + 3] = q[0][ch].w;
     }
+    const float img_lane = qi[0];
 #pragma unroll
-    for (int i = 0; i + 1 < PF; ++i)
+    for (int i = 0; i + 1 < PF; ++i) {
+      qi[i] = qi[i + 1];
 #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) q[i][ch] = q[i + 1][ch];
-    fetch(p + PF * nwarps, q[PF - 1]);
+    }
+    fetch(p + PF * nwarps, q[PF - 1], qi[PF - 1]);
     if (p >= a.npix) {  // padding rows: zero gradient so the dW reduction ignores them
       if (a.mode != 0 && on)
 #pragma unroll
@@ -330,9 +337,9 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
       av[2 * j] = f.x;
       av[2 * j + 1] = f.y;
     }
-    float y[kMaxOut];
+    float y[CT];
 #pragma unroll
-    for (int cc = 0; cc < kMaxOut; ++cc) {
+    for (int cc = 0; cc < CT; ++cc) {
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < NCH * 8; ++j) s = fmaf(av[j], wr[cc][j], s);
@@ -340,28 +347,29 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       y[cc] = s;
     }
-    float g[kMaxOut];
+    float g[CT];
 #pragma unroll
-    for (int cc = 0; cc < kMaxOut; ++cc) {
+    for (int cc = 0; cc < CT; ++cc) {
       g[cc] = 0.f;
       if (cc < a.C) {
         const float z = y[cc] + a.b[cc];
         const float o = a.outermost_linear ? z : sinf(z * a.omega_last);
         const float pred = o / 2 + 0.5f;
         if (a.pred && lane == cc) a.pred[p * a.C + cc] = pred;
+        const float tgt = __shfl_sync(0xffffffffu, img_lane, cc);
         if (a.mode == 1) {
-          const float d = pred - a.img[p * a.C + cc];
+          const float d = pred - tgt;
           if (lane == 0) lsum += d * d;
           g[cc] = d * G;
         } else if (a.mode == 2) {
-          g[cc] = 0.5f * a.img[p * a.C + cc] * G;
+          g[cc] = 0.5f * tgt * G;
         }
         if (!a.outermost_linear) g[cc] *= a.omega_last * cosf(z * a.omega_last);
       }
     }
     if (a.mode != 0) {
 #pragma unroll
-      for (int cc = 0; cc < kMaxOut; ++cc) {
+      for (int cc = 0; cc < CT; ++cc) {
         if (lane == 0) dbacc[cc] += g[cc];
 #pragma unroll
         for (int j = 0; j < NCH * 8; ++j) dwacc[cc][j] = fmaf(g[cc], av[j], dwacc[cc][j]);
@@ -373,7 +381,7 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
         for (int j2 = 0; j2 < 4; ++j2) {
           float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < kMaxOut; ++cc) {
+          for (int cc = 0; cc < CT; ++cc) {
             d0 = fmaf(g[cc], wr[cc][ch * 8 + 2 * j2], d0);
             d1 = fmaf(g[cc], wr[cc][ch * 8 + 2 * j2 + 1], d1);
           }
@@ -390,18 +398,18 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
   }
   if (a.mode == 0) return;
   // block reduction of the per-warp partial sums (8 warps) through shared memory
-  __shared__ float red[8][kMaxOut + 1];
-  __shared__ float buf[8][32][kMaxOut];
+  __shared__ float red[8][CT + 1];
+  __shared__ float buf[8][32][CT];
   float* out = a.part + int64_t(blockIdx.x) * (a.C * W + a.C + 1);
 #pragma unroll
   for (int j = 0; j < NCH * 8; ++j) {
     __syncthreads();
 #pragma unroll
-    for (int cc = 0; cc < kMaxOut; ++cc) buf[warp][lane][cc] = dwacc[cc][j];
+    for (int cc = 0; cc < CT; ++cc) buf[warp][lane][cc] = dwacc[cc][j];
     __syncthreads();
     if (warp == 0 && on) {
 #pragma unroll
-      for (int cc = 0; cc < kMaxOut; ++cc) {
+      for (int cc = 0; cc < CT; ++cc) {
         if (cc < a.C) {
           float s = 0.f;
           for (int w8 = 0; w8 < 8; ++w8) s += buf[w8][lane][cc];
@@ -414,12 +422,12 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int cc = 0; cc < kMaxOut; ++cc) red[warp][cc] = dbacc[cc];
-    red[warp][kMaxOut] = lsum;
+    for (int cc = 0; cc < CT; ++cc) red[warp][cc] = dbacc[cc];
+    red[warp][CT] = lsum;
   }
   __syncthreads();
   if (threadIdx.x <= a.C) {
-    const int idx = threadIdx.x < a.C ? threadIdx.x : kMaxOut;
+    const int idx = threadIdx.x < a.C ? threadIdx.x : CT;
     float s = 0.f;
     for (int w8 = 0; w8 < 8; ++w8) s += red[w8][idx];
     out[a.C * W + threadIdx.x] = s;  // db[0..C-1], then sum of squared error
@@ -434,7 +442,7 @@ __global__ void __launch_bounds__(256) tc_layer0_grad_kernel(CoordSrc c, const _
                                                              float* __restrict__ part, int64_t npix) {
   constexpr int TPR = W / 8;      // threads per row (8 columns = 16 bytes each)
   constexpr int RL = 256 / TPR;   // row lanes
-  constexpr int UN = 4;           // rows in flight per thread
+  constexpr int UN = 8;           // rows in flight per thread
   const int tc = threadIdx.x % TPR, tr = threadIdx.x / TPR;
   const int64_t per_block = (npix + gridDim.x - 1) / gridDim.x;
   const int64_t p0 = blockIdx.x * per_block;
@@ -502,6 +510,14 @@ struct PrepArgs {
   __half* wh;   // [nlayers][W][W]
   __half* wth;  // [nlayers][W][W]
   float* stats; // zeroed here (start of a step); may be null
+  // epilogue constants of the fused forward kernel
+  const float* bias[kMaxLayers];  // hidden-layer biases
+  const float* w0;                // layer 0 weight [W, 2] and bias [W]
+  const float* b0;
+  float omega0, omega_h;
+  float4* tab0;                   // [W] (omega0*w_h, omega0*w_w, omega0*b0, 0)
+  float* bias_w;                  // [nlayers][W] omega_h * bias
+  float* bias_raw;                // [nlayers][W] bias
 };
 __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const PrepArgs a) {
   __shared__ float tile[32][33];
@@ -510,6 +526,14 @@ __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const PrepArgs a) 
   const int l = blockIdx.z;
   const float* w = a.w[l];
   const int W = a.W;
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int i = threadIdx.x; i < W; i += 256) {
+      a.bias_w[l * W + i] = a.omega_h * a.bias[l][i];
+      a.bias_raw[l * W + i] = a.bias[l][i];
+      if (l == 0)
+        a.tab0[i] = make_float4(a.omega0 * a.w0[2 * i], a.omega0 * a.w0[2 * i + 1], a.omega0 * a.b0[i], 0.f);
+    }
+  }
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int r = ty; r < 32; r += 8) {

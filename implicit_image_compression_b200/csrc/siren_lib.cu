@@ -85,7 +85,12 @@ struct sirenb200_plan {
   __half* dz = nullptr;   // [(D-1)][npix_pad, W] fp16 gradients (seed units)
   __half* wh = nullptr;   // [(D-2)][W, W]
   __half* wth = nullptr;  // [(D-2)][W, W]
-  CUtensorMap tm_act{}, tm_dz{};
+  float4* tab0 = nullptr; // [W] layer-0 epilogue table (fused forward)
+  float* bias_w = nullptr;  // [(D-2)][W] omega * bias
+  float* bias_raw = nullptr;  // [(D-2)][W] bias (contiguous copy for the fused forward)
+  CUtensorMap tm_act{}, tm_dz{}, tm_wstack{};
+  bool fused_fwd = false;
+  long long* dbg_timeline = nullptr;  // SIRENB200_TIMELINE=1: 3*4*8*16 clock64 slots (debug)
   std::vector<CUtensorMap> tm_w, tm_wt;
   float* dw_part = nullptr;  // [splits][D-2][W][W]
   float* db_part = nullptr;  // [splits][D-2][W]
@@ -247,6 +252,14 @@ int tc_prep(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* 
     pa.wh = p->wh;
     pa.wth = p->wth;
     pa.stats = stats_to_zero;
+    for (int l = 1; l <= nh; ++l) pa.bias[l - 1] = prm[2 * l + 1];
+    pa.w0 = prm[0];
+    pa.b0 = prm[1];
+    pa.omega0 = omega_of(p, 0);
+    pa.omega_h = p->cfg.hidden_omega;
+    pa.tab0 = p->tab0;
+    pa.bias_w = p->bias_w;
+    pa.bias_raw = p->bias_raw;
     {
       ProfScope ps(p, PK_PREP, st);
       tc_prep_weights_kernel<<<dim3(W / 32, W / 32, nh), 256, 0, st>>>(pa);
@@ -259,8 +272,48 @@ int tc_prep(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* 
 }
 
 template <int W>
+int launch_fused_fwd(sirenb200_plan* p, const Chunk& ch, cudaStream_t st) {
+  if constexpr (W == 256) {
+    using Cfg = FusedFwdCfg<W>;
+    auto kfn = fused_fwd_kernel<W>;
+    static bool attr_set[64] = {};
+    if (!attr_set[p->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(Cfg::SMEM_BYTES)));
+      attr_set[p->device & 63] = true;
+    }
+    FusedFwdArgs fa{};
+    fa.num_tiles = ch.ntiles;
+    fa.nh = p->D - 2;
+    fa.npix = ch.npix;
+    fa.npix_pad = p->npix_pad;
+    fa.tab0 = p->tab0;
+    fa.bias_w = p->bias_w;
+    fa.bias_raw = p->bias_raw;
+    fa.omega = p->cfg.hidden_omega;
+    fa.lin_h = p->coord.lin_h;
+    fa.lin_w = p->coord.lin_w;
+    fa.coords = p->coord.coords;
+    fa.width = p->coord.width;
+    fa.row_begin = p->coord.row_begin;
+    fa.dbg = p->dbg_timeline;
+    const int grid = ch.ntiles < p->nsm ? ch.ntiles : p->nsm;
+    {
+      ProfScope ps(p, PK_FWD_GEMM, st);
+      kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p->tm_wstack, p->tm_act, fa,
+                                                      umma_idesc(128, W, 0, 0, 0, 0));
+    }
+    LAUNCH_CHECK();
+    return 0;
+  } else {
+    return fail(SIRENB200_ERR_INVALID, "fused forward needs hidden = 256");
+  }
+}
+
+template <int W>
 int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
   const int nh = p->D - 2;
+  if (p->fused_fwd && ch.index == 0 && p->nchunks == 1) return launch_fused_fwd<W>(p, ch, st);
   {
     int grid = p->nsm * 8;
     const int need = cdiv(ch.npix_pad, 256 / (W / 8));
@@ -309,7 +362,10 @@ int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const fl
   la.omega_prev = omega_of(p, D - 2);
   {
     ProfScope ps(p, PK_LAST, st);
-    tc_last_layer_kernel<W><<<p->last_grid, 256, 0, st>>>(la);
+    if (C == 3)
+      tc_last_layer_kernel<W, 3><<<p->last_grid, 256, 0, st>>>(la);
+    else
+      tc_last_layer_kernel<W, kMaxOut><<<p->last_grid, 256, 0, st>>>(la);
   }
   LAUNCH_CHECK();
   return 0;
@@ -664,6 +720,9 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     ALLOC(p->dz, int64_t(D - 1) * p->npix_pad * W);
     ALLOC(p->wh, int64_t(nh > 0 ? nh : 1) * W * W);
     ALLOC(p->wth, int64_t(nh > 0 ? nh : 1) * W * W);
+    ALLOC(p->tab0, W);
+    ALLOC(p->bias_w, int64_t(nh > 0 ? nh : 1) * W);
+    ALLOC(p->bias_raw, int64_t(nh > 0 ? nh : 1) * W);
     int splits = nh > 0 ? p->nsm / (nh * (W / 128)) : 1;
     if (splits < 1) splits = 1;
     if (splits > p->ntiles) splits = p->ntiles;
@@ -704,9 +763,22 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       trc |= make_tmap_16bit(&p->tm_w[l], p->wh + size_t(l) * W * W, W, W, W, false);
       trc |= make_tmap_16bit(&p->tm_wt[l], p->wth + size_t(l) * W * W, W, W, W, false);
     }
+    if (nh > 0) trc |= make_tmap_16bit(&p->tm_wstack, p->wh, uint64_t(nh) * W, W, W, false);
     if (trc) {
       sirenb200_destroy(p);
       return fail(SIRENB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", trc);
+    }
+    if (getenv("SIRENB200_TIMELINE")) {
+      ALLOC(p->dbg_timeline, 3 * 4 * 8 * 16);
+      cudaMemset(p->dbg_timeline, 0, 3 * 4 * 8 * 16 * sizeof(long long));
+    }
+    {
+      // The fused multi-layer forward (tc_kernels.cuh: fused_fwd_kernel) is correct (same tests pass)
+      // but measured SLOWER than the per-layer kernels at config 2 (0.39-0.47 ms vs 0.38 ms): with one
+      // CTA per SM its sin epilogue (~3500-4400 cycles per 128x256 tile-layer, MUFU + issue bound) does
+      // not overlap the MMAs well and the 3-stage weight ring starves.  Opt-in until the 2-CTA version.
+      const char* env = getenv("SIRENB200_FUSED_FWD");
+      p->fused_fwd = (W == 256 && nh > 0) && (env && atoi(env) != 0);
     }
   }
 #undef ALLOC
@@ -719,7 +791,7 @@ int sirenb200_destroy(sirenb200_handle_t p) {
   void* ptrs[] = {p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
                   p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
                   p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
-                  p->l0_part};
+                  p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
@@ -728,6 +800,12 @@ int sirenb200_destroy(sirenb200_handle_t p) {
 }
 
 int64_t sirenb200_workspace_bytes(sirenb200_handle_t h) { return h ? h->bytes : 0; }
+
+int sirenb200_debug_timeline(sirenb200_handle_t h, long long* h_out, int32_t n) {
+  if (!h || !h->dbg_timeline) return fail(SIRENB200_ERR_STATE, "timeline capture not enabled");
+  CUDA_TRY(cudaMemcpy(h_out, h->dbg_timeline, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 int sirenb200_profile_enable(sirenb200_handle_t h, int32_t enable) {
   if (!h) return fail(SIRENB200_ERR_INVALID, "null handle");

@@ -475,4 +475,331 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// fused forward: layer 0 (CUDA cores, in-kernel coordinates) + every hidden layer (tcgen05) for one
+// 128-pixel tile at a time, activations never leave the SM between layers.
+//
+//   smem : two 64 KiB activation buffers (K-major SW128, the epilogue's output tile of layer l IS the
+//          A operand of layer l+1 and the source of the TMA store that stashes it for the backward
+//          pass) + a 3-stage ring of 32 KiB weight k-blocks streamed from L2 by TMA.
+//   TMEM : two 128 x W fp32 accumulators (layer l drains while layer l+1 accumulates).
+//   MMA order is K-outer: layer l+1 starts on k-block c as soon as the epilogue of layer l has written
+//   column chunk c, so the tensor pipe trails the (MUFU-bound) epilogue by one chunk.
+// ------------------------------------------------------------------------------------------
+struct FusedFwdArgs {
+  int num_tiles;
+  int nh;                  // hidden (W x W) layers: 1 .. nh
+  int64_t npix;            // valid pixels of this launch
+  int64_t npix_pad;        // rows per layer inside the activation stack
+  const float4* tab0;      // [W] (omega0*w_h, omega0*w_w, omega0*b, 0) of layer 0
+  const float* bias_w;     // [nh][W] omega * bias of the hidden layers (unused by the fused kernel)
+  const float* bias_raw;   // [nh][W] bias of the hidden layers: the accumulators are INITIALISED with it
+  float omega;             // hidden omega
+  // coordinates (see CoordSrc)
+  const float* lin_h;
+  const float* lin_w;
+  const float* coords;
+  int width;
+  int row_begin;
+  long long* dbg;          // optional timeline capture (tools/fused_timeline.py); null in production
+};
+
+// timeline slots: dbg[((role * 4 + tile) * 8 + layer) * 16 + k], block 0 only, first 4 tiles
+#define SB_DBG(role, tile_i, layer, k)                                                        \
+  do {                                                                                        \
+    if (args.dbg && blockIdx.x == 0 && (tile_i) < 4)                                          \
+      args.dbg[(((role) * 4 + (tile_i)) * 8 + (layer)) * 16 + (k)] = clock64();               \
+  } while (0)
+
+template <int W>
+struct FusedFwdCfg {
+  static_assert(W == 256, "fused forward is instantiated for hidden = 256");
+  static constexpr int KB = W / 64;
+  static constexpr int SW = 3;  // weight ring depth
+  static constexpr uint32_t A_BUF = 128 * W * 2;      // 64 KiB
+  static constexpr uint32_t W_STAGE = W * 128;        // 32 KiB: [W rows x 64 K]
+  static constexpr uint32_t OFF_A = 0;
+  static constexpr uint32_t OFF_W = 2 * A_BUF;
+  static constexpr uint32_t OFF_BAR = OFF_W + SW * W_STAGE;
+  // w_full/empty[SW], chunk_done[2][KB], region_free[2][KB], acc_full[2], acc_empty[2]
+  static constexpr int NUM_BARS = 2 * SW + 4 * KB + 4;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr int THREADS = 640;  // warp 0 W-TMA, warp 1 MMA, warp 2 stash stores, warps 4-19 epilogue
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
+};
+
+// Epilogue warp layout: warps 4..19; quadrant q = warp & 3 owns TMEM lanes / tile rows [32q, 32q+32),
+// chunk c = (warp-4)>>2 is the 64-column slice this warp produces in every layer.  All four chunks of a
+// layer are produced concurrently (4 epilogue warps per SM sub-partition hide MUFU / TMEM latency) and
+// no block-wide barrier is needed: each warp arrives on chunk_done[buf][c] (count 4), which the MMA
+// issuer and the store thread wait on.
+template <int W>
+__global__ void __launch_bounds__(640, 1)
+fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmAct,
+                 const FusedFwdArgs args, const uint32_t idesc) {
+  using C = FusedFwdCfg<W>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* w_full = bars;
+  uint64_t* w_empty = w_full + C::SW;
+  uint64_t* chunk_done = w_empty + C::SW;          // [2][KB], 4 arrivals (one per quadrant warp)
+  uint64_t* region_free = chunk_done + 2 * C::KB;  // [2][KB], 1 arrival (store thread)
+  uint64_t* acc_full = region_free + 2 * C::KB;    // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::SW; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2 * C::KB; ++i) {
+      mbar_init(&chunk_done[i], 4);
+      mbar_init(&region_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 16);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmAct);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nh = args.nh;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t iw = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x)
+        for (int l = 1; l <= nh; ++l)
+          for (int kb = 0; kb < C::KB; ++kb, ++iw) {
+            const uint32_t s = iw % C::SW, ph = (iw / C::SW) & 1u;
+            mbar_wait(&w_empty[s], ph ^ 1u);
+            mbar_expect_tx(&w_full[s], C::W_STAGE);
+            tma_load_2d(smem + C::OFF_W + s * C::W_STAGE, &tmW, &w_full[s], kb * 64, (l - 1) * W);
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t iw = 0;
+      uint32_t use_acc0 = 0, use_acc1 = 0;  // completed uses of each accumulator
+      uint32_t use_buf0 = 0, use_buf1 = 0;  // write phases of each activation buffer accounted for
+      int ti = -1;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+        ++ti;
+        if (t != int(blockIdx.x)) {
+          // layer nh of the previous tile is not consumed by any MMA, but its chunk_done phases must
+          // still be observed: a parity wait may never run two phases ahead of the barrier
+          const uint32_t lb = nh & 1u;
+          const uint32_t ul = lb ? use_buf1 : use_buf0;
+          for (int kb = 0; kb < C::KB; ++kb) mbar_wait(&chunk_done[lb * C::KB + kb], ul & 1u);
+          if (lb) ++use_buf1; else ++use_buf0;
+        }
+        for (int l = 1; l <= nh; ++l) {
+          const uint32_t acc = l & 1u, src = (l - 1) & 1u;
+          const uint32_t ua = acc ? use_acc1 : use_acc0;
+          const uint32_t ub = src ? use_buf1 : use_buf0;
+          SB_DBG(0, ti, l, 0);
+          mbar_wait(&acc_empty[acc], ua & 1u);  // phase 0 = initial bias fill, then one per drain
+          SB_DBG(0, ti, l, 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * W;
+          for (int kb = 0; kb < C::KB; ++kb, ++iw) {
+            const uint32_t s = iw % C::SW, ph = (iw / C::SW) & 1u;
+            mbar_wait(&chunk_done[src * C::KB + kb], ub & 1u);
+            SB_DBG(0, ti, l, 2 + 2 * kb);
+            mbar_wait(&w_full[s], ph);
+            SB_DBG(0, ti, l, 3 + 2 * kb);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + C::OFF_A + src * C::A_BUF + kb * kChunkBytes);
+            const uint32_t b_addr = smem_u32(smem + C::OFF_W + s * C::W_STAGE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_smem_desc(a_addr + k * 32, 0, 1024, 2);
+              const uint64_t db = umma_smem_desc(b_addr + k * 32, 0, 1024, 2);
+              umma_f16(d_tmem, da, db, idesc, 1u);  // accumulator starts at the bias
+            }
+            umma_commit(&w_empty[s]);
+          }
+          umma_commit(&acc_full[acc]);
+          SB_DBG(0, ti, l, 10);
+          if (acc) ++use_acc1; else ++use_acc0;
+          if (src) ++use_buf1; else ++use_buf0;
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== stash stores: activation chunk -> HBM, then free the region ==========
+    if (lane == 0) {
+      uint32_t use_buf0 = 0, use_buf1 = 0;
+      int pend_buf[2] = {-1, -1}, pend_c[2] = {0, 0};  // stores whose smem read may be in flight
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+        const int tile_row = t * kRowsPerTile;
+        for (int l = 0; l <= nh; ++l) {
+          const uint32_t buf = l & 1u;
+          const uint32_t ub = buf ? use_buf1 : use_buf0;
+          for (int c = 0; c < C::KB; ++c) {
+            mbar_wait(&chunk_done[buf * C::KB + c], ub & 1u);
+            tma_store_2d(&tmAct, smem + C::OFF_A + buf * C::A_BUF + c * kChunkBytes, c * 64,
+                         int(l * args.npix_pad) + tile_row);
+            tma_store_commit();
+            // keep two stores in flight; the one issued two chunks ago has been read out of smem
+            tma_store_wait_read<2>();
+            if (pend_buf[0] >= 0) mbar_arrive(&region_free[pend_buf[0] * C::KB + pend_c[0]]);
+            pend_buf[0] = pend_buf[1];
+            pend_c[0] = pend_c[1];
+            pend_buf[1] = int(buf);
+            pend_c[1] = c;
+          }
+          if (buf) ++use_buf1; else ++use_buf0;
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int c = (warp - 4) >> 2;  // this warp's 64-column chunk
+    const int r_in_tile = q * 32 + lane;
+    uint32_t use_acc0 = 0, use_acc1 = 0, use_buf0 = 0, use_buf1 = 0;
+    // Bias folding: every accumulator is pre-loaded with the bias of the layer that will use it next
+    // (each warp fills the lanes x columns it later drains), so the MMAs always accumulate and the
+    // epilogue needs no per-column constant.  Initial fill: acc 1 <- bias of layer 1, acc 0 <- layer 2.
+    auto fill_bias = [&](uint32_t acc_idx, int layer, int col0) {
+      uint32_t bv[32];
+      const float4* src = reinterpret_cast<const float4*>(args.bias_raw + (layer - 1) * W + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 f = __ldg(src + j);
+        bv[4 * j] = __float_as_uint(f.x);
+        bv[4 * j + 1] = __float_as_uint(f.y);
+        bv[4 * j + 2] = __float_as_uint(f.z);
+        bv[4 * j + 3] = __float_as_uint(f.w);
+      }
+      tmem_st_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc_idx * W + col0, bv);
+    };
+    for (int hb = 0; hb < 2; ++hb) {
+      fill_bias(1, 1, c * 64 + hb * 32);
+      if (nh >= 2) fill_bias(0, 2, c * 64 + hb * 32);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {  // both accumulators are ready for their first use
+      mbar_arrive(&acc_empty[1]);
+      mbar_arrive(&acc_empty[0]);
+    }
+    const int role = (lane == 0 && q == 0 && (c == 0 || c == 3)) ? (c == 0 ? 1 : 2) : -1;
+    int ti = -1;
+    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      ++ti;
+      const int tile_row = t * kRowsPerTile;
+      float xh, xw;
+      {
+        int64_t p = int64_t(tile_row) + r_in_tile;
+        if (p >= args.npix) p = args.npix - 1;
+        float gh, gw;
+        if (args.coords) {
+          const float2 v = reinterpret_cast<const float2*>(args.coords)[p];
+          gh = v.x;
+          gw = v.y;
+        } else {
+          const unsigned pu = unsigned(p);
+          const int r = int(pu / unsigned(args.width));
+          const int col = int(pu - unsigned(r) * unsigned(args.width));
+          gh = __ldg(args.lin_h + args.row_begin + r);
+          gw = __ldg(args.lin_w + col);
+        }
+        xh = (gh - 0.5f) * 2.0f;
+        xw = (gw - 0.5f) * 2.0f;
+      }
+      for (int l = 0; l <= nh; ++l) {
+        const uint32_t buf = l & 1u, acc = l & 1u;
+        const uint32_t ub = buf ? use_buf1 : use_buf0;
+        if (role > 0) SB_DBG(role, ti, l, 0);
+        if (l > 0) {
+          mbar_wait(&acc_full[acc], (acc ? use_acc1 : use_acc0) & 1u);
+          tc_fence_after();
+        }
+        if (role > 0) SB_DBG(role, ti, l, 1);
+        // the previous occupant of this region (two layers back) must have been stored
+        mbar_wait(&region_free[buf * C::KB + c], (ub & 1u) ^ 1u);
+        if (role > 0) SB_DBG(role, ti, l, 2);
+        const uint32_t row_addr =
+            smem_u32(smem + C::OFF_A + buf * C::A_BUF) + c * kChunkBytes + r_in_tile * 128;
+        const int nxt = (l + 2 <= nh) ? l + 2 : ((l & 1) ? 1 : 2);  // next layer accumulating here
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          uint32_t o[16];
+          const int col0 = c * 64 + hb * 32;
+          if (l == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float4 ta = __ldg(args.tab0 + col0 + 2 * j);
+              const float4 tb = __ldg(args.tab0 + col0 + 2 * j + 1);
+              const float t0 = fmaf(xh, ta.x, fmaf(xw, ta.y, ta.z));
+              const float t1 = fmaf(xh, tb.x, fmaf(xw, tb.y, tb.z));
+              o[j] = sine_signed_half2(t0, t1);
+            }
+          } else {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * W + col0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float t0 = __uint_as_float(v[2 * j]) * args.omega;
+              const float t1 = __uint_as_float(v[2 * j + 1]) * args.omega;
+              o[j] = sine_signed_half2(t0, t1);
+            }
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
+            st_shared_v4(row_addr + (chunk << 4), o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2],
+                         o[4 * c4 + 3]);
+          }
+          // refill the drained columns with the bias of the next layer that accumulates here
+          if (l > 0 && nxt <= nh) fill_bias(acc, nxt, col0);
+        }
+        if (role > 0) SB_DBG(role, ti, l, 3);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&chunk_done[buf * C::KB + c]);
+        if (role > 0) SB_DBG(role, ti, l, 4);
+        if (l > 0) {
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+          if (acc) ++use_acc1; else ++use_acc0;
+        }
+        if (buf) ++use_buf1; else ++use_buf0;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
 }  // namespace sb

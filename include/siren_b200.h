@@ -135,6 +135,10 @@ int sirenb200_fakequant_per_channel(const float* w, int32_t rows, int32_t cols, 
 int sirenb200_profile_enable(sirenb200_handle_t h, int32_t enable);
 int sirenb200_profile_read(sirenb200_handle_t h, float* h_total_ms, int32_t* h_count, int32_t n_kinds);
 
+/* Developer aid: copies the fused-forward timeline capture (clock64 stamps of block 0; enabled by the
+ * SIRENB200_TIMELINE environment variable at create time) to a HOST array of n int64. */
+int sirenb200_debug_timeline(sirenb200_handle_t h, long long* h_out, int32_t n);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t sirenb200_launch_count(void);
 
