@@ -303,9 +303,10 @@ def run_gpu_arm(args):
                     "avg_launch_ms": avg_ms, "launches": kinds[dom][1], "peak_source": peaks["source"],
                     "share_of_step": kinds[dom][0] / ms}
     step_tflops = f_step(H * W) * value / 1e12
-    roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16_sustained"] or peaks["bf16"],
-                     "unit": "TFLOP/s", "frac": step_tflops / (peaks["bf16_sustained"] or peaks["bf16"]),
-                     "frac_of_burst_peak": step_tflops / peaks["bf16"],
+    tpeak = (peaks["bf16_sustained"] or peaks["bf16"]) * world
+    roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": tpeak,
+                     "unit": "TFLOP/s", "frac": step_tflops / tpeak,
+                     "frac_of_burst_peak": step_tflops / (peaks["bf16"] * world),
                      "note": "whole fit step, algorithmic FLOPs (SURVEY.md §8d) vs measured cuBLAS bf16 "
                              "(sustained) — fp16 tcgen05 MMA has the same peak"}
     kernel_ms = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
