@@ -150,7 +150,7 @@ int dev_alloc(sirenb200_plan* p, T** ptr, int64_t count) {
   return 0;
 }
 
-bool tc_supported(int W) { return W == 128 || W == 256; }
+bool tc_supported(int W) { return W == 128 || W == 256 || W == 512; }
 
 float omega_of(const sirenb200_plan* p, int layer) {
   return layer == 0 ? p->cfg.first_omega : p->cfg.hidden_omega;
@@ -170,16 +170,19 @@ template <int W, int MODE>
 int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap& tmE, const CUtensorMap& tmO, const RowGemmArgs& args,
                    cudaStream_t st) {
-  using Cfg = RowGemmCfg<W, W, MODE>;
-  auto kfn = rowgemm_kernel<W, W, MODE, false>;
+  constexpr int NT = W < 256 ? W : 256;  // output columns per work item
+  constexpr int NPARTS = W / NT;
+  using Cfg = RowGemmCfg<W, NT, MODE, NPARTS>;
+  auto kfn = rowgemm_kernel<W, NT, MODE, false, NPARTS>;
   static bool attr_set[64] = {};
   if (!attr_set[p->device & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   int(Cfg::SMEM_BYTES)));
     attr_set[p->device & 63] = true;
   }
-  const int grid = args.num_tiles < p->nsm ? args.num_tiles : p->nsm;
-  const uint32_t idesc = umma_idesc(128, W, 0, 0, 0, 0);
+  const int items = args.num_tiles * NPARTS;
+  const int grid = items < p->nsm ? items : p->nsm;
+  const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
     kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
@@ -190,19 +193,20 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
 
 template <int W>
 int launch_colgemm(sirenb200_plan* p, const ColGemmJobs& jobs, cudaStream_t st) {
-  using Cfg = ColGemmCfg<W>;
-  auto kfn = colgemm_kernel<W>;
+  constexpr int NT = W < 256 ? W : 256;
+  using Cfg = ColGemmCfg<NT>;
+  auto kfn = colgemm_kernel<NT>;
   static bool attr_set[64] = {};
   if (!attr_set[p->device & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   int(Cfg::SMEM_BYTES)));
     attr_set[p->device & 63] = true;
   }
-  const int grid = jobs.num_problems * jobs.mblocks * jobs.splits;
+  const int grid = jobs.num_problems * jobs.mblocks * jobs.nparts * jobs.splits;
   {
     ProfScope ps(p, PK_DW_GEMM, st);
     kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(p->tm_dz, p->tm_act, jobs,
-                                            umma_idesc(128, W, 0, 0, 1, 1),
+                                            umma_idesc(128, NT, 0, 0, 1, 1),
                                             umma_idesc(128, 16, 0, 0, 1, 1));
   }
   LAUNCH_CHECK();
@@ -390,6 +394,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     ColGemmJobs jobs{};
     jobs.num_problems = nh;
     jobs.mblocks = W / 128;
+    jobs.nparts = W / (W < 256 ? W : 256);
     jobs.splits = p->col_splits;
     jobs.tile0 = ch.t0;
     jobs.tiles_total = ch.ntiles;
@@ -402,6 +407,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     jobs.dw_partial = p->dw_part;
     jobs.db_partial = p->db_part;
     jobs.nx = W;
+    jobs.ny_total = W;
     int rc = launch_colgemm<W>(p, jobs, st);
     if (rc) return rc;
   }
@@ -476,6 +482,16 @@ int tc_run(sirenb200_plan* p, const float* const* prm, int mode, const float* im
   }
   if (!rc && mode != 0) rc = tc_reduce<W>(p, grads, scale, stats, int(chunks.size()), st);
   return rc;
+}
+
+int tc_dispatch(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
+                float* pred, float* const* grads, float scale, float* stats, cudaStream_t st) {
+  switch (p->W) {
+    case 128: return tc_run<128>(p, prm, mode, img_or_dpred, pred, grads, scale, stats, st);
+    case 256: return tc_run<256>(p, prm, mode, img_or_dpred, pred, grads, scale, stats, st);
+    case 512: return tc_run<512>(p, prm, mode, img_or_dpred, pred, grads, scale, stats, st);
+    default: return fail(SIRENB200_ERR_INVALID, "no tensor-core kernels for hidden %d", p->W);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -656,7 +672,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
                 prop.major, prop.minor);
   if (cfg->precision == SIRENB200_PREC_F16TC && !tc_supported(cfg->hidden))
     return fail(SIRENB200_ERR_INVALID,
-                "tensor-core path supports hidden in {128, 256}; got %d (use SIRENB200_PREC_FP32)",
+                "tensor-core path supports hidden in {128, 256, 512}; got %d (use SIRENB200_PREC_FP32)",
                 cfg->hidden);
   if (cfg->precision != SIRENB200_PREC_F16TC && cfg->precision != SIRENB200_PREC_FP32)
     return fail(SIRENB200_ERR_INVALID, "unknown precision %d", cfg->precision);
@@ -723,7 +739,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     ALLOC(p->tab0, W);
     ALLOC(p->bias_w, int64_t(nh > 0 ? nh : 1) * W);
     ALLOC(p->bias_raw, int64_t(nh > 0 ? nh : 1) * W);
-    int splits = nh > 0 ? p->nsm / (nh * (W / 128)) : 1;
+    int splits = nh > 0 ? p->nsm / (nh * (W / 128) * (W / (W < 256 ? W : 256))) : 1;
     if (splits < 1) splits = 1;
     if (splits > p->ntiles) splits = p->ntiles;
     p->col_splits = splits;  // (re-clamped to the chunk size below)
@@ -760,10 +776,11 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     p->tm_w.resize(nh > 0 ? nh : 0);
     p->tm_wt.resize(nh > 0 ? nh : 0);
     for (int l = 0; l < nh; ++l) {
-      trc |= make_tmap_16bit(&p->tm_w[l], p->wh + size_t(l) * W * W, W, W, W, false);
-      trc |= make_tmap_16bit(&p->tm_wt[l], p->wth + size_t(l) * W * W, W, W, W, false);
+      const uint32_t brows = W < 256 ? W : 256;  // B box rows = output columns per work item
+      trc |= make_tmap_16bit(&p->tm_w[l], p->wh + size_t(l) * W * W, W, W, brows, false);
+      trc |= make_tmap_16bit(&p->tm_wt[l], p->wth + size_t(l) * W * W, W, W, brows, false);
     }
-    if (nh > 0) trc |= make_tmap_16bit(&p->tm_wstack, p->wh, uint64_t(nh) * W, W, W, false);
+    if (nh > 0) trc |= make_tmap_16bit(&p->tm_wstack, p->wh, uint64_t(nh) * W, W, W < 256 ? W : 256, false);
     if (trc) {
       sirenb200_destroy(p);
       return fail(SIRENB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", trc);
@@ -857,10 +874,8 @@ int sirenb200_forward(sirenb200_handle_t h, const float* const* prm, float* pred
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (h->cfg.precision == SIRENB200_PREC_FP32) {
     rc = f32_forward(h, prm, 0, nullptr, pred, st);
-  } else if (h->W == 256) {
-    rc = tc_run<256>(h, prm, 0, nullptr, pred, nullptr, 0.f, nullptr, st);
   } else {
-    rc = tc_run<128>(h, prm, 0, nullptr, pred, nullptr, 0.f, nullptr, st);
+    rc = tc_dispatch(h, prm, 0, nullptr, pred, nullptr, 0.f, nullptr, st);
   }
   h->have_fwd = (rc == 0);
   return rc;
@@ -880,8 +895,7 @@ int sirenb200_forward_backward(sirenb200_handle_t h, const float* const* prm, co
     if (!rc) rc = f32_backward(h, prm, grads, scale, stats, st);
     if (!rc) rc = finalize(h, h->loss_part, 256, 1, stats, false, st);
   } else {
-    rc = (h->W == 256) ? tc_run<256>(h, prm, 1, img, nullptr, grads, scale, stats, st)
-                       : tc_run<128>(h, prm, 1, img, nullptr, grads, scale, stats, st);
+    rc = tc_dispatch(h, prm, 1, img, nullptr, grads, scale, stats, st);
     if (!rc)
       rc = finalize(h, h->last_part + h->C * h->W + h->C, h->last_grid * h->nchunks,
                     int64_t(h->C) * h->W + h->C + 1, stats, true, st);
@@ -915,8 +929,7 @@ int sirenb200_backward(sirenb200_handle_t h, const float* const* prm, const floa
   } else {
     absmax_scale_kernel<<<1, 1024, 0, st>>>(dpred, h->npix * h->C, h->gstate);
     LAUNCH_CHECK();
-    rc = (h->W == 256) ? tc_run<256>(h, prm, 2, dpred, nullptr, grads, 1.0f, stats, st)
-                       : tc_run<128>(h, prm, 2, dpred, nullptr, grads, 1.0f, stats, st);
+    rc = tc_dispatch(h, prm, 2, dpred, nullptr, grads, 1.0f, stats, st);
   }
   return rc;
 }

@@ -71,20 +71,26 @@ __device__ __forceinline__ float cos_from_signed_half(uint32_t h16) {
 // ------------------------------------------------------------------------------------------
 // rowgemm
 // ------------------------------------------------------------------------------------------
-template <int KDIM, int NDIM, int MODE>
+// NDIM = output columns per work item (<= 256, one UMMA N); NPARTS = output width / NDIM.  When the whole
+// B operand (NDIM x KDIM fp16) fits next to the rings it stays RESIDENT in shared memory for the kernel's
+// lifetime (hidden <= 256); otherwise (hidden 512) its 64-wide k-blocks are streamed through the same
+// ring stage as the A k-blocks and every 128-row tile is visited once per output part.
+template <int KDIM, int NDIM, int MODE, int NPARTS = 1>
 struct RowGemmCfg {
   static_assert(KDIM % 64 == 0 && NDIM % 64 == 0, "hidden size must be a multiple of 64");
   static_assert(NDIM >= 16 && NDIM <= 256, "UMMA N range");
   static constexpr int KB = KDIM / 64;  // 64-wide K blocks
   static constexpr int NB = NDIM / 64;  // 64-wide output chunks
-  static constexpr int SA = 3;          // A-tile ring depth (16 KiB stages)
+  static constexpr int SA = 3;          // ring depth
   static constexpr int SEO = (MODE == MODE_DX) ? 3 : 2;  // epilogue in/out ring depth
   static constexpr uint32_t B_KB_BYTES = NDIM * 128;
+  static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u);
+  static constexpr uint32_t A_STAGE = kChunkBytes + (STREAM_B ? B_KB_BYTES : 0u);
   static constexpr uint32_t OFF_B = 0;
-  static constexpr uint32_t OFF_A = OFF_B + KB * B_KB_BYTES;
-  static constexpr uint32_t OFF_EO = OFF_A + SA * kChunkBytes;
+  static constexpr uint32_t OFF_A = OFF_B + (STREAM_B ? 0u : KB * B_KB_BYTES);
+  static constexpr uint32_t OFF_EO = OFF_A + SA * A_STAGE;
   static constexpr uint32_t OFF_CONST = OFF_EO + SEO * kChunkBytes;
-  static constexpr uint32_t CONST_BYTES = (MODE == MODE_FWD) ? NDIM * 4 : 0;
+  static constexpr uint32_t CONST_BYTES = (MODE == MODE_FWD) ? NDIM * NPARTS * 4 : 0;
   static constexpr uint32_t OFF_BAR = OFF_CONST + CONST_BYTES;
   static constexpr int NUM_BARS = 2 * SA + 1 + 2 * SEO + 4;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;  // + align slack
@@ -102,12 +108,13 @@ struct RowGemmArgs {
   const float* bias;  // MODE_FWD: fp32 bias[NDIM]
 };
 
-template <int KDIM, int NDIM, int MODE, bool OUT_BF16>
+template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1>
 __global__ void __launch_bounds__(256, 1)
 rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
                const RowGemmArgs args, const uint32_t idesc) {
-  using C = RowGemmCfg<KDIM, NDIM, MODE>;
+  using C = RowGemmCfg<KDIM, NDIM, MODE, NPARTS>;
+  const int num_items = args.num_tiles * NPARTS;  // item = (tile, output part)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -150,7 +157,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (MODE == MODE_FWD && warp >= 4) {
     float* cst = reinterpret_cast<float*>(smem + C::OFF_CONST);
-    for (int i = threadIdx.x - 128; i < NDIM; i += 128) cst[i] = args.omega * args.bias[i];
+    for (int i = threadIdx.x - 128; i < NDIM * NPARTS; i += 128) cst[i] = args.omega * args.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -160,27 +167,33 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer: B once, then A k-blocks =====================
     if (lane == 0) {
-      mbar_expect_tx(b_full, C::KB * C::B_KB_BYTES);
-      for (int kb = 0; kb < C::KB; ++kb)
-        tma_load_2d(smem + C::OFF_B + kb * C::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
+      if (!C::STREAM_B) {
+        mbar_expect_tx(b_full, C::KB * C::B_KB_BYTES);
+        for (int kb = 0; kb < C::KB; ++kb)
+          tma_load_2d(smem + C::OFF_B + kb * C::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
+      }
       uint32_t ia = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+        const int t = it / NPARTS, part = it % NPARTS;
         const int row = args.a_row0 + t * kRowsPerTile;
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
           mbar_wait(&a_empty[s], ph ^ 1u);
-          mbar_expect_tx(&a_full[s], kChunkBytes);
-          tma_load_2d(smem + C::OFF_A + s * kChunkBytes, &tmA, &a_full[s], kb * 64, row);
+          mbar_expect_tx(&a_full[s], C::A_STAGE);
+          tma_load_2d(smem + C::OFF_A + s * C::A_STAGE, &tmA, &a_full[s], kb * 64, row);
+          if (C::STREAM_B)
+            tma_load_2d(smem + C::OFF_A + s * C::A_STAGE + kChunkBytes, &tmB, &a_full[s], kb * 64,
+                        part * NDIM);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      mbar_wait(b_full, 0);
+      if (!C::STREAM_B) mbar_wait(b_full, 0);
       tc_fence_after();
       uint32_t ia = 0, it = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
         mbar_wait(&tm_empty[acc], aph ^ 1u);
         tc_fence_after();
@@ -189,8 +202,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
           mbar_wait(&a_full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + C::OFF_A + s * kChunkBytes);
-          const uint32_t b_addr = smem_u32(smem + C::OFF_B + kb * C::B_KB_BYTES);
+          const uint32_t a_addr = smem_u32(smem + C::OFF_A + s * C::A_STAGE);
+          const uint32_t b_addr = C::STREAM_B ? a_addr + kChunkBytes
+                                              : smem_u32(smem + C::OFF_B + kb * C::B_KB_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = umma_smem_desc(a_addr + k * 32, 0, 1024, 2);
@@ -206,13 +220,15 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue-input producer (MODE_DX only) =====================
     if (MODE == MODE_DX && lane == 0) {
       uint32_t ic = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int t = item / NPARTS, part = item % NPARTS;
         const int row = args.e_row0 + t * kRowsPerTile;
         for (int nb = 0; nb < C::NB; ++nb, ++ic) {
           const uint32_t s = ic % C::SEO, ph = (ic / C::SEO) & 1u;
           mbar_wait(&eo_empty[s], ph ^ 1u);
           mbar_expect_tx(&eo_full[s], kChunkBytes);
-          tma_load_2d(smem + C::OFF_EO + s * kChunkBytes, &tmE, &eo_full[s], nb * 64, row);
+          tma_load_2d(smem + C::OFF_EO + s * kChunkBytes, &tmE, &eo_full[s], part * NDIM + nb * 64,
+                      row);
         }
       }
     }
@@ -223,7 +239,8 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool issuer = (threadIdx.x == 128);
     const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
     uint32_t it = 0, ic = 0;
-    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int t = item / NPARTS, part = item % NPARTS;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       mbar_wait(&tm_full[acc], aph);
       tc_fence_after();
@@ -245,7 +262,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (MODE == MODE_FWD) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int col = nb * 64 + hb * 32 + 2 * j;
+              const int col = part * NDIM + nb * 64 + hb * 32 + 2 * j;
               const float t0 = fmaf(__uint_as_float(v[2 * j]), args.omega, cst[col]);
               const float t1 = fmaf(__uint_as_float(v[2 * j + 1]), args.omega, cst[col + 1]);
               o[j] = sine_signed_half2(t0, t1);
@@ -279,7 +296,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer) {
-          tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, nb * 64,
+          tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, part * NDIM + nb * 64,
                        args.o_row0 + t * kRowsPerTile);
           tma_store_commit();
           if (ic > 0) {
@@ -307,6 +324,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // colgemm: weight-gradient reduction over the pixel dimension (split-K over pixel tiles)
 // ------------------------------------------------------------------------------------------
+// NY = dW columns per job (<= 256, one UMMA N); wider layers (hidden 512) are split into column parts.
 template <int NY>
 struct ColGemmCfg {
   static_assert(NY % 64 == 0 && NY >= 64 && NY <= 256, "operand width");
@@ -328,16 +346,18 @@ struct ColGemmCfg {
 struct ColGemmJobs {
   int num_problems;     // e.g. hidden layers 1..D-2
   int mblocks;          // output row blocks per problem (NX / 128)
-  int splits;           // pixel splits per (problem, mblock)
+  int nparts;           // output column parts per problem (width / NY)
+  int splits;           // pixel splits per (problem, mblock, part)
   int tile0;            // first 128-pixel tile of this launch (row chunks)
   int tiles_total;      // 128-pixel tiles in the launch's row range
   int tiles_per_split;  // ceil(tiles_total / splits)
   int accumulate;       // add to the existing partials instead of overwriting them
   int x_row0[8];        // first row of problem p in the X (dZ) tensor map
   int y_row0[8];        // first row of problem p in the Y (activation) tensor map
-  float* dw_partial;    // [splits][num_problems][NX][NY] fp32
+  float* dw_partial;    // [splits][num_problems][NX][ny_total] fp32
   float* db_partial;    // [splits][num_problems][NX] fp32
   int nx;               // rows of dW per problem (= X width)
+  int ny_total;         // columns of dW per problem (= Y width = NY * nparts)
 };
 
 template <int NY>
@@ -359,8 +379,9 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   // job decode
   const int job = blockIdx.x;
   const int split = job % jobs.splits;
-  const int mb = (job / jobs.splits) % jobs.mblocks;
-  const int prob = job / (jobs.splits * jobs.mblocks);
+  const int part = (job / jobs.splits) % jobs.nparts;
+  const int mb = (job / (jobs.splits * jobs.nparts)) % jobs.mblocks;
+  const int prob = job / (jobs.splits * jobs.nparts * jobs.mblocks);
   const int tile_begin = split * jobs.tiles_per_split;
   int tile_end = tile_begin + jobs.tiles_per_split;
   if (tile_end > jobs.tiles_total) tile_end = jobs.tiles_total;
@@ -403,7 +424,7 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           tma_load_2d(st + c * kChunkBytes, &tmX, &full[s], mb * 128 + c * 64,
                       jobs.x_row0[prob] + prow);
         for (int c = 0; c < C::YC; ++c)
-          tma_load_2d(st + (C::XC + c) * kChunkBytes, &tmY, &full[s], c * 64,
+          tma_load_2d(st + (C::XC + c) * kChunkBytes, &tmY, &full[s], part * NY + c * 64,
                       jobs.y_row0[prob] + prow);
       }
     }
@@ -433,7 +454,8 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int q = warp & 3;
     const int m = mb * 128 + q * 32 + lane;  // output row of this thread
     float* dw = jobs.dw_partial +
-                ((size_t(split) * jobs.num_problems + prob) * jobs.nx + m) * size_t(NY);
+                ((size_t(split) * jobs.num_problems + prob) * jobs.nx + m) * size_t(jobs.ny_total) +
+                part * NY;
     float* dbp = jobs.db_partial + (size_t(split) * jobs.num_problems + prob) * jobs.nx + m;
     if (ntiles > 0) {
       mbar_wait(done, 0);
@@ -457,13 +479,15 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           *dst = o;
         }
       }
-      uint32_t b8[8];
-      tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + NY, b8);
-      tmem_ld_wait();
-      *dbp = __uint_as_float(b8[0]) + (jobs.accumulate ? *dbp : 0.f);
+      if (part == 0) {  // the bias gradient does not depend on the column part
+        uint32_t b8[8];
+        tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + NY, b8);
+        tmem_ld_wait();
+        *dbp = __uint_as_float(b8[0]) + (jobs.accumulate ? *dbp : 0.f);
+      }
     } else if (!jobs.accumulate) {
       for (int j = 0; j < NY / 4; ++j) reinterpret_cast<uint4*>(dw)[j] = make_uint4(0, 0, 0, 0);
-      *dbp = 0.0f;
+      if (part == 0) *dbp = 0.0f;
     }
   }
 

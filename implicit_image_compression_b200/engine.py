@@ -11,7 +11,7 @@ from . import _lib
 
 def default_precision(hidden):
     """fp16 tensor-core path when the hidden width has a tcgen05 kernel, else the fp32 CUDA-core path."""
-    return _lib.PREC_F16TC if hidden in (128, 256) else _lib.PREC_FP32
+    return _lib.PREC_F16TC if hidden in (128, 256, 512) else _lib.PREC_FP32
 
 
 class SirenEngine:

@@ -114,6 +114,28 @@ def test_edge_shapes_and_arbitrary_grids(precision, hidden):
     assert (pred.cpu() - O.siren_forward(ref, grid, 50.0, 30.0)).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("depth,H,W", [(3, 24, 40), (4, 33, 47)])
+def test_hidden_512_tensor_core_path_vs_oracle(depth, H, W):
+    """hidden 512 (configs 3 and 5): streamed-B rowgemm with two output parts, 4x2 colgemm blocks."""
+    _, _, _, Siren, _ = _pkg()
+    torch.manual_seed(0)
+    model = Siren(depth=depth, hidden_size=512, first_omega_0=50, hidden_omega_0=30, precision="f16tc")
+    ref = O.siren_init(0, depth, 512, 50.0, 30.0)
+    for p, r in zip(model.parameters(), ref):
+        assert torch.equal(p.detach(), r)
+    model = model.cuda()
+    grid, img = O.get_grid(H, W), O.synth_image(H, W, 0)
+    loss, grads = O.siren_loss_and_grads(ref, grid, img, 50.0, 30.0)
+    with torch.no_grad():
+        pred = model(grid.cuda())
+    assert (pred.cpu() - O.siren_forward(ref, grid, 50.0, 30.0)).abs().max().item() <= TOL["f16tc"]["pred"]
+    out = [torch.full_like(p, float("nan")) for p in model.hot_parameters()]
+    stats = model.engine_for(grid.cuda()).forward_backward(model.kernel_parameters(), img.cuda(), out)
+    assert abs(stats[1].item() - loss.item()) <= TOL["f16tc"]["loss"] * loss.item()
+    for i, (a, b) in enumerate(zip(out, grads)):
+        assert _rel(a, b) <= TOL["f16tc"]["grad"], f"grad {i}"
+
+
 def test_sine_output_layer_variant():
     _, get_grid, synth_image, Siren, _ = _pkg()
     torch.manual_seed(2)

@@ -203,6 +203,8 @@ static int test_colgemm(int rows, bool timing) {
     ColGemmJobs jobs{};
     jobs.num_problems = nprob;
     jobs.mblocks = NX / 128;
+    jobs.nparts = 1;
+    jobs.ny_total = NY;
     jobs.splits = nsm / (nprob * jobs.mblocks);
     if (jobs.splits > tiles) jobs.splits = tiles;
     jobs.tiles_total = tiles;
