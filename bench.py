@@ -24,20 +24,25 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# default workload = BASELINE.json configs[1]; --workload c3 (configs[2]: hidden 512, depth 8, 2048x2048) is a
+# developer option for the pixel-sharded large-image case and is NOT what the driver's contract line measures
+WORKLOADS = {"c2": (6, 256, 512, 768), "c3": (8, 512, 2048, 2048)}
 DEPTH, HIDDEN, H, W, C = 6, 256, 512, 768, 3
 OMEGA0, OMEGA = 50.0, 30.0
 LR = 3e-4
 METRIC, UNIT = "siren_fit_steps_per_sec", "steps/s"
 
 
-def f_step(n_pix, depth=DEPTH, w=HIDDEN):
+def f_step(n_pix, depth=None, w=None):
     """Algorithmic FLOPs per fit step: 2 N [3 (D-2) W^2 + 13 W]."""
+    depth = DEPTH if depth is None else depth
+    w = HIDDEN if w is None else w
     return 2.0 * n_pix * (3 * (depth - 2) * w * w + 13 * w)
 
 
 def workload_config(n_gpus):
     return {
-        "workload": f"c2: SIREN hidden {HIDDEN} depth {DEPTH}, {H}x{W} synthetic 16-bit RGB, dense Adam fit step"
+        "workload": f"{'c2' if HIDDEN == 256 else 'c3'}: SIREN hidden {HIDDEN} depth {DEPTH}, {H}x{W} synthetic 16-bit RGB, dense Adam fit step"
                     + ("" if n_gpus == 1 else f", rows sharded over {n_gpus} ranks + NCCL grad all-reduce"),
         "hidden_size": HIDDEN, "depth": DEPTH, "height": H, "width": W, "pixels": H * W,
         "optimizer": "adam lr 3e-4 + StepLR(2000, 0.5)", "precision_mode": "f16tc",
@@ -338,7 +343,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global DEPTH, HIDDEN, H, W
+    DEPTH, HIDDEN, H, W = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args)
     else:
