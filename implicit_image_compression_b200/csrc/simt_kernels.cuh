@@ -230,17 +230,34 @@ __global__ void __launch_bounds__(256) tc_first_layer_kernel(CoordSrc c, const f
     wb[j] = w0[(tc * 8 + j) * 2 + 1] * omega;
     bb[j] = b0[tc * 8 + j] * omega;
   }
-  for (int64_t p = int64_t(blockIdx.x) * RPB + tr; p < npix_pad; p += int64_t(gridDim.x) * RPB) {
+  // row / column of the pixel are tracked incrementally (one division per thread, not per pixel)
+  const int64_t pfirst = int64_t(blockIdx.x) * RPB + tr;
+  const unsigned step = gridDim.x * RPB;
+  const unsigned step_r = step / unsigned(c.width), step_c = step % unsigned(c.width);
+  const uint64_t g0 = uint64_t(pfirst + c.p_offset);
+  unsigned row = unsigned(g0 / unsigned(c.width)), col = unsigned(g0 % unsigned(c.width));
+  for (int64_t p = pfirst; p < npix_pad; p += step) {
     uint32_t o[4] = {0, 0, 0, 0};
     if (p < npix) {
       float xh, xw;
-      load_xy(c, p, xh, xw);
+      if (c.coords) {
+        load_xy(c, p, xh, xw);
+      } else {
+        xh = (__ldg(c.lin_h + c.row_begin + row) - 0.5f) * 2.0f;
+        xw = (__ldg(c.lin_w + col) - 0.5f) * 2.0f;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float t0 = fmaf(xh, wa[2 * j], fmaf(xw, wb[2 * j], bb[2 * j]));
         const float t1 = fmaf(xh, wa[2 * j + 1], fmaf(xw, wb[2 * j + 1], bb[2 * j + 1]));
         o[j] = sine_signed_half2(t0, t1);
       }
+    }
+    row += step_r;
+    col += step_c;
+    if (col >= unsigned(c.width)) {
+      col -= unsigned(c.width);
+      ++row;
     }
     reinterpret_cast<uint4*>(act0 + p * W)[tc] = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -437,51 +454,94 @@ __global__ void __launch_bounds__(256) tc_last_layer_kernel(const LastArgs a) {
 // ------------------------------------------------------------------------------------------
 // tensor-core path, layer-0 gradients: dW0[j, {h,w}] = sum_p dz0[p, j] * x[p], db0[j] = sum_p dz0
 // ------------------------------------------------------------------------------------------
+// Streaming version: each block owns a contiguous pixel range and pulls it through a ring of
+// shared-memory stages with 1-D bulk copies (dozens of KB in flight per SM without register cost).
+template <int W>
+struct L0GradCfg {
+  static constexpr int ROWS = 32;                       // pixels per stage
+  static constexpr int STAGES = 6;
+  static constexpr uint32_t STAGE_BYTES = ROWS * W * 2;
+  static constexpr uint32_t OFF_XY = STAGES * STAGE_BYTES + STAGES * 8 + 16;  // float2 xy[2][ROWS]
+  static constexpr uint32_t SMEM_BYTES = OFF_XY + 2 * ROWS * 8;
+};
+
 template <int W>
 __global__ void __launch_bounds__(256) tc_layer0_grad_kernel(CoordSrc c, const __half* __restrict__ dz0,
                                                              float* __restrict__ part, int64_t npix) {
+  using Cfg = L0GradCfg<W>;
   constexpr int TPR = W / 8;      // threads per row (8 columns = 16 bytes each)
   constexpr int RL = 256 / TPR;   // row lanes
-  constexpr int UN = 8;           // rows in flight per thread
+  extern __shared__ __align__(128) uint8_t l0_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(l0_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   const int tc = threadIdx.x % TPR, tr = threadIdx.x / TPR;
-  const int64_t per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const int64_t per_block = ((npix + gridDim.x - 1) / gridDim.x + Cfg::ROWS - 1) / Cfg::ROWS * Cfg::ROWS;
   const int64_t p0 = blockIdx.x * per_block;
   const int64_t p1 = min(npix, p0 + per_block);
-  float ah[8] = {}, aw[8] = {}, ab[8] = {};
-  for (int64_t p = p0 + tr; p < p1; p += RL * UN) {
-    uint4 v[UN];
-    float xh[UN], xw[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int64_t q = p + u * RL;
-      v[u] = make_uint4(0, 0, 0, 0);
-      xh[u] = xw[u] = 0.f;
-      if (q < p1) {
-        v[u] = reinterpret_cast<const uint4*>(dz0 + q * W)[tc];
-        load_xy(c, q, xh[u], xw[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
-        ah[2 * j] = fmaf(g.x, xh[u], ah[2 * j]);
-        aw[2 * j] = fmaf(g.x, xw[u], aw[2 * j]);
-        ab[2 * j] += g.x;
-        ah[2 * j + 1] = fmaf(g.y, xh[u], ah[2 * j + 1]);
-        aw[2 * j + 1] = fmaf(g.y, xw[u], aw[2 * j + 1]);
-        ab[2 * j + 1] += g.y;
-      }
-    }
+  const int niter = p1 > p0 ? int((p1 - p0 + Cfg::ROWS - 1) / Cfg::ROWS) : 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
   }
-  __shared__ float red[RL][3][W + 8];
+  __syncthreads();
+  auto issue = [&](int it) {
+    const int s = it % Cfg::STAGES;
+    const int64_t q0 = p0 + int64_t(it) * Cfg::ROWS;
+    const int64_t left = p1 - q0;
+    const int rows = left < Cfg::ROWS ? int(left) : Cfg::ROWS;
+    mbar_expect_tx(&full[s], uint32_t(rows) * W * 2);
+    bulk_load_1d(l0_smem + s * Cfg::STAGE_BYTES, dz0 + q0 * W, uint32_t(rows) * W * 2, &full[s]);
+  };
+  if (threadIdx.x == 0)
+    for (int it = 0; it < Cfg::STAGES && it < niter; ++it) issue(it);
+  // coordinates of a stage's rows are computed once (32 threads) one iteration ahead
+  float2* xy = reinterpret_cast<float2*>(l0_smem + Cfg::OFF_XY);
+  auto stage_coords = [&](int it) {
+    if (threadIdx.x < Cfg::ROWS && it < niter) {
+      const int64_t q = p0 + int64_t(it) * Cfg::ROWS + threadIdx.x;
+      float xh = 0.f, xw = 0.f;
+      if (q < p1) load_xy(c, q, xh, xw);
+      xy[(it & 1) * Cfg::ROWS + threadIdx.x] = make_float2(xh, xw);
+    }
+  };
+  stage_coords(0);
+  __syncthreads();
+  float ah[8] = {}, aw[8] = {}, ab[8] = {};
+  for (int it = 0; it < niter; ++it) {
+    const int s = it % Cfg::STAGES;
+    stage_coords(it + 1);
+    mbar_wait(&full[s], (it / Cfg::STAGES) & 1);
+    const int64_t q0 = p0 + int64_t(it) * Cfg::ROWS;
+    const uint8_t* st = l0_smem + s * Cfg::STAGE_BYTES;
+#pragma unroll
+    for (int r = tr; r < Cfg::ROWS; r += RL) {
+      if (q0 + r < p1) {
+        const float2 cxy = xy[(it & 1) * Cfg::ROWS + r];
+        const float xh = cxy.x, xw = cxy.y;
+        const uint4 v = *reinterpret_cast<const uint4*>(st + (r * W + tc * 8) * 2);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 g = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
+          ah[2 * j] = fmaf(g.x, xh, ah[2 * j]);
+          aw[2 * j] = fmaf(g.x, xw, aw[2 * j]);
+          ab[2 * j] += g.x;
+          ah[2 * j + 1] = fmaf(g.y, xh, ah[2 * j + 1]);
+          aw[2 * j + 1] = fmaf(g.y, xw, aw[2 * j + 1]);
+          ab[2 * j + 1] += g.y;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with stage s
+    if (threadIdx.x == 0 && it + Cfg::STAGES < niter) issue(it + Cfg::STAGES);
+  }
+  // block reduction over the row lanes, reusing stage memory: red[RL][3][W]
+  float* red = reinterpret_cast<float*>(l0_smem);
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[tr][0][tc * 8 + j] = ah[j];
-    red[tr][1][tc * 8 + j] = aw[j];
-    red[tr][2][tc * 8 + j] = ab[j];
+    red[(tr * 3 + 0) * W + tc * 8 + j] = ah[j];
+    red[(tr * 3 + 1) * W + tc * 8 + j] = aw[j];
+    red[(tr * 3 + 2) * W + tc * 8 + j] = ab[j];
   }
   __syncthreads();
   float* out = part + int64_t(blockIdx.x) * (3 * W);
@@ -489,7 +549,7 @@ __global__ void __launch_bounds__(256) tc_layer0_grad_kernel(CoordSrc c, const _
     const int k = i / W, col = i % W;
     float sum = 0.f;
 #pragma unroll
-    for (int r = 0; r < RL; ++r) sum += red[r][k][col];
+    for (int r = 0; r < RL; ++r) sum += red[(r * 3 + k) * W + col];
     if (k < 2)
       out[col * 2 + k] = sum;  // dW0[col, {h, w}]
     else

@@ -101,6 +101,15 @@ struct sirenb200_plan {
   int l0_grid = 0;
   int chunk_tiles = 0;         // 128-row tiles per L2-resident chunk (0 = whole shard)
   int nchunks = 1;
+  // backward overlap: the dW GEMM of layer l runs on a second stream concurrently with the dX GEMM of
+  // layer l (both read dz[l] and act[l-1]; whichever comes second finds them in L2)
+  bool bwd_overlap = false;
+  int dx_grid = 0;             // CTAs given to the dX GEMM when overlapping (rest goes to the dW GEMM)
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork[kMaxLayers] = {};
+  cudaEvent_t ev_join = nullptr;
+  int grid_override = 0;       // transient: rowgemm grid size for the next launch
+  int active_splits = 1;       // split slabs the dW GEMM actually writes (<= col_splits)
 
   // ---- optional per-kernel timing (cudaEvent pairs recorded around tagged launches) ----
   bool prof_on = false;
@@ -181,7 +190,8 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
     attr_set[p->device & 63] = true;
   }
   const int items = args.num_tiles * NPARTS;
-  const int grid = items < p->nsm ? items : p->nsm;
+  int grid = items < p->nsm ? items : p->nsm;
+  if (p->grid_override > 0 && p->grid_override < grid) grid = p->grid_override;
   const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
@@ -378,36 +388,60 @@ int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const fl
 template <int W>
 int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
   const int nh = p->D - 2;
+  constexpr int NPARTS = W / (W < 256 ? W : 256);
+  auto fill_jobs = [&](ColGemmJobs& jobs, int l_first, int nprob, int splits, int interleave) {
+    jobs.num_problems = nprob;
+    jobs.mblocks = W / 128;
+    jobs.nparts = NPARTS;
+    jobs.splits = splits;
+    jobs.tile0 = ch.t0;
+    jobs.tiles_total = ch.ntiles;
+    jobs.tiles_per_split = cdiv(ch.ntiles, splits);
+    jobs.accumulate = ch.index > 0 ? 1 : 0;
+    for (int i = 0; i < nprob; ++i) {
+      jobs.x_row0[i] = int((l_first + i) * p->npix_pad);
+      jobs.y_row0[i] = int((l_first + i - 1) * p->npix_pad);
+    }
+    jobs.dw_partial = p->dw_part;
+    jobs.db_partial = p->db_part;
+    jobs.nx = W;
+    jobs.ny_total = W;
+    jobs.prob0 = l_first - 1;
+    jobs.prob_total = nh;
+    jobs.interleave = interleave;
+  };
+  const bool overlap = p->bwd_overlap && nh > 0 && p->st2;
   // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
   for (int l = nh; l >= 1; --l) {
+    if (overlap) {
+      // dz[l] is complete on `st` here: fork the weight-gradient GEMM of layer l onto the side stream
+      CUDA_TRY(cudaEventRecord(p->ev_fork[l], st));
+      CUDA_TRY(cudaStreamWaitEvent(p->st2, p->ev_fork[l], 0));
+    }
     RowGemmArgs ra{};
     ra.num_tiles = ch.ntiles;
     ra.a_row0 = int(l * p->npix_pad + ch.p0);
     ra.e_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.o_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.valid_rows = int(ch.npix);
+    p->grid_override = overlap ? p->dx_grid : 0;
     int rc = launch_rowgemm<W, MODE_DX>(p, p->tm_dz, p->tm_wt[l - 1], p->tm_act, p->tm_dz, ra, st);
+    p->grid_override = 0;
     if (rc) return rc;
+    if (overlap) {
+      ColGemmJobs jobs{};
+      int splits = (p->nsm - p->dx_grid) / ((W / 128) * NPARTS);
+      if (splits < 1) splits = 1;
+      if (splits > p->col_splits) splits = p->col_splits;
+      fill_jobs(jobs, l, 1, splits, 1);
+      rc = launch_colgemm<W>(p, jobs, p->st2);
+      if (rc) return rc;
+    }
   }
   // hidden-layer weight / bias gradients: one split-K launch over all layers
-  if (nh > 0) {
+  if (nh > 0 && !overlap) {
     ColGemmJobs jobs{};
-    jobs.num_problems = nh;
-    jobs.mblocks = W / 128;
-    jobs.nparts = W / (W < 256 ? W : 256);
-    jobs.splits = p->col_splits;
-    jobs.tile0 = ch.t0;
-    jobs.tiles_total = ch.ntiles;
-    jobs.tiles_per_split = cdiv(ch.ntiles, p->col_splits);
-    jobs.accumulate = ch.index > 0 ? 1 : 0;
-    for (int l = 1; l <= nh; ++l) {
-      jobs.x_row0[l - 1] = int(l * p->npix_pad);
-      jobs.y_row0[l - 1] = int((l - 1) * p->npix_pad);
-    }
-    jobs.dw_partial = p->dw_part;
-    jobs.db_partial = p->db_part;
-    jobs.nx = W;
-    jobs.ny_total = W;
+    fill_jobs(jobs, 1, nh, p->col_splits, 0);
     int rc = launch_colgemm<W>(p, jobs, st);
     if (rc) return rc;
   }
@@ -416,11 +450,21 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     cs.p_offset = ch.p0;
     int grid = p->l0_grid;
     ProfScope ps(p, PK_L0_GRAD, st);
-    tc_layer0_grad_kernel<W><<<grid, 256, 0, st>>>(cs, p->dz + ch.p0 * W,
+    static bool l0_attr[64] = {};
+    if (!l0_attr[p->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(tc_layer0_grad_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(L0GradCfg<W>::SMEM_BYTES)));
+      l0_attr[p->device & 63] = true;
+    }
+    tc_layer0_grad_kernel<W><<<grid, 256, L0GradCfg<W>::SMEM_BYTES, st>>>(cs, p->dz + ch.p0 * W,
                                                   p->l0_part + size_t(ch.index) * p->l0_grid * 3 * W,
                                                   ch.npix);
   }
   LAUNCH_CHECK();
+  if (overlap) {  // join the side stream before the partials are reduced
+    CUDA_TRY(cudaEventRecord(p->ev_join, p->st2));
+    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join, 0));
+  }
   return 0;
 }
 
@@ -442,9 +486,9 @@ int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats,
   add(grads[0], p->l0_part, 2 * W, p->l0_grid * nchunks, 3 * W);
   add(grads[1], p->l0_part + 2 * W, W, p->l0_grid * nchunks, 3 * W);
   for (int l = 1; l <= nh; ++l) {
-    add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, W * W, p->col_splits,
+    add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, W * W, p->active_splits,
         int64_t(nh) * W * W);
-    add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, W, p->col_splits, int64_t(nh) * W);
+    add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, W, p->active_splits, int64_t(nh) * W);
   }
   const int64_t lstride = int64_t(C) * W + C + 1;
   add(grads[2 * (D - 1)], p->last_part, C * W, p->last_grid * nchunks, lstride);
@@ -758,11 +802,33 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->nchunks = cdiv(p->ntiles, ct);
     }
     if (p->col_splits > p->chunk_tiles) p->col_splits = p->chunk_tiles;
+    p->active_splits = p->col_splits;
+    {
+      const char* env = getenv("SIRENB200_BWD_OVERLAP");
+      p->bwd_overlap = env && atoi(env) != 0 && nh > 0;
+      const char* eg = getenv("SIRENB200_DX_GRID");
+      p->dx_grid = eg ? atoi(eg) : (p->nsm * 2) / 3;
+      if (p->dx_grid < 1 || p->dx_grid >= p->nsm) p->dx_grid = (p->nsm * 2) / 3;
+      if (p->bwd_overlap) {
+        cudaError_t e = cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
+        for (int i = 0; i < kMaxLayers && e == cudaSuccess; ++i)
+          e = cudaEventCreateWithFlags(&p->ev_fork[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+          sirenb200_destroy(p);
+          return fail(SIRENB200_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+        }
+        int splits = (p->nsm - p->dx_grid) / ((W / 128) * (W / (W < 256 ? W : 256)));
+        if (splits < 1) splits = 1;
+        if (splits > p->col_splits) splits = p->col_splits;
+        p->active_splits = splits;
+      }
+    }
     const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
     p->last_grid = p->nsm * 2;
     if (int64_t(p->last_grid) * 8 > chunk_pad) p->last_grid = cdiv(chunk_pad, 8);
     ALLOC(p->last_part, int64_t(p->nchunks) * p->last_grid * (C * W + C + 1));
-    p->l0_grid = p->nsm * 4;
+    p->l0_grid = p->nsm * 2;
     if (p->l0_grid > p->chunk_tiles) p->l0_grid = p->chunk_tiles;
     ALLOC(p->l0_part, int64_t(p->nchunks) * p->l0_grid * 3 * W);
     cudaError_t e = cudaMemset(p->dz, 0, size_t(D - 1) * p->npix_pad * W * sizeof(__half));
@@ -812,6 +878,10 @@ int sirenb200_destroy(sirenb200_handle_t p) {
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->ev_fork)
+    if (e) cudaEventDestroy(e);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->st2) cudaStreamDestroy(p->st2);
   delete p;
   return 0;
 }

@@ -358,6 +358,10 @@ struct ColGemmJobs {
   float* db_partial;    // [splits][num_problems][NX] fp32
   int nx;               // rows of dW per problem (= X width)
   int ny_total;         // columns of dW per problem (= Y width = NY * nparts)
+  int prob0;            // index of this launch's first problem inside the partial buffers
+  int prob_total;       // problems per split slab in the partial buffers
+  int interleave;       // 1: split s visits tiles s, s+splits, ... (sweeps the image front to back,
+                        //    in step with a concurrently running rowgemm); 0: contiguous tile ranges
 };
 
 template <int NY>
@@ -382,10 +386,18 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int part = (job / jobs.splits) % jobs.nparts;
   const int mb = (job / (jobs.splits * jobs.nparts)) % jobs.mblocks;
   const int prob = job / (jobs.splits * jobs.nparts * jobs.mblocks);
-  const int tile_begin = split * jobs.tiles_per_split;
-  int tile_end = tile_begin + jobs.tiles_per_split;
-  if (tile_end > jobs.tiles_total) tile_end = jobs.tiles_total;
-  const int ntiles = tile_end > tile_begin ? tile_end - tile_begin : 0;
+  int tile_begin, tile_step, ntiles;
+  if (jobs.interleave) {
+    tile_begin = split;
+    tile_step = jobs.splits;
+    ntiles = split < jobs.tiles_total ? (jobs.tiles_total - split + jobs.splits - 1) / jobs.splits : 0;
+  } else {
+    tile_begin = split * jobs.tiles_per_split;
+    tile_step = 1;
+    int tile_end = tile_begin + jobs.tiles_per_split;
+    if (tile_end > jobs.tiles_total) tile_end = jobs.tiles_total;
+    ntiles = tile_end > tile_begin ? tile_end - tile_begin : 0;
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
@@ -416,7 +428,7 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       for (int i = 0; i < ntiles; ++i) {
         const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
-        const int prow = (jobs.tile0 + tile_begin + i) * kRowsPerTile;
+        const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], C::STAGE_BYTES);
         uint8_t* st = smem + s * C::STAGE_BYTES;
@@ -453,10 +465,9 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int m = mb * 128 + q * 32 + lane;  // output row of this thread
-    float* dw = jobs.dw_partial +
-                ((size_t(split) * jobs.num_problems + prob) * jobs.nx + m) * size_t(jobs.ny_total) +
-                part * NY;
-    float* dbp = jobs.db_partial + (size_t(split) * jobs.num_problems + prob) * jobs.nx + m;
+    const size_t slab = size_t(split) * jobs.prob_total + jobs.prob0 + prob;
+    float* dw = jobs.dw_partial + (slab * jobs.nx + m) * size_t(jobs.ny_total) + part * NY;
+    float* dbp = jobs.db_partial + slab * jobs.nx + m;
     if (ntiles > 0) {
       mbar_wait(done, 0);
       tc_fence_after();

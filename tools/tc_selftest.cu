@@ -205,6 +205,9 @@ static int test_colgemm(int rows, bool timing) {
     jobs.mblocks = NX / 128;
     jobs.nparts = 1;
     jobs.ny_total = NY;
+    jobs.prob0 = 0;
+    jobs.prob_total = nprob;
+    jobs.interleave = 0;
     jobs.splits = nsm / (nprob * jobs.mblocks);
     if (jobs.splits > tiles) jobs.splits = tiles;
     jobs.tiles_total = tiles;
