@@ -91,7 +91,9 @@ struct sirenb200_plan {
   CUtensorMap tm_act{}, tm_dz{}, tm_wstack{};
   bool fused_fwd = false;
   long long* dbg_timeline = nullptr;  // SIRENB200_TIMELINE=1: 3*4*8*16 clock64 slots (debug)
-  std::vector<CUtensorMap> tm_w, tm_wt;
+  std::vector<CUtensorMap> tm_w, tm_wt, tm_wt_half;
+  bool fused_bwd = false;      // one-pass dX + dW kernel per hidden layer (hidden = 256)
+  int bwd_pairs = 0;           // CTA pairs of that kernel (= partial slabs it writes)
   float* dw_part = nullptr;  // [splits][D-2][W][W]
   float* db_part = nullptr;  // [splits][D-2][W]
   int col_splits = 1;
@@ -385,10 +387,59 @@ int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const fl
   return 0;
 }
 
+int launch_bwd_layer(sirenb200_plan* p, int l, const Chunk& ch, cudaStream_t st) {
+  auto kfn = bwd_layer_kernel;
+  static bool attr_set[64] = {};
+  if (!attr_set[p->device & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  int(BwdCfg::SMEM_BYTES)));
+    attr_set[p->device & 63] = true;
+  }
+  BwdArgs ba{};
+  ba.num_tiles = ch.ntiles;
+  ba.dz_row0 = int(l * p->npix_pad + ch.p0);
+  ba.act_row0 = int((l - 1) * p->npix_pad + ch.p0);
+  ba.out_row0 = int((l - 1) * p->npix_pad + ch.p0);
+  ba.valid_rows = int(ch.npix);
+  ba.dw_partial = p->dw_part;
+  ba.db_partial = p->db_part;
+  ba.prob = l - 1;
+  ba.prob_total = p->D - 2;
+  {
+    ProfScope ps(p, PK_DX_GEMM, st);
+    kfn<<<2 * p->bwd_pairs, 256, BwdCfg::SMEM_BYTES, st>>>(
+        p->tm_dz, p->tm_act, p->tm_wt_half[l - 1], ba, umma_idesc(128, 128, 0, 0, 0, 0),
+        umma_idesc(128, 256, 0, 0, 1, 1), umma_idesc(128, 16, 0, 0, 1, 1));
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
 template <int W>
 int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
   const int nh = p->D - 2;
   constexpr int NPARTS = W / (W < 256 ? W : 256);
+  if (p->fused_bwd && W == 256 && p->nchunks == 1) {
+    for (int l = nh; l >= 1; --l) {
+      int rc = launch_bwd_layer(p, l, ch, st);
+      if (rc) return rc;
+    }
+    CoordSrc cs = p->coord;
+    cs.p_offset = ch.p0;
+    static bool l0_attr[64] = {};
+    if (!l0_attr[p->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(tc_layer0_grad_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(L0GradCfg<W>::SMEM_BYTES)));
+      l0_attr[p->device & 63] = true;
+    }
+    {
+      ProfScope ps(p, PK_L0_GRAD, st);
+      tc_layer0_grad_kernel<W><<<p->l0_grid, 256, L0GradCfg<W>::SMEM_BYTES, st>>>(
+          cs, p->dz + ch.p0 * W, p->l0_part + size_t(ch.index) * p->l0_grid * 3 * W, ch.npix);
+    }
+    LAUNCH_CHECK();
+    return 0;
+  }
   auto fill_jobs = [&](ColGemmJobs& jobs, int l_first, int nprob, int splits, int interleave) {
     jobs.num_problems = nprob;
     jobs.mblocks = W / 128;
@@ -787,8 +838,19 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     if (splits < 1) splits = 1;
     if (splits > p->ntiles) splits = p->ntiles;
     p->col_splits = splits;  // (re-clamped to the chunk size below)
-    ALLOC(p->dw_part, int64_t(splits) * (nh > 0 ? nh : 1) * W * W);
-    ALLOC(p->db_part, int64_t(splits) * (nh > 0 ? nh : 1) * W);
+    p->bwd_pairs = p->nsm / 2;
+    if (p->bwd_pairs > p->ntiles) p->bwd_pairs = p->ntiles;
+    {
+      // One-pass dX + dW kernel (tc_kernels.cuh: bwd_layer_kernel): correct, removes the split-K pass's
+      // 402 MB/layer re-read, but with a single 128 KB input buffer per CTA (smem is full) the
+      // load -> MMA -> epilogue chain is serial: measured 204 us/layer vs 174 us for dX + dW kernels.
+      // Opt-in (SIRENB200_FUSED_BWD=1) until a cta_group::2 version can double-buffer its inputs.
+      const char* env = getenv("SIRENB200_FUSED_BWD");
+      p->fused_bwd = (W == 256 && nh > 0) && (env && atoi(env) != 0);
+    }
+    const int slabs = (p->fused_bwd && p->bwd_pairs > splits) ? p->bwd_pairs : splits;
+    ALLOC(p->dw_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W * W);
+    ALLOC(p->db_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W);
     {
       // Row chunking (forward+backward per chunk so a chunk's stash is re-read from L2) is OFF by
       // default: measured on B200 at config 2 it loses (1.56 ms/step unchunked vs 2.0 ms with two
@@ -823,6 +885,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
         if (splits > p->col_splits) splits = p->col_splits;
         p->active_splits = splits;
       }
+      if (p->fused_bwd && p->nchunks == 1) p->active_splits = p->bwd_pairs;
     }
     const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
     p->last_grid = p->nsm * 2;
@@ -841,10 +904,12 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     trc |= make_tmap_16bit(&p->tm_dz, p->dz, uint64_t(D - 1) * p->npix_pad, W, 128, false);
     p->tm_w.resize(nh > 0 ? nh : 0);
     p->tm_wt.resize(nh > 0 ? nh : 0);
+    p->tm_wt_half.resize(nh > 0 ? nh : 0);
     for (int l = 0; l < nh; ++l) {
       const uint32_t brows = W < 256 ? W : 256;  // B box rows = output columns per work item
       trc |= make_tmap_16bit(&p->tm_w[l], p->wh + size_t(l) * W * W, W, W, brows, false);
       trc |= make_tmap_16bit(&p->tm_wt[l], p->wth + size_t(l) * W * W, W, W, brows, false);
+      trc |= make_tmap_16bit(&p->tm_wt_half[l], p->wth + size_t(l) * W * W, W, W, 128, false);
     }
     if (nh > 0) trc |= make_tmap_16bit(&p->tm_wstack, p->wh, uint64_t(nh) * W, W, W < 256 ? W : 256, false);
     if (trc) {

@@ -837,4 +837,249 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// fused backward step of one hidden layer l (hidden = 256):
+//     dz[l-1] = (dz[l] . omega W_l) (*) +-sqrt(1 - act[l-1]^2)          (the dX GEMM + cos epilogue)
+//     dW_l   += dz[l]^T . act[l-1],   db_l += sum_p dz[l]                (the pixel reduction)
+// from ONE pass over dz[l] and act[l-1]: the separate split-K pass (which re-reads both tensors,
+// 402 MB per layer at config 2) disappears.
+//
+// Work is split by FEATURE HALF, not only by pixels: CTA b handles half h = b & 1 of the features for the
+// 128-pixel tiles t = b/2, b/2 + grid/2, ...: it computes the 128 output columns [128h, 128h+128) of
+// dz[l-1] (UMMA M=128 px, N=128, K=256) and the 128 rows [128h, ..) of dW_l (UMMA M=128, N=256, K=128 px),
+// whose accumulator (256 TMEM columns) stays resident for the whole kernel.  CTAs 2j and 2j+1 load the
+// same two tiles at the same time, so the second read is served by L2.
+//   smem : omega W_l^T half (64 KiB, resident) | dz tile (4 chunks) | act tile (4 chunks) | 2 output chunks
+//   TMEM : dX accumulator 128 cols | dW accumulator 256 cols | db accumulator 16 cols
+// ------------------------------------------------------------------------------------------
+struct BwdArgs {
+  int num_tiles;       // 128-pixel tiles
+  int dz_row0;         // first row of dz[l] inside the dz tensor map
+  int act_row0;        // first row of act[l-1] inside the activation tensor map
+  int out_row0;        // first row of dz[l-1] inside the dz tensor map
+  int valid_rows;      // pixel rows >= valid_rows are written as zero
+  float* dw_partial;   // [pairs][prob_total][256][256] fp32 (slab = pair * prob_total + prob)
+  float* db_partial;   // [pairs][prob_total][256]
+  int prob;            // index of this layer inside the partial slabs
+  int prob_total;
+};
+
+struct BwdCfg {
+  static constexpr int W = 256;
+  static constexpr uint32_t OFF_B = 0;                       // 4 k-blocks of [128 x 64] = 64 KiB
+  static constexpr uint32_t OFF_D = 65536;                   // dz tile: 4 chunks
+  static constexpr uint32_t OFF_E = OFF_D + 4 * kChunkBytes; // act tile: 4 chunks
+  static constexpr uint32_t OFF_O = OFF_E + 4 * kChunkBytes; // output staging: 2 chunks
+  static constexpr uint32_t OFF_ONES = OFF_O + 2 * kChunkBytes;
+  static constexpr uint32_t OFF_BAR = OFF_ONES + 512;
+  static constexpr int NUM_BARS = 8;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t TM_DX = 0, TM_DW = 128, TM_DB = 384;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
+};
+
+__global__ void __launch_bounds__(256, 1)
+bwd_layer_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmAct,
+                 const __grid_constant__ CUtensorMap tmWt, const BwdArgs args, const uint32_t idesc_dx,
+                 const uint32_t idesc_dw, const uint32_t idesc_ones) {
+  using C = BwdCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* b_full = bars + 0;    // resident weights landed
+  uint64_t* in_full = bars + 1;   // dz + act tiles landed (128 KiB)
+  uint64_t* in_empty = bars + 2;  // 2 arrivals: all MMAs of the item retired + epilogue done with act
+  uint64_t* dx_full = bars + 3;   // dX accumulator complete
+  uint64_t* dx_empty = bars + 4;  // dX accumulator drained (4 epilogue warps)
+  uint64_t* dw_done = bars + 5;   // final: dW/db accumulators complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.x & 1;          // feature half of this CTA
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    mbar_init(b_full, 1);
+    mbar_init(in_full, 1);
+    mbar_init(in_empty, 2);
+    mbar_init(dx_full, 1);
+    mbar_init(dx_empty, 4);
+    mbar_init(dw_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmDz);
+    tma_prefetch_desc(&tmAct);
+    tma_prefetch_desc(&tmWt);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + C::OFF_ONES);
+    for (int i = threadIdx.x - 128; i < 128; i += 128) ones[i] = 0x3C003C00u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(b_full, 4 * kChunkBytes);
+      for (int kb = 0; kb < 4; ++kb)  // rows [128h, 128h+128) of omega W_l^T, k-block kb
+        tma_load_2d(smem + C::OFF_B + kb * kChunkBytes, &tmWt, b_full, kb * 64, h * 128);
+      uint32_t it = 0;
+      for (int t = pair; t < args.num_tiles; t += npairs, ++it) {
+        mbar_wait(in_empty, (it & 1u) ^ 1u);
+        mbar_expect_tx(in_full, 8 * kChunkBytes);
+        const int prow = t * kRowsPerTile;
+        for (int c = 0; c < 4; ++c)
+          tma_load_2d(smem + C::OFF_D + c * kChunkBytes, &tmDz, in_full, c * 64, args.dz_row0 + prow);
+        for (int c = 0; c < 4; ++c)
+          tma_load_2d(smem + C::OFF_E + c * kChunkBytes, &tmAct, in_full, c * 64,
+                      args.act_row0 + prow);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      const uint32_t b_addr = smem_u32(smem + C::OFF_B);
+      const uint32_t d_addr = smem_u32(smem + C::OFF_D);
+      const uint32_t e_addr = smem_u32(smem + C::OFF_E);
+      const uint64_t d_ones = umma_smem_desc(smem_u32(smem + C::OFF_ONES), 128, 256, 0);
+      uint32_t it = 0;
+      for (int t = pair; t < args.num_tiles; t += npairs, ++it) {
+        mbar_wait(in_full, it & 1u);
+        mbar_wait(dx_empty, (it & 1u) ^ 1u);
+        tc_fence_after();
+        // dX half: [128 px x 128] = dz tile (K-major, 4 k-blocks) x W^T half
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc(d_addr + kb * kChunkBytes + k * 32, 0, 1024, 2);
+            const uint64_t db = umma_smem_desc(b_addr + kb * kChunkBytes + k * 32, 0, 1024, 2);
+            umma_f16(tmem_base + C::TM_DX, da, db, idesc_dx, (kb | k) != 0 ? 1u : 0u);
+          }
+        umma_commit(dx_full);
+        // dW half / db half: A = dz columns [128h, 128h+128) read MN-major (chunks 2h, 2h+1),
+        // B = act tile read MN-major (4 chunks); K = the tile's 128 pixels in 8 steps of 16
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t dx =
+              umma_smem_desc(d_addr + 2 * h * kChunkBytes + k * 2048, kChunkBytes, 1024, 2);
+          const uint64_t dy = umma_smem_desc(e_addr + k * 2048, kChunkBytes, 1024, 2);
+          const uint32_t accum = (it | uint32_t(k)) != 0 ? 1u : 0u;
+          umma_f16(tmem_base + C::TM_DW, dx, dy, idesc_dw, accum);
+          umma_f16(tmem_base + C::TM_DB, dx, d_ones, idesc_ones, accum);
+        }
+        umma_commit(in_empty);  // every MMA that reads the tile buffers has retired
+      }
+      umma_commit(dw_done);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int r_in_tile = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 128);
+    uint32_t it = 0;
+    for (int t = pair; t < args.num_tiles; t += npairs, ++it) {
+      mbar_wait(in_full, it & 1u);  // the act chunks read below were written by TMA
+      mbar_wait(dx_full, it & 1u);
+      tc_fence_after();
+      const bool row_valid = (t * kRowsPerTile + r_in_tile) < args.valid_rows;
+      // the previous item's two output chunks must have been read by their TMA stores
+      if (issuer) tma_store_wait_read<0>();
+      named_bar_sync(1, 128);
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        const uint32_t e_row =
+            smem_u32(smem + C::OFF_E + (2 * h + nb) * kChunkBytes) + r_in_tile * 128;
+        const uint32_t o_row = smem_u32(smem + C::OFF_O + nb * kChunkBytes) + r_in_tile * 128;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DX + nb * 64 + hb * 32, v);
+          uint32_t e[16];
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
+            const uint4 ld = ld_shared_v4(e_row + (chunk << 4));
+            e[4 * c4 + 0] = ld.x;
+            e[4 * c4 + 1] = ld.y;
+            e[4 * c4 + 2] = ld.z;
+            e[4 * c4 + 3] = ld.w;
+          }
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float g0 = __uint_as_float(v[2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
+            float g1 = __uint_as_float(v[2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
+            if (!row_valid) g0 = g1 = 0.0f;
+            o[j] = pack_f16x2(g0, g1);
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
+            st_shared_v4(o_row + (chunk << 4), o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+          }
+        }
+      }
+      // accumulator drained and act chunks read: release both
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dx_empty);
+      named_bar_sync(1, 128);
+      if (issuer) {
+        mbar_arrive(in_empty);
+        for (int nb = 0; nb < 2; ++nb)
+          tma_store_2d(&tmDz, smem + C::OFF_O + nb * kChunkBytes, h * 128 + nb * 64,
+                       args.out_row0 + t * kRowsPerTile);
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+    // ---- final: this CTA's half of dW_l and db_l -> partial slab of its pair ----
+    const int m = h * 128 + r_in_tile;  // dW row (output feature of layer l)
+    const size_t slab = size_t(pair) * args.prob_total + args.prob;
+    float* dw = args.dw_partial + (slab * 256 + m) * size_t(256);
+    float* dbp = args.db_partial + slab * 256 + m;
+    if (pair < args.num_tiles) {
+      mbar_wait(dw_done, 0);
+      tc_fence_after();
+      for (int cb = 0; cb < 8; ++cb) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DW + cb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<uint4*>(dw + cb * 32)[j] =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      uint32_t b8[8];
+      tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DB, b8);
+      tmem_ld_wait();
+      *dbp = __uint_as_float(b8[0]);
+    } else {
+      for (int j = 0; j < 64; ++j) reinterpret_cast<uint4*>(dw)[j] = make_uint4(0, 0, 0, 0);
+      *dbp = 0.0f;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
 }  // namespace sb
