@@ -81,7 +81,8 @@ struct RowGemmCfg {
   static_assert(NDIM >= 16 && NDIM <= 256, "UMMA N range");
   static constexpr int KB = KDIM / 64;  // 64-wide K blocks
   static constexpr int NB = NDIM / 64;  // 64-wide output chunks
-  static constexpr int SA = 3;          // ring depth
+  // ring depth: 4 stages when the (resident-B, forward) configuration has the shared memory for it
+  static constexpr int SA = (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? 4 : 3;
   static constexpr int SEO = (MODE == MODE_DX) ? 3 : 2;  // epilogue in/out ring depth
   static constexpr uint32_t B_KB_BYTES = NDIM * 128;
   static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u);
