@@ -197,7 +197,7 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
-    kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
+    kfn<<<grid, 384, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
   }
   LAUNCH_CHECK();
   return 0;

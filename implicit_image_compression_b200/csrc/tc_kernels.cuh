@@ -110,7 +110,9 @@ struct RowGemmArgs {
 };
 
 template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1>
-__global__ void __launch_bounds__(256, 1)
+// 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue-input producer, 3 = spare, 4..11 = epilogue
+// (two warps per TMEM lane quadrant; each takes 32 of the 64 columns of every output chunk).
+__global__ void __launch_bounds__(384, 1)
 rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
                const RowGemmArgs args, const uint32_t idesc) {
@@ -144,7 +146,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tm_full[i], 1);
-      mbar_init(&tm_empty[i], 4);
+      mbar_init(&tm_empty[i], 8);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -158,7 +160,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (MODE == MODE_FWD && warp >= 4) {
     float* cst = reinterpret_cast<float*>(smem + C::OFF_CONST);
-    for (int i = threadIdx.x - 128; i < NDIM * NPARTS; i += 128) cst[i] = args.omega * args.bias[i];
+    for (int i = threadIdx.x - 128; i < NDIM * NPARTS; i += 256) cst[i] = args.omega * args.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -236,6 +238,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> f() -> smem -> TMA store =====================
     const int q = warp & 3;
+    const int hb = (warp - 4) >> 2;  // which 32 of the 64 columns of a chunk this warp handles
     const int r_in_tile = q * 32 + lane;
     const bool issuer = (threadIdx.x == 128);
     const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
@@ -254,8 +257,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&eo_full[s], ph);
         else
           mbar_wait(&eo_empty[s], ph ^ 1u);
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
+        {
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * NDIM + nb * 64 + hb * 32, v);
           tmem_ld_wait();
@@ -295,7 +297,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (issuer) {
           tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, part * NDIM + nb * 64,
                        args.o_row0 + t * kRowsPerTile);

@@ -93,17 +93,17 @@ static int test_rowgemm(int rows, bool timing) {
         using C = RowGemmCfg<W, W, MODE_FWD>;
         auto kfn = rowgemm_kernel<W, W, MODE_FWD, false>;
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        kfn<<<grid, 256, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
+        kfn<<<grid, 384, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
       } else if (mode == 1) {
         using C = RowGemmCfg<W, W, MODE_DX>;
         auto kfn = rowgemm_kernel<W, W, MODE_DX, false>;
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        kfn<<<grid, 256, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
+        kfn<<<grid, 384, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
       } else {
         using C = RowGemmCfg<W, W, MODE_DX>;
         auto kfn = rowgemm_kernel<W, W, MODE_DX, true>;
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        kfn<<<grid, 256, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
+        kfn<<<grid, 384, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
       }
     };
     launch();
