@@ -575,6 +575,14 @@ struct PrepArgs {
   const float* w0;                // layer 0 weight [W, 2] and bias [W]
   const float* b0;
   float omega0, omega_h;
+  // operands of the tensor-core last layer
+  const float* w_last;            // [C, W]
+  int C;
+  float omega_prev_last;          // omega of the layer feeding the last layer
+  __half* wl16;                   // [16, W]: rows < C = W_last, rest 0
+  __half* wlt16;                  // [W x 16] in UMMA no-swizzle K-major core-matrix order:
+                                  // element (n, k) at (n%8)*8 + (n/8)*128 + (k/8)*64 + (k%8) halves,
+                                  // value omega_prev * W_last[k, n] for k < C, else 0
   float4* tab0;                   // [W] (omega0*w_h, omega0*w_w, omega0*b0, 0)
   float* bias_w;                  // [nlayers][W] omega_h * bias
   float* bias_raw;                // [nlayers][W] bias
@@ -586,6 +594,17 @@ __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const PrepArgs a) 
   const int l = blockIdx.z;
   const float* w = a.w[l];
   const int W = a.W;
+  if (blockIdx.x == 1 % gridDim.x && blockIdx.y == 0 && l == 0 && a.wl16) {
+    for (int i = threadIdx.x; i < 16 * W; i += 256) {
+      const int c = i / W, n = i % W;
+      a.wl16[i] = __float2half_rn(c < a.C ? a.w_last[c * W + n] : 0.f);
+    }
+    for (int i = threadIdx.x; i < W * 16; i += 256) {
+      const int n = i / 16, c = i % 16;
+      const int off = (n % 8) * 8 + (n / 8) * 128 + (c / 8) * 64 + (c % 8);
+      a.wlt16[off] = __float2half_rn(c < a.C ? a.omega_prev_last * a.w_last[c * W + n] : 0.f);
+    }
+  }
   if (blockIdx.x == 0 && blockIdx.y == 0) {
     for (int i = threadIdx.x; i < W; i += 256) {
       a.bias_w[l * W + i] = a.omega_h * a.bias[l][i];

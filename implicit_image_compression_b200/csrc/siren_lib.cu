@@ -90,6 +90,10 @@ struct sirenb200_plan {
   float* bias_raw = nullptr;  // [(D-2)][W] bias (contiguous copy for the fused forward)
   CUtensorMap tm_act{}, tm_dz{}, tm_wstack{};
   bool fused_fwd = false;
+  __half* wl16 = nullptr;   // [16, W] last-layer weights for the tensor-core last layer
+  __half* wlt16 = nullptr;  // [W, 64]
+  CUtensorMap tm_wl{}, tm_wlt{};
+  bool last_tc = false;
   long long* dbg_timeline = nullptr;  // SIRENB200_TIMELINE=1: 3*4*8*16 clock64 slots (debug)
   std::vector<CUtensorMap> tm_w, tm_wt, tm_wt_half;
   bool fused_bwd = false;      // one-pass dX + dW kernel per hidden layer (hidden = 256)
@@ -275,6 +279,11 @@ int tc_prep(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* 
     pa.omega_h = p->cfg.hidden_omega;
     pa.tab0 = p->tab0;
     pa.bias_w = p->bias_w;
+    pa.w_last = prm[2 * (p->D - 1)];
+    pa.C = p->C;
+    pa.omega_prev_last = omega_of(p, p->D - 2);
+    pa.wl16 = p->last_tc ? p->wl16 : nullptr;
+    pa.wlt16 = p->wlt16;
     pa.bias_raw = p->bias_raw;
     {
       ProfScope ps(p, PK_PREP, st);
@@ -357,8 +366,48 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
 }
 
 template <int W>
+int launch_last_tc(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
+                   float* pred, const Chunk& ch, cudaStream_t st) {
+  if constexpr (W == 128 || W == 256) {
+    using Cfg = LastTcCfg<W>;
+    auto kfn = last_layer_tc_kernel<W>;
+    static bool attr_set[64] = {};
+    if (!attr_set[p->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(Cfg::SMEM_BYTES)));
+      attr_set[p->device & 63] = true;
+    }
+    const int D = p->D, C = p->C;
+    LastTcArgs la{};
+    la.num_tiles = ch.ntiles;
+    la.act_row0 = int((D - 2) * p->npix_pad + ch.p0);
+    la.dz_row0 = int((D - 2) * p->npix_pad + ch.p0);
+    la.npix = ch.npix;
+    la.b = prm[2 * (D - 1) + 1];
+    la.img = img_or_dpred ? img_or_dpred + ch.p0 * C : nullptr;
+    la.pred = pred ? pred + ch.p0 * C : nullptr;
+    la.part = p->last_part + size_t(ch.index) * p->last_grid * (C * W + C + 1);
+    la.gscale = p->gstate;
+    la.C = C;
+    la.mode = mode;
+    la.outermost_linear = p->cfg.outermost_linear;
+    la.omega_last = omega_of(p, D - 1);
+    la.dbg = p->dbg_timeline ? p->dbg_timeline + 3 * 4 * 8 * 16 : nullptr;
+    {
+      ProfScope ps(p, PK_LAST, st);
+      kfn<<<p->last_grid, 384, Cfg::SMEM_BYTES, st>>>(p->tm_act, p->tm_dz, p->tm_wl, p->wlt16, la);
+    }
+    LAUNCH_CHECK();
+    return 0;
+  } else {
+    return fail(SIRENB200_ERR_INVALID, "tensor-core last layer needs hidden 128 or 256");
+  }
+}
+
+template <int W>
 int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
                   float* pred, const Chunk& ch, cudaStream_t st) {
+  if (p->last_tc) return launch_last_tc<W>(p, prm, mode, img_or_dpred, pred, ch, st);
   const int D = p->D, C = p->C;
   LastArgs la{};
   la.act = p->act + (size_t(D - 2) * p->npix_pad + ch.p0) * W;
@@ -832,6 +881,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     ALLOC(p->wh, int64_t(nh > 0 ? nh : 1) * W * W);
     ALLOC(p->wth, int64_t(nh > 0 ? nh : 1) * W * W);
     ALLOC(p->tab0, W);
+    ALLOC(p->wl16, 16 * W);
+    ALLOC(p->wlt16, int64_t(W) * 64);
     ALLOC(p->bias_w, int64_t(nh > 0 ? nh : 1) * W);
     ALLOC(p->bias_raw, int64_t(nh > 0 ? nh : 1) * W);
     int splits = nh > 0 ? p->nsm / (nh * (W / 128) * (W / (W < 256 ? W : 256))) : 1;
@@ -888,8 +939,16 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       if (p->fused_bwd && p->nchunks == 1) p->active_splits = p->bwd_pairs;
     }
     const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
+    {
+      const char* env = getenv("SIRENB200_LAST_TC");
+      p->last_tc = (W == 128 || W == 256) && nh > 0 && !(env && atoi(env) == 0);
+    }
     p->last_grid = p->nsm * 2;
     if (int64_t(p->last_grid) * 8 > chunk_pad) p->last_grid = cdiv(chunk_pad, 8);
+    if (p->last_tc) {  // persistent tensor-core kernel: one CTA per SM (or per tile)
+      p->last_grid = p->nsm;
+      if (p->last_grid > p->chunk_tiles) p->last_grid = p->chunk_tiles;
+    }
     ALLOC(p->last_part, int64_t(p->nchunks) * p->last_grid * (C * W + C + 1));
     p->l0_grid = p->nsm * 2;
     if (p->l0_grid > p->chunk_tiles) p->l0_grid = p->chunk_tiles;
@@ -911,14 +970,17 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       trc |= make_tmap_16bit(&p->tm_wt[l], p->wth + size_t(l) * W * W, W, W, brows, false);
       trc |= make_tmap_16bit(&p->tm_wt_half[l], p->wth + size_t(l) * W * W, W, W, 128, false);
     }
+    if (p->last_tc) {
+      trc |= make_tmap_16bit(&p->tm_wl, p->wl16, 16, W, 16, false);
+    }
     if (nh > 0) trc |= make_tmap_16bit(&p->tm_wstack, p->wh, uint64_t(nh) * W, W, W < 256 ? W : 256, false);
     if (trc) {
       sirenb200_destroy(p);
       return fail(SIRENB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", trc);
     }
     if (getenv("SIRENB200_TIMELINE")) {
-      ALLOC(p->dbg_timeline, 3 * 4 * 8 * 16);
-      cudaMemset(p->dbg_timeline, 0, 3 * 4 * 8 * 16 * sizeof(long long));
+      ALLOC(p->dbg_timeline, 3 * 4 * 8 * 16 + 12 * 16);
+      cudaMemset(p->dbg_timeline, 0, (3 * 4 * 8 * 16 + 12 * 16) * sizeof(long long));
     }
     {
       // The fused multi-layer forward (tc_kernels.cuh: fused_fwd_kernel) is correct (same tests pass)
@@ -939,7 +1001,8 @@ int sirenb200_destroy(sirenb200_handle_t p) {
   void* ptrs[] = {p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
                   p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
                   p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
-                  p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline};
+                  p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline,
+                  p->wl16,   p->wlt16};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);

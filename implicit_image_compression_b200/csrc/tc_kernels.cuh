@@ -26,6 +26,7 @@ constexpr int kRowsPerTile = 128;
 constexpr uint32_t kChunkBytes = 128 * 128;  // one {64 x 128-row} fp16 box = 16 KiB
 constexpr float kInvPi = 0.318309886183790671538f;
 constexpr float kRoundMagic = 12582912.0f;  // 1.5 * 2^23: fp32 add rounds to integer, even LSB
+constexpr int kMaxOutTc = 4;                // output channels handled by the tensor-core last layer
 
 enum RowGemmMode { MODE_FWD = 0, MODE_DX = 1 };
 
@@ -1074,6 +1075,357 @@ bwd_layer_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant
     } else {
       for (int j = 0; j < 64; ++j) reinterpret_cast<uint4*>(dw)[j] = make_uint4(0, 0, 0, 0);
       *dbp = 0.0f;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// last layer on tensor cores (hidden <= 256, out <= 4): per 128-pixel tile, from ONE read of act[D-2]:
+//   y  = act . W_last^T (+ b)            UMMA M=128 px, N=16, K=W       -> pred, squared error, seed g
+//   dA = g . (omega W_last)              UMMA M=128 px, N=W,  K=16      -> dz[D-2] = dA (*) +-sqrt(1-a^2)
+//   dW_last^T += act^T . g               UMMA M=128 feat, N=16, K=128 px (act tile read MN-major)
+// The seed tile g (128 x 16 fp16, 4 KiB, no-swizzle core-matrix layout) is written once by the epilogue
+// and read twice: K-major as the A operand of dA and MN-major as the B operand of dW_last.
+// (reference: siren.py:64,110-118,131 last SineLayer + /2+0.5; train_helper.py:151-161 mse + backward)
+// ------------------------------------------------------------------------------------------
+struct LastTcArgs {
+  int num_tiles;
+  int act_row0;          // first row of act[D-2] inside the activation tensor map
+  int dz_row0;           // first row of dz[D-2] inside the dz tensor map
+  int64_t npix;          // valid pixels
+  const float* b;        // [C] last-layer bias
+  const float* img;      // mode 1: target [npix, C]; mode 2: dpred [npix, C]
+  float* pred;           // [npix, C] or null
+  float* part;           // per-CTA partials [grid][C*W + C + 1] (dW_last, db_last, sum sq err)
+  const float* gscale;   // device seed scale G
+  int C;
+  int mode;              // 0 forward only, 1 MSE, 2 external dpred
+  int outermost_linear;
+  float omega_last;
+  long long* dbg;        // optional timeline capture (block 0): dbg[tile * 16 + k], first 12 tiles
+};
+
+#define SB_DBG_L(tile_i, k)                                                 \
+  do {                                                                      \
+    if (args.dbg && blockIdx.x == 0 && (tile_i) < 12)                       \
+      args.dbg[(tile_i) * 16 + (k)] = clock64();                            \
+  } while (0)
+
+template <int W>
+struct LastTcCfg {
+  static_assert(W == 128 || W == 256, "tensor-core last layer: hidden 128 or 256");
+  static constexpr int NCH = W / 64;
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t STAGE_BYTES = NCH * kChunkBytes;       // act tile
+  static constexpr uint32_t OFF_ACT = 0;
+  static constexpr uint32_t OFF_WL = STAGES * STAGE_BYTES;          // [16 x W] fp16, NCH k-blocks of 2 KiB
+  static constexpr uint32_t OFF_WLT = OFF_WL + NCH * 2048;          // [W x 16] fp16, core-matrix order
+  static constexpr uint32_t WLT_BYTES = W * 32;
+  static constexpr uint32_t OFF_G = OFF_WLT + WLT_BYTES;            // seed tile 128 x 16 fp16
+  static constexpr uint32_t OFF_RED = OFF_G + 4096;                 // block reduction scratch
+  static constexpr uint32_t OFF_BAR = OFF_RED + 8 * 8 * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 5;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+  static constexpr uint32_t TM_Y = 0, TM_DW = 32, TM_DA = 64;       // TMEM columns
+  static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
+};
+
+template <int W>
+__global__ void __launch_bounds__(384, 1)
+last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmDz,
+                     const __grid_constant__ CUtensorMap tmWl, const __half* __restrict__ wlt_interleaved,
+                     const LastTcArgs args) {
+  using C = LastTcCfg<W>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* act_full = bars;                   // [STAGES]
+  uint64_t* act_empty = act_full + C::STAGES;  // [STAGES]
+  uint64_t* w_full = act_empty + C::STAGES;
+  uint64_t* y_full = w_full + 1;   // y accumulator complete
+  uint64_t* g_ready = y_full + 1;  // seed tile written (4 warps)
+  uint64_t* mma_done = g_ready + 1;  // dA and dW MMAs of the tile retired
+  uint64_t* fin_done = mma_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool train = args.mode != 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&act_full[i], 1);
+      mbar_init(&act_empty[i], 1);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(y_full, 1);
+    mbar_init(g_ready, 4);
+    mbar_init(mma_done, 1);
+    mbar_init(fin_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAct);
+    tma_prefetch_desc(&tmDz);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, C::NCH * 2048 + (train ? C::WLT_BYTES : 0));
+      for (int kb = 0; kb < C::NCH; ++kb)
+        tma_load_2d(smem + C::OFF_WL + kb * 2048, &tmWl, w_full, kb * 64, 0);
+      // omega W_last^T arrives already in the no-swizzle core-matrix order (prep kernel), 1-D bulk copy
+      if (train) bulk_load_1d(smem + C::OFF_WLT, wlt_interleaved, C::WLT_BYTES, w_full);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+        mbar_wait(&act_empty[s], ph ^ 1u);
+        mbar_expect_tx(&act_full[s], C::STAGE_BYTES);
+        for (int c = 0; c < C::NCH; ++c)
+          tma_load_2d(smem + C::OFF_ACT + s * C::STAGE_BYTES + c * kChunkBytes, &tmAct, &act_full[s],
+                      c * 64, args.act_row0 + t * kRowsPerTile);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t id_y = umma_idesc(128, 16, 0, 0, 0, 0);
+      const uint32_t id_da = umma_idesc(128, W, 0, 0, 0, 0);
+      const uint32_t id_dw = umma_idesc(128, 16, 0, 0, 1, 1);
+      const uint32_t wl_addr = smem_u32(smem + C::OFF_WL);
+      const uint32_t wlt_addr = smem_u32(smem + C::OFF_WLT);
+      const uint32_t g_addr = smem_u32(smem + C::OFF_G);
+      mbar_wait(w_full, 0);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+        const uint32_t a_addr = smem_u32(smem + C::OFF_ACT + s * C::STAGE_BYTES);
+        mbar_wait(&act_full[s], ph);
+        SB_DBG_L(it, 6);
+        tc_fence_after();
+        // y = act . W_last^T  (the epilogue of the previous tile has drained TM_Y: it waited mma_done,
+        // which was committed after that tile's y was consumed)
+#pragma unroll
+        for (int kb = 0; kb < C::NCH; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr + kb * kChunkBytes + k * 32, 0, 1024, 2);
+            const uint64_t db = umma_smem_desc(wl_addr + kb * 2048 + k * 32, 0, 1024, 2);
+            umma_f16(tmem_base + C::TM_Y, da, db, id_y, (kb | k) != 0 ? 1u : 0u);
+          }
+        umma_commit(y_full);
+        SB_DBG_L(it, 7);
+        // the epilogue has read y (and, when training, written the seed tile)
+        mbar_wait(g_ready, it & 1u);
+        SB_DBG_L(it, 8);
+        tc_fence_after();
+        if (train) {
+          // dA = g (K-major, no swizzle: LBO 128 between the two 8-wide K halves, SBO 256 between
+          // 8-row groups) . omega W_last^T (same core-matrix layout, 256 rows x K 16)
+          umma_f16(tmem_base + C::TM_DA, umma_smem_desc(g_addr, 128, 256, 0),
+                   umma_smem_desc(wlt_addr, 128, 256, 0), id_da, 0u);
+          // dW_last^T[feature, channel] += act^T . g : A = act tile MN-major, B = g MN-major
+          // (same bytes: LBO 256 between 8-pixel groups, SBO 128 between the two 8-channel halves)
+#pragma unroll
+          for (int mb = 0; mb < W / 128; ++mb)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t da =
+                  umma_smem_desc(a_addr + 2 * mb * kChunkBytes + k * 2048, kChunkBytes, 1024, 2);
+              const uint64_t db = umma_smem_desc(g_addr + k * 512, 256, 128, 0);
+              umma_f16(tmem_base + C::TM_DW + mb * 16, da, db, id_dw, (it | uint32_t(k)) != 0 ? 1u : 0u);
+            }
+          umma_commit(mma_done);
+          SB_DBG_L(it, 9);
+        }
+      }
+      umma_commit(fin_done);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps) =====================
+    const int q = warp & 3;
+    const int hb = (warp - 4) >> 2;
+    const int r_in_tile = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 128);
+    const float G = train ? *args.gscale : 1.f;
+    float bias[kMaxOutTc];
+#pragma unroll
+    for (int c = 0; c < kMaxOutTc; ++c) bias[c] = c < args.C ? args.b[c] : 0.f;
+    float sse = 0.f, dbs[kMaxOutTc] = {};
+    // the target (or upstream gradient) of this thread's row is fetched one tile ahead
+    float tgt_next[kMaxOutTc] = {};
+    auto fetch_target = [&](int tile) {
+      const int64_t pn = int64_t(tile) * kRowsPerTile + r_in_tile;
+#pragma unroll
+      for (int c = 0; c < kMaxOutTc; ++c)
+        tgt_next[c] = (train && hb == 0 && tile < args.num_tiles && pn < args.npix && c < args.C)
+                          ? args.img[pn * args.C + c]
+                          : 0.f;
+    };
+    fetch_target(blockIdx.x);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+      const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1u;
+      const int64_t p = int64_t(t) * kRowsPerTile + r_in_tile;
+      const bool row_valid = p < args.npix;
+      float tgt[kMaxOutTc];
+#pragma unroll
+      for (int c = 0; c < kMaxOutTc; ++c) tgt[c] = tgt_next[c];
+      fetch_target(t + gridDim.x);
+      const bool dbgw = (threadIdx.x == 128);
+      if (dbgw) SB_DBG_L(it, 0);
+      mbar_wait(y_full, it & 1u);
+      if (dbgw) SB_DBG_L(it, 1);
+      tc_fence_after();
+      if (hb == 0) {
+        uint32_t yv[8];
+        tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + C::TM_Y, yv);
+        tmem_ld_wait();
+        float g[kMaxOutTc];
+#pragma unroll
+        for (int c = 0; c < kMaxOutTc; ++c) {
+          g[c] = 0.f;
+          if (c < args.C && row_valid) {
+            const float z = __uint_as_float(yv[c]) + bias[c];
+            const float o = args.outermost_linear ? z : sinf(z * args.omega_last);
+            const float pr = o / 2 + 0.5f;
+            if (args.pred) args.pred[p * args.C + c] = pr;
+            if (args.mode == 1) {
+              const float d = pr - tgt[c];
+              sse += d * d;
+              g[c] = d * G;
+            } else if (args.mode == 2) {
+              g[c] = 0.5f * tgt[c] * G;
+            }
+            if (!args.outermost_linear) g[c] *= args.omega_last * cosf(z * args.omega_last);
+            dbs[c] += g[c];
+          }
+        }
+        if (train) {
+          // seed row -> core-matrix layout: 8 channels (16 B) at (r%8)*16 + (r/8)*256, next 8 at +128
+          const uint32_t ga = smem_u32(smem + C::OFF_G) + (r_in_tile & 7) * 16 + (r_in_tile >> 3) * 256;
+          st_shared_v4(ga, pack_f16x2(g[0], g[1]), pack_f16x2(g[2], g[3]), 0u, 0u);
+          st_shared_v4(ga + 128, 0u, 0u, 0u, 0u);
+          fence_proxy_async_smem();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_ready);
+      }
+      if (!train) {
+        // forward only: the stage can be reused as soon as y has been read by every warp
+        named_bar_sync(1, 256);
+        if (issuer) mbar_arrive(&act_empty[s]);
+        continue;
+      }
+      if (dbgw) SB_DBG_L(it, 2);
+      mbar_wait(&act_full[s], ph);  // the act tile read below was written by TMA
+      mbar_wait(mma_done, it & 1u);
+      if (dbgw) SB_DBG_L(it, 3);
+      tc_fence_after();
+      const uint32_t tile_addr = smem_u32(smem + C::OFF_ACT + s * C::STAGE_BYTES);
+#pragma unroll 1
+      for (int nb = 0; nb < C::NCH; ++nb) {
+        const uint32_t row_addr = tile_addr + nb * kChunkBytes + r_in_tile * 128;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DA + nb * 64 + hb * 32, v);
+        uint32_t e[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
+          const uint4 ld = ld_shared_v4(row_addr + (chunk << 4));
+          e[4 * c4 + 0] = ld.x;
+          e[4 * c4 + 1] = ld.y;
+          e[4 * c4 + 2] = ld.z;
+          e[4 * c4 + 3] = ld.w;
+        }
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float g0 = __uint_as_float(v[2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
+          float g1 = __uint_as_float(v[2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
+          if (!row_valid) g0 = g1 = 0.0f;
+          o[j] = pack_f16x2(g0, g1);
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
+          st_shared_v4(row_addr + (chunk << 4), o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+        }
+      }
+      if (dbgw) SB_DBG_L(it, 4);
+      tc_fence_before();
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (dbgw) SB_DBG_L(it, 5);
+      if (issuer) {
+        for (int nb = 0; nb < C::NCH; ++nb)
+          tma_store_2d(&tmDz, smem + C::OFF_ACT + s * C::STAGE_BYTES + nb * kChunkBytes, nb * 64,
+                       args.dz_row0 + t * kRowsPerTile);
+        tma_store_commit();
+        // the previous tile's stores have been read out of their stage: hand it back to the producer
+        if (it > 0) {
+          tma_store_wait_read<1>();
+          mbar_arrive(&act_empty[(it - 1) % C::STAGES]);
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+    // ---- per-CTA partials: db_last / squared error (block reduction), dW_last from TMEM ----
+    float* out = args.part + int64_t(blockIdx.x) * (args.C * W + args.C + 1);
+    float* red = reinterpret_cast<float*>(smem + C::OFF_RED);  // [8 warps][8]
+    if (train) {
+      float vals[kMaxOutTc + 1];
+#pragma unroll
+      for (int c = 0; c < kMaxOutTc; ++c) vals[c] = dbs[c];
+      vals[kMaxOutTc] = sse;
+#pragma unroll
+      for (int k = 0; k <= kMaxOutTc; ++k) {
+        float x = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[(warp - 4) * 8 + k] = x;
+      }
+      named_bar_sync(1, 256);
+      if (threadIdx.x - 128 <= unsigned(args.C)) {
+        const int k = int(threadIdx.x) - 128;
+        const int idx = k < args.C ? k : kMaxOutTc;
+        float x = 0.f;
+        for (int w8 = 0; w8 < 8; ++w8) x += red[w8 * 8 + idx];
+        out[args.C * W + k] = x;  // db_last[0..C-1], then the squared error
+      }
+      if (hb == 0) {
+        const bool any = int(blockIdx.x) < args.num_tiles;
+        if (any) {
+          mbar_wait(fin_done, 0);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int mb = 0; mb < W / 128; ++mb) {
+          uint32_t dv[8] = {};
+          if (any) {
+            tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DW + mb * 16, dv);
+            tmem_ld_wait();
+          }
+          for (int c = 0; c < args.C; ++c) out[c * W + mb * 128 + r_in_tile] = __uint_as_float(dv[c]);
+        }
+      }
     }
   }
 
