@@ -224,7 +224,6 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
-    fitter.engine.profile(True)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -236,9 +235,25 @@ def run_gpu_arm(args):
     t1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
+    if fitter._graph is not None:
+        # graph replays re-issue the launches captured once: count them per replayed step
+        launches = args.steps * fitter.launches_per_step
+    clocks = sampler.stop(t0, t1)
+    # per-kernel device times: an immediately following EAGER pass of the same K steps with cudaEvent
+    # pairs around every library kernel (events cannot be timed inside a replayed graph)
+    graph_mode = fitter.use_graph
+    fitter.use_graph = False
+    fitter.engine.profile(True)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    pe0.record()
+    fitter.steps(args.steps)
+    pe1.record()
+    barrier()
+    ms_eager = pe0.elapsed_time(pe1)
     prof = fitter.engine.profile_read()
     fitter.engine.profile(False)
-    clocks = sampler.stop(t0, t1)
+    fitter.use_graph = graph_mode
     if world > 1:
         tms = torch.tensor([ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -326,7 +341,9 @@ def run_gpu_arm(args):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm"],
                     "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
                     "avg_launch_ms": avg_ms, "launches": kinds[dom][1], "peak_source": peaks["source"],
-                    "share_of_step": kinds[dom][0] / ms}
+                    "share_of_step": kinds[dom][0] / ms_eager,
+                    "note": "kernel timed with cudaEvent pairs in an eager pass of the same K steps run "
+                            "right after the (CUDA-graph) timed region"}
     step_tflops = f_step(H * W) * value / 1e12
     tpeak = (peaks["bf16_sustained"] or peaks["bf16"]) * world
     roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": tpeak,
@@ -345,7 +362,8 @@ def run_gpu_arm(args):
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
         "data": "synthetic", "config": workload_config(world),
-        "final_loss": float(losses[-1].item()),
+        "final_loss": float(losses[-1].item()), "cuda_graph": bool(graph_mode and fitter._graph is not None),
+        "ms_per_step_eager_profiled": ms_eager / args.steps,
         "roofline": roofline, "roofline_step": roofline_step, "kernel_ms": kernel_ms,
         "cpu_baseline": None if cpu_val is None else
         {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_desc},

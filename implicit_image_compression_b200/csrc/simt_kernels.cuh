@@ -793,15 +793,15 @@ struct AdamArgs {
   const float* skip_flag;
   int zero_grad;
   // device-driven schedule (graph replay): when non-null, step_size / bc2_sqrt are read from here
-  const float* dev_sched;  // [0] step_size, [1] bc2_sqrt
+  const double* dev_sched;  // [0] step_size, [1] bc2_sqrt
 };
 __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamArgs a) {
   int t = 0;
   while (t + 1 < a.ntensors && int(blockIdx.x) >= a.chunk_begin[t + 1]) ++t;
   const int base = (blockIdx.x - a.chunk_begin[t]) * 1024;
   const bool skip = a.skip_flag && (*a.skip_flag != 0.f);
-  const float step_size = a.dev_sched ? a.dev_sched[0] : a.step_size;
-  const float bc2_sqrt = a.dev_sched ? a.dev_sched[1] : a.bc2_sqrt;
+  const float step_size = a.dev_sched ? float(a.dev_sched[0]) : a.step_size;
+  const float bc2_sqrt = a.dev_sched ? float(a.dev_sched[1]) : a.bc2_sqrt;
   float* P = a.p[t];
   float* G = a.g[t];
   float* M = a.m[t];
@@ -826,6 +826,31 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamArgs a) {
     P[i] = p;
     if (a.zero_grad) G[i] = 0.f;
   }
+}
+
+// Device-side optimiser schedule (CUDA-graph replay: nothing that changes per step may be a launch
+// argument).  One thread: computes this step's Adam step size / bias correction from the device step
+// counter, records the loss of the step that just ran, advances the counter.
+//   state (doubles, so the host's double-precision schedule arithmetic is reproduced exactly):
+//   [0] step, [1] lr0, [2] gamma, [3] period, [4] beta1, [5] beta2, [6] out step_size, [7] out bc2_sqrt
+struct SchedArgs {
+  double* state;
+  const float* stats;   // [0] sum sq err, [1] loss
+  float inv_count;      // >0: loss = stats[0] * inv_count (pixel-sharded fits), else stats[1]
+  float* loss_ring;
+  int ring_len;
+};
+__global__ void sched_step_kernel(const SchedArgs a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int step = int(a.state[0]);  // 0-based index of the optimiser step about to run
+  // (the eager path hands lr to the library as a C float: reproduce that rounding)
+  const double lr = double(float(a.state[1] * pow(a.state[2], double(step / int(a.state[3])))));
+  const double bc1 = 1.0 - pow(double(float(a.state[4])), double(step + 1));  // betas arrive as C floats
+  const double bc2 = 1.0 - pow(double(float(a.state[5])), double(step + 1));  // on the eager path too
+  a.state[6] = lr / bc1;
+  a.state[7] = sqrt(bc2);
+  if (a.loss_ring) a.loss_ring[step % a.ring_len] = a.inv_count > 0.f ? a.stats[0] * a.inv_count : a.stats[1];
+  a.state[0] = double(step + 1);
 }
 
 __global__ void apply_mask_kernel(float* w, const float* mask, int64_t n) {

@@ -1190,6 +1190,53 @@ int sirenb200_adam_step(int32_t nt, float* const* prm, float* const* grads, floa
   return 0;
 }
 
+int sirenb200_sched_step(double* state, const float* stats, float inv_count, float* loss_ring,
+                         int32_t ring_len, sirenb200_stream_t stream) {
+  if (!state || !stats) return fail(SIRENB200_ERR_INVALID, "null argument");
+  SchedArgs a{state, stats, inv_count, loss_ring, ring_len > 0 ? ring_len : 1};
+  sched_step_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int sirenb200_adam_step_dev(int32_t nt, float* const* prm, float* const* grads, float* const* m,
+                            float* const* v, const float* const* mask, const int64_t* numel,
+                            float beta1, float beta2, float eps, const double* sched_state,
+                            float inv_scale, const float* skip_flag, int32_t zero_grad,
+                            sirenb200_stream_t stream) {
+  if (nt < 1 || nt > kMaxTensors) return fail(SIRENB200_ERR_INVALID, "tensor count %d", nt);
+  if (!prm || !grads || !m || !v || !numel || !sched_state)
+    return fail(SIRENB200_ERR_INVALID, "bad argument");
+  AdamArgs a{};
+  int chunks = 0;
+  for (int i = 0; i < nt; ++i) {
+    a.p[i] = prm[i];
+    a.g[i] = grads[i];
+    a.m[i] = m[i];
+    a.v[i] = v[i];
+    a.mask[i] = mask ? mask[i] : nullptr;
+    if (numel[i] < 0 || numel[i] > 0x7fffffff) return fail(SIRENB200_ERR_INVALID, "numel");
+    a.n[i] = int(numel[i]);
+    a.chunk_begin[i] = chunks;
+    chunks += cdiv(numel[i], 1024);
+  }
+  a.chunk_begin[nt] = chunks;
+  a.ntensors = nt;
+  a.beta1 = beta1;
+  a.beta2 = beta2;
+  a.eps = eps;
+  a.omb1 = float(1.0 - double(beta1));
+  a.omb2 = float(1.0 - double(beta2));
+  a.inv_scale = inv_scale;
+  a.skip_flag = skip_flag;
+  a.zero_grad = zero_grad;
+  a.dev_sched = sched_state + 6;  // [6] step_size, [7] bc2_sqrt
+  if (chunks == 0) return 0;
+  adam_multi_kernel<<<chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int sirenb200_apply_mask(float* w, const float* mask, int64_t n, sirenb200_stream_t stream) {
   if (!w || !mask || n < 0) return fail(SIRENB200_ERR_INVALID, "bad argument");
   if (n == 0) return 0;

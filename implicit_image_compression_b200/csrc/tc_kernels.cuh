@@ -83,8 +83,12 @@ struct RowGemmCfg {
   static constexpr int KB = KDIM / 64;  // 64-wide K blocks
   static constexpr int NB = NDIM / 64;  // 64-wide output chunks
   // ring depth: 4 stages when the (resident-B, forward) configuration has the shared memory for it
-  static constexpr int SA = (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? 4 : 3;
-  static constexpr int SEO = (MODE == MODE_DX) ? 3 : 2;  // epilogue in/out ring depth
+#ifndef SB_FWD_SA
+#define SB_FWD_SA 4
+#define SB_FWD_SEO 2
+#endif
+  static constexpr int SA = (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
+  static constexpr int SEO = (MODE == MODE_DX) ? 3 : ((KDIM * NDIM * 2 <= 131072) ? SB_FWD_SEO : 2);  // epilogue in/out ring depth
   static constexpr uint32_t B_KB_BYTES = NDIM * 128;
   static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u);
   static constexpr uint32_t A_STAGE = kChunkBytes + (STREAM_B ? B_KB_BYTES : 0u);

@@ -5,17 +5,28 @@ device->host sync per step).  `Fitter.steps(k)` runs k steps back to back on the
 backward, (optional) gradient all-reduce for pixel-sharded fits, fused Adam (+mask), StepLR — and returns
 the per-step losses as a DEVICE tensor; nothing blocks until the caller reads it.  Mask topology updates
 (every `interval` steps) run host-side torch exactly where the reference runs them.
+
+When nothing on the step needs the host (dense fit or dense-gradient masks, no quantisation transforms), ONE
+step is captured in a CUDA graph and replayed: the learning-rate schedule, Adam's bias correction and the
+loss history live in device memory (sirenb200_sched_step / sirenb200_adam_step_dev), so the ~16 kernel
+launches of a step cost one graph launch.  This matters most for pixel-sharded fits, where a rank's kernels
+are only a few microseconds long.
 """
+import ctypes
+import os
+
 import torch
 
 from . import _lib
 from .parallel import FlatGrads, shard_rows
 from .utils.train_helper import FusedAdam
 
+_RING = 1 << 14
+
 
 class Fitter:
     def __init__(self, model, optim, grid, img, lr_scheduler=None, mask=None, masking_cfg=None,
-                 rank=0, world_size=1, group=None):
+                 rank=0, world_size=1, group=None, use_graph=None):
         if not isinstance(optim, FusedAdam):
             raise _lib.SirenB200Error("Fitter needs the FusedAdam from get_optimizer_lr_scheduler")
         _lib.require_cuda(grid, "grid")
@@ -32,20 +43,26 @@ class Fitter:
         self.flat.attach()
         self.inv_count = 1.0 / float(img.numel())
         self.step_index = 0
+        if use_graph is None:
+            use_graph = os.environ.get("SIRENB200_GRAPH", "1") != "0"
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._graph_key = None
+        self.launches_per_step = 0  # library kernels per fit step (measured on the eager capture run)
 
-    def steps(self, k):
-        """Run k fit steps; returns a device tensor [k] with each step's (pre-update) loss."""
+    # ------------------------------------------------------------------ eager path
+    def _eager_steps(self, k, losses, offset):
         model, optim, flat = self.model, self.optim, self.flat
-        model.train()
-        losses = torch.empty(k, dtype=torch.float32, device=self.img.device)
         for i in range(k):
             model.run_weight_transforms()
             self.engine.forward_backward(model.kernel_parameters(), self.img, flat.views, flat.stats)
+            for fn in model._post_backward:
+                fn(model)
             if self.world > 1:
                 flat.all_reduce(self.group)
-                losses[i] = flat.stats[0] * self.inv_count
+                losses[offset + i] = flat.stats[0] * self.inv_count
             else:
-                losses[i:i + 1].copy_(flat.stats[1:2], non_blocking=True)
+                losses[offset + i:offset + i + 1].copy_(flat.stats[1:2], non_blocking=True)
             optim.skip_flag = flat.stats[2:3]
             if self.mask:
                 self.mask.step()
@@ -53,9 +70,149 @@ class Fitter:
                 optim.step()
             if self.sched:
                 self.sched.step()
+
+    # ------------------------------------------------------------------ graph path
+    def _graph_eligible(self):
+        m, opt = self.model, self.optim
+        if not self.use_graph or m._weight_transforms or m._post_backward or m._param_override:
+            return False
+        if self.mask is not None and not self.mask.dense_gradients:
+            return False
+        if len(opt.param_groups) != 1:
+            return False
+        steps_done = opt.param_groups[0].get("_fused_step", 0)
+        if self.sched is not None:
+            if type(self.sched).__name__ != "StepLR" or self.sched.last_epoch != steps_done:
+                return False
+        return True
+
+    def _graph_body(self):
+        lib, flat, g = self.engine.lib, self.flat, self._g
+        self.engine.forward_backward(self.model.kernel_parameters(), self.img, flat.views, flat.stats)
+        if self.world > 1:
+            flat.all_reduce(self.group)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.sirenb200_sched_step(g["state"].data_ptr(), flat.stats.data_ptr(),
+                                            self.inv_count if self.world > 1 else 0.0,
+                                            g["ring"].data_ptr(), _RING, stream))
+        _lib.check(lib.sirenb200_adam_step_dev(
+            g["n"], g["p"], g["g"], g["m"], g["v"], g["mask"], g["numel"], g["beta1"], g["beta2"],
+            g["eps"], g["state"].data_ptr(), 1.0, flat.stats[2:3].data_ptr(), 0, stream))
+
+    def _prepare_graph(self):
+        opt = self.optim
+        group = opt.param_groups[0]
+        params = [p for p in group["params"]]
+        for p in params:
+            opt._ensure_state(p)
+        key = tuple(p.data_ptr() for p in params) + (self.img.data_ptr(),)
+        if self._graph is not None and key == self._graph_key:
+            return
+        beta1, beta2 = group["betas"]
+        dev = self.img.device
+        masks = None
+        mask_bufs = {}
+        if self.mask is not None:
+            for n, w in self.mask._masked_parameters():
+                mask_bufs[w] = self.mask.mask_dict[n].clone()
+            masks = _lib.ptr_array([mask_bufs.get(p) for p in params])
+        n = len(params)
+        self._g = {
+            "state": torch.zeros(8, dtype=torch.float64, device=dev),
+            "ring": torch.zeros(_RING, dtype=torch.float32, device=dev),
+            "n": n, "p": _lib.ptr_array([p.data for p in params]),
+            "g": _lib.ptr_array([p.grad for p in params]),
+            "m": _lib.ptr_array([opt.state[p]["exp_avg"] for p in params]),
+            "v": _lib.ptr_array([opt.state[p]["exp_avg_sq"] for p in params]),
+            "mask": masks, "mask_bufs": mask_bufs,
+            "numel": (ctypes.c_int64 * n)(*[p.numel() for p in params]),
+            "beta1": float(beta1), "beta2": float(beta2), "eps": float(group["eps"]),
+        }
+        self._sync_sched_state()
+        # one eager run of the body (a real step) initialises everything lazily created, then capture
+        self._graph = None
+        self._graph_key = key
+
+    def _sync_sched_state(self):
+        group = self.optim.param_groups[0]
+        steps_done = group.get("_fused_step", 0)
+        if self.sched is not None:
+            lr0, gamma, period = self.sched.base_lrs[0], self.sched.gamma, self.sched.step_size
+        else:
+            lr0, gamma, period = group["lr"], 1.0, 1 << 30
+        beta1, beta2 = group["betas"]
+        self._g["state"].copy_(torch.tensor([float(steps_done), lr0, gamma, float(period), beta1, beta2,
+                                             0.0, 0.0], dtype=torch.float64))
+
+    def _advance_host(self, k):
+        group = self.optim.param_groups[0]
+        group["_fused_step"] = group.get("_fused_step", 0) + k
+        if self.sched is not None:
+            self.sched.last_epoch += k
+            lr = self.sched.base_lrs[0] * self.sched.gamma ** (self.sched.last_epoch // self.sched.step_size)
+            group["lr"] = lr
+            self.sched._last_lr = [lr]
+        if self.mask is not None:
+            for _ in range(k):  # host bookkeeping of Masking.step (core.py:690-702)
+                decay = self.mask.prune_rate_decay
+                if decay.mode == "cumulative":
+                    decay.step(self.mask.mask_step, 1 - self.mask.stats.total_density)
+                else:
+                    decay.step(self.mask.mask_step)
+                self.mask.mask_step += 1
+
+    def _graph_steps(self, k, losses, offset):
+        self._prepare_graph()
+        g = self._g
+        if self.mask is not None:  # masks may have been replaced by update_connections()
+            for n, w in self.mask._masked_parameters():
+                g["mask_bufs"][w].copy_(self.mask.mask_dict[n])
+        group = self.optim.param_groups[0]
+        step0 = group.get("_fused_step", 0)
+        done = 0
+        self._sync_sched_state()
+        if self._graph is None:
+            n0 = _lib.launch_count()
+            self._graph_body()  # eager: counts as a step
+            self.launches_per_step = _lib.launch_count() - n0
+            done = 1
+            if k > 1:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._graph_body()
+                # the capture itself does not execute anything
+                self._graph = graph
+        while done < k:
+            self._graph.replay()
+            done += 1
+        idx = (torch.arange(k, device=losses.device) + step0) % _RING
+        losses[offset:offset + k] = g["ring"][idx]
+        self._advance_host(k)
+
+    # ------------------------------------------------------------------ public
+    def steps(self, k):
+        """Run k fit steps; returns a device tensor [k] with each step's (pre-update) loss."""
+        self.model.train()
+        losses = torch.empty(k, dtype=torch.float32, device=self.img.device)
+        done = 0
+        while done < k:
+            # segment up to (and including) the next topology update
+            seg = k - done
+            update_after = False
             if self.mask and self.masking_cfg is not None:
-                if self.step_index <= self.masking_cfg["end_when"] and \
-                        self.step_index % self.masking_cfg["interval"] == 0:
-                    self.mask.update_connections()
-            self.step_index += 1
+                interval, end_when = self.masking_cfg["interval"], self.masking_cfg["end_when"]
+                nxt = self.step_index + ((-self.step_index) % interval)  # next multiple of interval
+                if nxt <= end_when and nxt - self.step_index + 1 <= seg:
+                    seg = nxt - self.step_index + 1
+                    update_after = True
+            seg = min(seg, _RING)
+            if self._graph_eligible():
+                self._graph_steps(seg, losses, done)
+            else:
+                self._eager_steps(seg, losses, done)
+            self.step_index += seg
+            done += seg
+            if update_after:
+                self.mask.update_connections()
         return losses

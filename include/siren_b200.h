@@ -104,6 +104,21 @@ int sirenb200_adam_step(int32_t n_tensors, float* const* h_params, float* const*
                         float beta2, float eps, int32_t step, float inv_scale, const float* skip_flag,
                         int32_t zero_grad, sirenb200_stream_t stream);
 
+/* CUDA-graph friendly variants: every per-step quantity lives in device memory so that ONE captured fit step
+ * can be replayed.  sched_state is 8 doubles: [0] step (0-based index of the next optimiser step), [1] base lr,
+ * [2] StepLR gamma, [3] StepLR period, [4] beta1, [5] beta2, [6]/[7] outputs (step size, sqrt(1-beta2^t)).
+ * sirenb200_sched_step computes [6],[7] for the step about to run (train_helper.py:80-84 StepLR + Adam bias
+ * correction), stores the loss of the step that just ran into loss_ring[step % ring_len] (stats[1], or
+ * stats[0]*inv_count when inv_count > 0, i.e. after an all-reduce of pixel shards) and increments [0];
+ * sirenb200_adam_step_dev is sirenb200_adam_step reading the schedule from sched_state. */
+int sirenb200_sched_step(double* sched_state, const float* stats, float inv_count, float* loss_ring,
+                         int32_t ring_len, sirenb200_stream_t stream);
+int sirenb200_adam_step_dev(int32_t n_tensors, float* const* h_params, float* const* h_grads,
+                            float* const* h_exp_avg, float* const* h_exp_avg_sq,
+                            const float* const* h_mask, const int64_t* h_numel, float beta1, float beta2,
+                            float eps, const double* sched_state, float inv_scale, const float* skip_flag,
+                            int32_t zero_grad, sirenb200_stream_t stream);
+
 /* Masking.apply_mask for one tensor (pipeline/masking/core.py:272-279): w <- w * mask (bit-exact). */
 int sirenb200_apply_mask(float* w, const float* mask, int64_t n, sirenb200_stream_t stream);
 
