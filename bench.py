@@ -200,6 +200,11 @@ def run_gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    # NCCL prints its version banner on STDOUT at communicator creation: keep stdout clean for the one
+    # JSON line by pointing fd 1 at stderr until the warm-up (first collective) is over
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -221,6 +226,9 @@ def run_gpu_arm(args):
     # ---- device-resident throughput -----------------------------------------------------------
     fitter.steps(max(3, args.warmup))
     barrier()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
@@ -311,9 +319,19 @@ def run_gpu_arm(args):
                "note": "Fitter.steps(1) per step on every rank; each rank copies its image rows from pinned "
                        "host memory and reads the all-reduced loss back every step (max over ranks)"}
 
-    if rank != 0:
+    def finish():
+        # Tear-down: drop the captured graph (it holds NCCL kernels) before leaving, and leave without
+        # running NCCL's destructor chain — destroy_process_group() after a captured collective can hang.
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            fitter._graph = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peaks = load_peaks()
@@ -370,8 +388,7 @@ def run_gpu_arm(args):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

@@ -123,3 +123,36 @@ def test_c2_short_fit_psnr_tracks_fp32_path():
     np.testing.assert_allclose(psnr["f16tc"][1], psnr["fp32"][1], rtol=2e-2)
     assert abs(psnr["f16tc"][0] - psnr["fp32"][0]) <= 0.1, psnr
     assert psnr["f16tc"][0] > 15.0
+
+
+def test_fitter_graph_with_masks_matches_reference_loop():
+    """Fitter (CUDA-graph segments between topology updates, masks applied inside the captured Adam)
+    follows the reference loop train_epoch(mask=...) + update_connections() exactly."""
+    get_grid, synth_image, Fitter, Siren, th = _pkg()
+    H, W = 48, 64
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    cfg = dict(name="RigL", density=0.5, sparse_init="erdos-renyi-kernel", dense_gradients=True,
+               growth_mode="absolute-gradient", prune_mode="magnitude", redistribution_mode="none",
+               dense=False, prune_rate=0.1, decay_schedule="cosine", end_when=30, interval=5)
+    out = []
+    for use_fitter in (False, True):
+        torch.manual_seed(0)
+        model = Siren(depth=4, hidden_size=128, first_omega_0=50, hidden_omega_0=30).cuda()
+        optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
+        torch.manual_seed(7)
+        mask = th.setup_mask(model, optim, cfg)
+        if use_fitter:
+            f = Fitter(model, optim, grid, img, sched, mask, cfg)
+            losses = torch.cat([f.steps(13), f.steps(12)]).tolist()
+        else:
+            losses = []
+            for i in range(25):
+                losses.append(th.train_epoch(model, optim, grid, img, lr_scheduler=sched, mask=mask))
+                if i <= cfg["end_when"] and i % cfg["interval"] == 0:
+                    mask.update_connections()
+        out.append((losses, {n: m.clone() for n, m in mask.mask_dict.items()}, mask.mask_step,
+                    mask.prune_rate))
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-6)
+    for n in out[0][1]:
+        assert torch.equal(out[0][1][n], out[1][1][n]), n
+    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
