@@ -48,6 +48,8 @@ class Fitter:
         self.use_graph = bool(use_graph)
         self._graph = None
         self._graph_key = None
+        self._warmed = False
+        self._dev_state = None  # schedule state the device holds (skip the upload when unchanged)
         self.launches_per_step = 0  # library kernels per fit step (measured on the eager capture run)
 
     # ------------------------------------------------------------------ eager path
@@ -102,12 +104,12 @@ class Fitter:
     def _prepare_graph(self):
         opt = self.optim
         group = opt.param_groups[0]
-        params = [p for p in group["params"]]
+        params = group["params"]
+        key = tuple(p.data_ptr() for p in params) + (self.img.data_ptr(),)
+        if key == self._graph_key:
+            return
         for p in params:
             opt._ensure_state(p)
-        key = tuple(p.data_ptr() for p in params) + (self.img.data_ptr(),)
-        if self._graph is not None and key == self._graph_key:
-            return
         beta1, beta2 = group["betas"]
         dev = self.img.device
         masks = None
@@ -128,6 +130,7 @@ class Fitter:
             "numel": (ctypes.c_int64 * n)(*[p.numel() for p in params]),
             "beta1": float(beta1), "beta2": float(beta2), "eps": float(group["eps"]),
         }
+        self._dev_state = None
         self._sync_sched_state()
         # one eager run of the body (a real step) initialises everything lazily created, then capture
         self._graph = None
@@ -141,8 +144,10 @@ class Fitter:
         else:
             lr0, gamma, period = group["lr"], 1.0, 1 << 30
         beta1, beta2 = group["betas"]
-        self._g["state"].copy_(torch.tensor([float(steps_done), lr0, gamma, float(period), beta1, beta2,
-                                             0.0, 0.0], dtype=torch.float64))
+        want = (float(steps_done), lr0, gamma, float(period), beta1, beta2)
+        if want != self._dev_state:
+            self._g["state"].copy_(torch.tensor(want + (0.0, 0.0), dtype=torch.float64))
+            self._dev_state = want
 
     def _advance_host(self, k):
         group = self.optim.param_groups[0]
@@ -162,6 +167,8 @@ class Fitter:
                 self.mask.mask_step += 1
 
     def _graph_steps(self, k, losses, offset):
+        """k steps on the device-scheduled path; losses=None (k must be 1) returns that step's loss as a
+        Python float instead of storing it (train_epoch's contract: one device->host read per step)."""
         self._prepare_graph()
         g = self._g
         if self.mask is not None:  # masks may have been replaced by update_connections()
@@ -172,11 +179,13 @@ class Fitter:
         done = 0
         self._sync_sched_state()
         if self._graph is None:
-            n0 = _lib.launch_count()
-            self._graph_body()  # eager: counts as a step
-            self.launches_per_step = _lib.launch_count() - n0
-            done = 1
-            if k > 1:
+            if not self._warmed:
+                n0 = _lib.launch_count()
+                self._graph_body()  # eager: counts as a step
+                self.launches_per_step = _lib.launch_count() - n0
+                self._warmed = True
+                done = 1
+            if done < k:
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
@@ -186,14 +195,34 @@ class Fitter:
         while done < k:
             self._graph.replay()
             done += 1
-        idx = (torch.arange(k, device=losses.device) + step0) % _RING
-        losses[offset:offset + k] = g["ring"][idx]
+        value = None
+        if losses is None:
+            value = g["ring"][step0 % _RING].item()
+        elif k == 1:
+            losses[offset:offset + 1] = g["ring"][step0 % _RING:step0 % _RING + 1]
+        else:
+            idx = (torch.arange(k, device=losses.device) + step0) % _RING
+            losses[offset:offset + k] = g["ring"][idx]
         self._advance_host(k)
+        if self._dev_state is not None:  # the device advanced its own step counter
+            self._dev_state = (self._dev_state[0] + k,) + self._dev_state[1:]
+        return value
+
+    def step_loss(self):
+        """One device-scheduled step, loss returned as a float; None when the step is not graph-eligible."""
+        if self.masking_cfg is not None or not self._graph_eligible():
+            return None
+        if not self.model.training:
+            self.model.train()
+        value = self._graph_steps(1, None, 0)
+        self.step_index += 1
+        return value
 
     # ------------------------------------------------------------------ public
     def steps(self, k):
         """Run k fit steps; returns a device tensor [k] with each step's (pre-update) loss."""
-        self.model.train()
+        if not self.model.training:
+            self.model.train()
         losses = torch.empty(k, dtype=torch.float32, device=self.img.device)
         done = 0
         while done < k:

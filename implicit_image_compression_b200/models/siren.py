@@ -155,6 +155,8 @@ class Siren(nn.Module):
                 new.__dict__[k] = {}
             elif k == "_post_backward":
                 new.__dict__[k] = []
+            elif k == "_step_fitters":
+                new.__dict__[k] = {}
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
         return new

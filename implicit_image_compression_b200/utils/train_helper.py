@@ -140,6 +140,27 @@ def _fused_loss_and_grads(model, grid, img):
     return stats
 
 
+def _graph_step(model, optim, grid, img, lr_scheduler, mask):
+    """train_epoch through a cached fit.Fitter (CUDA-graph replay).  Returns None when the step is not
+    eligible (quantisation transforms, sparse-gradient masks, foreign scheduler, ...)."""
+    from ..fit import Fitter
+
+    if model._weight_transforms or model._post_backward or model._param_override:
+        return None
+    cache = model.__dict__.setdefault("_step_fitters", {})
+    key = (id(optim), id(lr_scheduler), id(mask), grid.data_ptr(), img.data_ptr(), tuple(img.shape))
+    fitter = cache.get(key)
+    if fitter is None:
+        if len(cache) >= 4:
+            cache.clear()
+        fitter = Fitter(model, optim, grid, img, lr_scheduler, mask, None)
+        cache[key] = fitter
+    flat = fitter.flat
+    if flat.params[0].grad is not flat.views[0] or flat.params[-1].grad is not flat.views[-1]:
+        flat.attach()  # param.grad must be the views the captured step writes
+    return fitter.step_loss()
+
+
 def train_epoch(model, optim, grid, img, **kwargs):
     """One fit step; returns this step's loss as a Python float (train_helper.py:132-185).
 
@@ -154,7 +175,17 @@ def train_epoch(model, optim, grid, img, **kwargs):
     if kwargs.get("preconditioner"):
         raise _lib.SirenB200Error("preconditioners (EKFAC) are dead code in the reference and unsupported")
 
-    model.train()
+    if not model.training:
+        model.train()
+    if criterion is F.mse_loss and hasattr(model, "hot_parameters") and isinstance(optim, FusedAdam):
+        # one replay of the captured step graph (fit.Fitter) when nothing on the step needs the host;
+        # the contract is unchanged: this step's loss as a float, param.grad populated, optimizer /
+        # scheduler / mask bookkeeping advanced by one
+        loss = _graph_step(model, optim, grid, img, lr_scheduler, mask)
+        if loss is not None:
+            if pbar:
+                pbar.update(1)
+            return loss
     if criterion is F.mse_loss and hasattr(model, "hot_parameters"):
         stats = _fused_loss_and_grads(model, grid, img)
         loss_t = stats[1]

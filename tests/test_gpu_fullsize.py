@@ -85,23 +85,31 @@ def test_pixel_shards_sum_to_full_image_gradient():
             assert _rel(a, f) <= tol
 
 
-def test_fitter_matches_train_epoch_and_improves_psnr():
+def test_fitter_matches_train_epoch_and_improves_psnr(monkeypatch):
+    """Three routes to the same 40 steps: train_epoch with every kernel launched eagerly and the schedule
+    on the host (SIRENB200_GRAPH=0), train_epoch replaying the captured step, and Fitter.steps(40)."""
     get_grid, synth_image, Fitter, Siren, th = _pkg()
     H, W = 64, 96
     grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
     runs = []
-    for use_fitter in (False, True):
+    for route in ("eager", "train_epoch", "fitter"):
+        monkeypatch.setenv("SIRENB200_GRAPH", "0" if route == "eager" else "1")
         torch.manual_seed(0)
         model = Siren(depth=4, hidden_size=128, first_omega_0=50, hidden_omega_0=30).cuda()
         optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
-        if use_fitter:
+        if route == "fitter":
             losses = Fitter(model, optim, grid, img, sched).steps(40).tolist()
         else:
             losses = [th.train_epoch(model, optim, grid, img, lr_scheduler=sched) for _ in range(40)]
+            if route == "train_epoch":
+                assert all(f._graph is not None for f in model._step_fitters.values())
+            assert optim.param_groups[0]["_fused_step"] == 40 and sched.last_epoch == 40
+            assert all(p.grad is not None for p in model.parameters())
         runs.append((losses, th.eval_epoch(model, grid, img)[2]))
     np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=1e-6)
+    np.testing.assert_allclose(runs[0][0], runs[2][0], rtol=1e-6)
     assert runs[0][0][-1] < 0.5 * runs[0][0][0]
-    assert abs(runs[0][1] - runs[1][1]) < 1e-3
+    assert abs(runs[0][1] - runs[1][1]) < 1e-3 and abs(runs[0][1] - runs[2][1]) < 1e-3
 
 
 def test_c2_short_fit_psnr_tracks_fp32_path():
@@ -125,7 +133,7 @@ def test_c2_short_fit_psnr_tracks_fp32_path():
     assert psnr["f16tc"][0] > 15.0
 
 
-def test_fitter_graph_with_masks_matches_reference_loop():
+def test_fitter_graph_with_masks_matches_reference_loop(monkeypatch):
     """Fitter (CUDA-graph segments between topology updates, masks applied inside the captured Adam)
     follows the reference loop train_epoch(mask=...) + update_connections() exactly."""
     get_grid, synth_image, Fitter, Siren, th = _pkg()
@@ -135,13 +143,14 @@ def test_fitter_graph_with_masks_matches_reference_loop():
                growth_mode="absolute-gradient", prune_mode="magnitude", redistribution_mode="none",
                dense=False, prune_rate=0.1, decay_schedule="cosine", end_when=30, interval=5)
     out = []
-    for use_fitter in (False, True):
+    for route in ("eager", "train_epoch", "fitter"):
+        monkeypatch.setenv("SIRENB200_GRAPH", "0" if route == "eager" else "1")
         torch.manual_seed(0)
         model = Siren(depth=4, hidden_size=128, first_omega_0=50, hidden_omega_0=30).cuda()
         optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
         torch.manual_seed(7)
         mask = th.setup_mask(model, optim, cfg)
-        if use_fitter:
+        if route == "fitter":
             f = Fitter(model, optim, grid, img, sched, mask, cfg)
             losses = torch.cat([f.steps(13), f.steps(12)]).tolist()
         else:
@@ -152,7 +161,8 @@ def test_fitter_graph_with_masks_matches_reference_loop():
                     mask.update_connections()
         out.append((losses, {n: m.clone() for n, m in mask.mask_dict.items()}, mask.mask_step,
                     mask.prune_rate))
-    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-6)
-    for n in out[0][1]:
-        assert torch.equal(out[0][1][n], out[1][1][n]), n
-    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
+    for other in out[1:]:
+        np.testing.assert_allclose(out[0][0], other[0], rtol=1e-6)
+        for n in out[0][1]:
+            assert torch.equal(out[0][1][n], other[1][n]), n
+        assert out[0][2] == other[2] and out[0][3] == other[3]
