@@ -966,42 +966,66 @@ __global__ void __launch_bounds__(256) kmeans_minmax_kernel(const float* w, int6
   }
 }
 
-// Lloyd assignment step for the non-zero weights: label32[i] = nearest centre, -1 for zeros.
-__global__ void __launch_bounds__(256) kmeans_label_kernel(const float* w, int64_t n,
+// Lloyd assignment step for the non-zero weights: label16[i] = nearest centre, 0xFFFF for zeros and for the
+// padding up to a multiple of 256 entries.  `done` (device flag) turns the remaining iterations into no-ops
+// once the centre shift has converged, so the host never synchronises inside the Lloyd loop.
+__global__ void __launch_bounds__(256) kmeans_label_kernel(const float* w, int64_t n, int64_t npad,
                                                            const float* cent, const int* k_cur,
-                                                           int* label32) {
+                                                           const int* done, uint16_t* label16) {
   extern __shared__ float sc[];
+  if (*done) return;
   const int k = *k_cur;
   for (int j = threadIdx.x; j < k; j += 256) sc[j] = cent[j];
   __syncthreads();
-  for (int64_t i = blockIdx.x * int64_t(256) + threadIdx.x; i < n; i += int64_t(gridDim.x) * 256) {
-    const float x = w[i];
-    label32[i] = (x == 0.f) ? -1 : kmeans_nearest(x, sc, k);
+  for (int64_t i = blockIdx.x * int64_t(256) + threadIdx.x; i < npad; i += int64_t(gridDim.x) * 256) {
+    const float x = (i < n) ? w[i] : 0.f;
+    label16[i] = (x == 0.f) ? uint16_t(0xFFFF) : uint16_t(kmeans_nearest(x, sc, k));
   }
 }
 
 // Per-cluster sum and count, one warp per cluster, accumulating in INDEX ORDER in fp32 so the result
 // is bit-identical to the reference's sequential index_add_ (scatter_mean restatement) on the CPU.
-__global__ void __launch_bounds__(256) kmeans_cluster_sum_kernel(const float* w, int64_t n,
-                                                                 const int* label32,
-                                                                 const int* k_cur, float* sums,
-                                                                 unsigned int* cnts) {
+// A lane scans 8 labels per 16-byte load (256 labels per warp iteration, next load in flight); only
+// the lanes that hold a hit fetch the weight.
+__global__ void __launch_bounds__(256) kmeans_cluster_sum_kernel(const float* w, int64_t npad,
+                                                                 const uint16_t* label16,
+                                                                 const int* k_cur, const int* done,
+                                                                 float* sums, unsigned int* cnts) {
+  if (*done) return;
   const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= *k_cur) return;
+  const uint32_t pat = uint32_t(c) | (uint32_t(c) << 16);
+  const uint4* lv = reinterpret_cast<const uint4*>(label16);
+  const int64_t ngroups = npad / 8;  // npad is a multiple of 256 -> ngroups a multiple of 32
   float sum = 0.f;
   unsigned int cnt = 0;
-  for (int64_t base = 0; base < n; base += 32) {
-    const int64_t i = base + lane;
-    const bool hit = (i < n) && (label32[i] == c);
-    const float x = hit ? w[i] : 0.f;
-    unsigned int bal = __ballot_sync(0xffffffffu, hit);
-    cnt += __popc(bal);
+  uint4 cur = lv[lane];
+  for (int64_t g0 = 0; g0 < ngroups; g0 += 32) {
+    uint4 nxt = cur;
+    if (g0 + 32 < ngroups) nxt = lv[g0 + 32 + lane];
+    const uint32_t e[4] = {cur.x ^ pat, cur.y ^ pat, cur.z ^ pat, cur.w ^ pat};
+    unsigned int m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      m |= ((e[q] & 0xFFFFu) == 0u ? 1u : 0u) << (2 * q);
+      m |= ((e[q] >> 16) == 0u ? 1u : 0u) << (2 * q + 1);
+    }
+    unsigned int bal = __ballot_sync(0xffffffffu, m != 0u);
     while (bal) {
       const int b = __ffs(bal) - 1;
       bal &= bal - 1;
-      sum += __shfl_sync(0xffffffffu, x, b);
+      unsigned int mb = __shfl_sync(0xffffffffu, m, b);
+      cnt += __popc(mb);
+      while (mb) {
+        const int j = __ffs(mb) - 1;
+        mb &= mb - 1;
+        float x = 0.f;
+        if (lane == b) x = w[(g0 + b) * 8 + j];
+        sum += __shfl_sync(0xffffffffu, x, b);
+      }
     }
+    cur = nxt;
   }
   if (lane == 0) {
     sums[c] = sum;
@@ -1017,10 +1041,13 @@ struct KmeansUpdateArgs {
   int* k_cur;         // current number of centres
   float* shift;       // out: (sum_i |c_i - c'_i|)
   int* status;        // out: 1 = shape mismatch (reference would raise)
+  int* done;          // in/out: set once shift**2 < tol (kmeans_helper.py:99-100) or on a shape mismatch
+  float tol;
 };
 __global__ void __launch_bounds__(1024) kmeans_update_kernel(const KmeansUpdateArgs a) {
   __shared__ float red[1024];
   __shared__ int smax;
+  if (*a.done) return;
   const int k = *a.k_cur;
   if (threadIdx.x == 0) smax = -1;
   __syncthreads();
@@ -1046,7 +1073,12 @@ __global__ void __launch_bounds__(1024) kmeans_update_kernel(const KmeansUpdateA
   }
   if (threadIdx.x == 0) {
     *a.shift = red[0];
-    *a.status = (nout == k) ? 0 : 1;
+    if (nout != k) {
+      *a.status = 1;
+      *a.done = 1;
+    } else if (red[0] * red[0] < a.tol) {
+      *a.done = 1;
+    }
   }
 }
 

@@ -789,6 +789,21 @@ int finalize(sirenb200_plan* p, const float* parts, int nparts, int64_t stride, 
 // =========================================================================================
 // C ABI
 // =========================================================================================
+// Scratch for the stateless entry points comes from the device's default stream-ordered pool.  Its default
+// release threshold is 0 (memory goes back to the driver at every synchronisation, so each call pays a
+// fresh allocation of milliseconds); keep what was allocated.
+static void keep_pool_memory() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 extern "C" {
 
 int sirenb200_version(void) { return 100; }
@@ -1137,6 +1152,7 @@ int sirenb200_eval_metrics(const float* pred, const float* img, int64_t n, float
   if (!pred || !img || !out || n <= 0) return fail(SIRENB200_ERR_INVALID, "bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   double* acc = nullptr;
+  keep_pool_memory();
   CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&acc), 2 * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
   int grid = cdiv(n, 256 * 8);
@@ -1264,11 +1280,13 @@ int sirenb200_kmeans_quantize(const float* w, int64_t n, int32_t bits, int32_t i
     return fail(SIRENB200_ERR_INVALID, "bad argument (bits must be in [1, 10])");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int k = (1 << bits) - 1;
-  // scratch: centres[k] | minmax[2] | shift | sums[k] | cnts[k] | k_cur | status | label32[n]
+  // scratch: centres[k] | minmax[2] | shift | sums[k] | cnts[k] | k_cur | status | done | label16[npad]
+  const int64_t npad = (n + 255) / 256 * 256;
   const size_t fbytes = (size_t(k) * 2 + 8) * sizeof(float);
-  const size_t ibytes = (size_t(k) + 8 + size_t(n)) * sizeof(int);
+  const size_t ibytes = (size_t(k) + 8) * sizeof(int);
   char* scratch = nullptr;
-  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), fbytes + ibytes, st));
+  keep_pool_memory();
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&scratch), fbytes + ibytes + 16 + size_t(npad) * 2, st));
   float* cent = reinterpret_cast<float*>(scratch);
   float* mm = cent + k;
   float* shift = mm + 2;
@@ -1276,10 +1294,13 @@ int sirenb200_kmeans_quantize(const float* w, int64_t n, int32_t bits, int32_t i
   unsigned int* cnts = reinterpret_cast<unsigned int*>(scratch + fbytes);
   int* k_cur = reinterpret_cast<int*>(cnts + k);
   int* status = k_cur + 1;
-  int* label32 = k_cur + 8;
+  int* done = k_cur + 2;
+  // 16-byte aligned: fbytes + ibytes = (3k + 16) * 4 with k odd -> round the label offset up
+  uint16_t* label16 = reinterpret_cast<uint16_t*>(scratch + (fbytes + ibytes + 15) / 16 * 16);
   const float inf_init[2] = {INFINITY, -INFINITY};
+  const int int_init[3] = {k, 0, 0};
   CUDA_TRY(cudaMemcpyAsync(mm, inf_init, sizeof(inf_init), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(k_cur, &k, sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(k_cur, int_init, sizeof(int_init), cudaMemcpyHostToDevice, st));
   int grid = cdiv(n, 256);
   if (grid > 592) grid = 592;
   int rc = 0;
@@ -1295,39 +1316,30 @@ int sirenb200_kmeans_quantize(const float* w, int64_t n, int32_t bits, int32_t i
     kmeans_linspace_kernel<<<cdiv(k, 256), 256, 0, st>>>(mm, k, cent);
     ++g_launches;
   }
+  // The whole Lloyd loop is enqueued at once: the convergence test (center_shift ** 2 < tolerance) runs on
+  // the device and turns the remaining iterations into no-ops.
   for (int it = 0; it < iter_limit; ++it) {
-    kmeans_label_kernel<<<grid, 256, k * sizeof(float), st>>>(w, n, cent, k_cur, label32);
-    ++g_launches;
-    kmeans_cluster_sum_kernel<<<cdiv(k, 8), 256, 0, st>>>(w, n, label32, k_cur, sums, cnts);
-    ++g_launches;
-    KmeansUpdateArgs ua{cent, sums, cnts, k_cur, shift, status};
+    kmeans_label_kernel<<<grid, 256, k * sizeof(float), st>>>(w, n, npad, cent, k_cur, done, label16);
+    kmeans_cluster_sum_kernel<<<cdiv(k, 8), 256, 0, st>>>(w, npad, label16, k_cur, done, sums, cnts);
+    KmeansUpdateArgs ua{cent, sums, cnts, k_cur, shift, status, done, tol};
     kmeans_update_kernel<<<1, 1024, 0, st>>>(ua);
-    ++g_launches;
-    float hs[1];
-    int hstat[1];
-    if (cudaMemcpyAsync(hs, shift, sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaMemcpyAsync(hstat, status, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-        cudaStreamSynchronize(st) != cudaSuccess) {
-      rc = fail(SIRENB200_ERR_CUDA, "k-means iteration failed: %s",
-                cudaGetErrorString(cudaGetLastError()));
-      return cleanup(rc);
-    }
-    if (hstat[0] != 0) {
-      rc = fail(SIRENB200_ERR_INVALID,
-                "k-means: top clusters are empty (the reference raises a shape mismatch here, "
-                "quant/kmeans_helper.py:91)");
-      return cleanup(rc);
-    }
-    if (hs[0] * hs[0] < tol) break;  // center_shift ** 2 < tolerance
+    g_launches += 3;
   }
   kmeans_codebook_kernel<<<1, 1024, 0, st>>>(cent, k_cur, centroids, n_centroids);
   ++g_launches;
   kmeans_predict_kernel<<<grid, 256, (k + 1) * sizeof(float), st>>>(w, n, centroids, n_centroids,
                                                                    labels, w_out);
   ++g_launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess)
-    return cleanup(fail(SIRENB200_ERR_CUDA, "k-means launch failed: %s", cudaGetErrorString(e)));
+  int hstat = 0;
+  if (cudaMemcpyAsync(&hstat, status, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {
+    rc = fail(SIRENB200_ERR_CUDA, "k-means failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return cleanup(rc);
+  }
+  if (hstat != 0)
+    return cleanup(fail(SIRENB200_ERR_INVALID,
+                        "k-means: top clusters are empty (the reference raises a shape mismatch here, "
+                        "quant/kmeans_helper.py:91)"));
   return cleanup(0);
 }
 

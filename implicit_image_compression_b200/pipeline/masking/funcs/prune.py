@@ -3,6 +3,7 @@ SIREN: per-layer `magnitude` (RigL / SNFS) and `global-magnitude` (Pruning).  Th
 never apply to 2-D weights and are out of scope."""
 import math
 
+import numpy as np
 import torch
 
 
@@ -26,13 +27,18 @@ def global_magnitude_prune(masking):
     if tokill <= 0:
         return 0
     masked = [(n, w) for n, w in masking.module.named_parameters() if n in masking.mask_dict]
+    # The reference probes `(|w| > threshold).sum()` per layer per iteration (hundreds of probes, each a
+    # kernel launch + host sync).  The same integer comes from ONE device sort: with the magnitudes sorted,
+    # #(|w| > t) = n - upper_bound(t).  torch compares an fp32 tensor with a Python float in fp32, so the
+    # threshold is rounded to fp32 for the probe exactly as `torch.abs(w) > threshold` rounds it.
+    mags = torch.sort(torch.cat([torch.abs(w.data).reshape(-1) for _, w in masked]))[0].cpu().numpy()
+    mags = mags[~np.isnan(mags)]  # NaN > t is False
+    nonzero_total = sum(masking.stats.nonzeros_dict[n] for n, _ in masked)
     total_removed = prev_removed = tries = 0
     increment = masking.increment
     while abs(total_removed - tokill) > tokill * masking.tolerance:
-        # one device->host sync per probe instead of one per layer
-        remain = torch.stack([(torch.abs(w.data) > masking.prune_threshold).sum() for _, w in masked])
-        remain = remain.tolist()
-        total_removed = sum(masking.stats.nonzeros_dict[n] - r for (n, _), r in zip(masked, remain))
+        remain = mags.size - int(np.searchsorted(mags, np.float32(masking.prune_threshold), side="right"))
+        total_removed = nonzero_total - remain
         if prev_removed == total_removed:
             tries += 1
             if tries == 10:

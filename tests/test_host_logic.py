@@ -151,3 +151,21 @@ def test_pixel_sharded_gradients_sum_to_full_image_gloo(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all(torch.load(tmp_path / f"ok{r}.pt") for r in range(2))
+
+
+def test_sorted_probe_equals_torch_threshold_count():
+    """global_magnitude_prune counts #(|w| > t) through one sort + upper_bound; torch compares an fp32 tensor
+    with a Python float in fp32 (prune.py:74-76 of the reference relies on that), ties included."""
+    import numpy as np
+    import torch
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(4096, generator=g) * 0.05
+    w[::7] = 0.0
+    w[1::11] = w[5]  # duplicates
+    mags = torch.sort(w.abs())[0].numpy()
+    probes = [0.0, 1e-3, float(mags[100]), float(mags[100]) * (1 + 1e-9), float(mags[100]) * (1 - 1e-9),
+              float(np.nextafter(mags[2000], np.float32(1))), 0.1, 1e9]
+    for t in probes:
+        direct = int((torch.abs(w) > t).sum())
+        via_sort = mags.size - int(np.searchsorted(mags, np.float32(t), side="right"))
+        assert direct == via_sort, t
