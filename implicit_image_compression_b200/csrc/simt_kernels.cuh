@@ -15,34 +15,6 @@ constexpr int kMaxLayers = 16;
 constexpr int kMaxTensors = 2 * kMaxLayers;
 constexpr int kMaxOut = 4;
 
-// Where the input coordinates of pixel p (local index inside this handle's rows) come from.
-struct CoordSrc {
-  const float* lin_h;   // [H] or null
-  const float* lin_w;   // [W] or null
-  const float* coords;  // [npix, 2] or null
-  int width;            // image width
-  int row_begin;        // first image row of this handle
-  int64_t p_offset;     // pixel offset of the current launch inside the handle's rows (row chunks)
-};
-
-// siren.py:125-128: x = (grid - 0.5) * 2, features ordered (h, w) (data.py:82-86, 'ij' meshgrid)
-__device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh, float& xw) {
-  float gh, gw;
-  p += c.p_offset;
-  if (c.coords) {
-    const float2 v = reinterpret_cast<const float2*>(c.coords)[p];
-    gh = v.x;
-    gw = v.y;
-  } else {
-    const unsigned pu = unsigned(p);  // npix < 2^31 (checked at create)
-    const int r = int(pu / unsigned(c.width)), col = int(pu - unsigned(r) * unsigned(c.width));
-    gh = __ldg(c.lin_h + c.row_begin + r);
-    gw = __ldg(c.lin_w + col);
-  }
-  xh = (gh - 0.5f) * 2.0f;
-  xw = (gw - 0.5f) * 2.0f;
-}
-
 // ------------------------------------------------------------------------------------------
 // generic fp32 tiled GEMM (64x64x16 tiles, 4x4 per thread) with fused epilogues
 // ------------------------------------------------------------------------------------------

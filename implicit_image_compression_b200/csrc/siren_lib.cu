@@ -94,6 +94,7 @@ struct sirenb200_plan {
   __half* wlt16 = nullptr;  // [W, 64]
   CUtensorMap tm_wl{}, tm_wlt{};
   bool last_tc = false;
+  bool gen_first = true;    // layer 0 generated inside the first hidden GEMM (SIRENB200_GEN_FIRST=0: own kernel)
   long long* dbg_timeline = nullptr;  // SIRENB200_TIMELINE=1: 3*4*8*16 clock64 slots (debug)
   std::vector<CUtensorMap> tm_w, tm_wt, tm_wt_half;
   bool fused_bwd = false;      // one-pass dX + dW kernel per hidden layer (hidden = 256)
@@ -181,14 +182,14 @@ int check_ready(const sirenb200_plan* p) {
 // ---------------------------------------------------------------------------------------
 // rowgemm / colgemm launch helpers
 // ---------------------------------------------------------------------------------------
-template <int W, int MODE>
+template <int W, int MODE, bool GEN = false>
 int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap& tmE, const CUtensorMap& tmO, const RowGemmArgs& args,
                    cudaStream_t st) {
   constexpr int NT = W < 256 ? W : 256;  // output columns per work item
   constexpr int NPARTS = W / NT;
   using Cfg = RowGemmCfg<W, NT, MODE, NPARTS>;
-  auto kfn = rowgemm_kernel<W, NT, MODE, false, NPARTS>;
+  auto kfn = rowgemm_kernel<W, NT, MODE, false, NPARTS, GEN>;
   static bool attr_set[64] = {};
   if (!attr_set[p->device & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -201,7 +202,7 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
-    kfn<<<grid, 384, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
+    kfn<<<grid, GEN ? 544 : 384, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
   }
   LAUNCH_CHECK();
   return 0;
@@ -339,12 +340,16 @@ template <int W>
 int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
   const int nh = p->D - 2;
   if (p->fused_fwd && ch.index == 0 && p->nchunks == 1) return launch_fused_fwd<W>(p, ch, st);
-  {
+  // Layer 0 runs inside the first hidden layer's GEMM (its A operand is generated in the kernel) when
+  // that kernel keeps its weights resident; otherwise as its own CUDA-core kernel.
+  constexpr bool kCanGen = (W <= 256);
+  const bool gen_first = kCanGen && p->gen_first && nh >= 1;
+  CoordSrc cs = p->coord;
+  cs.p_offset = ch.p0;
+  if (!gen_first) {
     int grid = p->nsm * 8;
     const int need = cdiv(ch.npix_pad, 256 / (W / 8));
     if (grid > need) grid = need;
-    CoordSrc cs = p->coord;
-    cs.p_offset = ch.p0;
     ProfScope ps(p, PK_FIRST, st);
     tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(cs, prm[0], prm[1], omega_of(p, 0),
                                                   p->act + ch.p0 * W, ch.npix, ch.npix_pad);
@@ -359,7 +364,20 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     ra.valid_rows = int(ch.npix);
     ra.omega = omega_of(p, l);
     ra.bias = prm[2 * l + 1];
-    int rc = launch_rowgemm<W, MODE_FWD>(p, p->tm_act, p->tm_w[l - 1], p->tm_act, p->tm_act, ra, st);
+    int rc;
+    if constexpr (kCanGen) {
+      if (l == 1 && gen_first) {
+        ra.gen_coord = cs;
+        ra.gen_w0 = prm[0];
+        ra.gen_b0 = prm[1];
+        ra.gen_omega = omega_of(p, 0);
+        ra.gen_tl = p->dbg_timeline;
+        rc = launch_rowgemm<W, MODE_FWD, true>(p, p->tm_act, p->tm_w[0], p->tm_act, p->tm_act, ra, st);
+        if (rc) return rc;
+        continue;
+      }
+    }
+    rc = launch_rowgemm<W, MODE_FWD>(p, p->tm_act, p->tm_w[l - 1], p->tm_act, p->tm_act, ra, st);
     if (rc) return rc;
   }
   return 0;
@@ -957,6 +975,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     {
       const char* env = getenv("SIRENB200_LAST_TC");
       p->last_tc = (W == 128 || W == 256) && nh > 0 && !(env && atoi(env) == 0);
+      env = getenv("SIRENB200_GEN_FIRST");
+      p->gen_first = !(env && atoi(env) == 0);
     }
     p->last_grid = p->nsm * 2;
     if (int64_t(p->last_grid) * 8 > chunk_pad) p->last_grid = cdiv(chunk_pad, 8);

@@ -69,6 +69,34 @@ __device__ __forceinline__ float cos_from_signed_half(uint32_t h16) {
   return __uint_as_float(__float_as_uint(c) ^ ((h16 & 1u) << 31));
 }
 
+// Where the input coordinates of pixel p (local index inside this handle's rows) come from.
+struct CoordSrc {
+  const float* lin_h;   // [H] or null
+  const float* lin_w;   // [W] or null
+  const float* coords;  // [npix, 2] or null
+  int width;            // image width
+  int row_begin;        // first image row of this handle
+  int64_t p_offset;     // pixel offset of the current launch inside the handle's rows (row chunks)
+};
+
+// siren.py:125-128: x = (grid - 0.5) * 2, features ordered (h, w) (data.py:82-86, 'ij' meshgrid)
+__device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh, float& xw) {
+  float gh, gw;
+  p += c.p_offset;
+  if (c.coords) {
+    const float2 v = reinterpret_cast<const float2*>(c.coords)[p];
+    gh = v.x;
+    gw = v.y;
+  } else {
+    const unsigned pu = unsigned(p);  // npix < 2^31 (checked at create)
+    const int r = int(pu / unsigned(c.width)), col = int(pu - unsigned(r) * unsigned(c.width));
+    gh = __ldg(c.lin_h + c.row_begin + r);
+    gw = __ldg(c.lin_w + col);
+  }
+  xh = (gh - 0.5f) * 2.0f;
+  xw = (gw - 0.5f) * 2.0f;
+}
+
 // ------------------------------------------------------------------------------------------
 // rowgemm
 // ------------------------------------------------------------------------------------------
@@ -112,12 +140,30 @@ struct RowGemmArgs {
   int valid_rows;     // rows >= valid_rows (relative to the launch) are written as zero (MODE_DX)
   float omega;        // MODE_FWD: sine frequency
   const float* bias;  // MODE_FWD: fp32 bias[NDIM]
+  // GEN (first hidden layer): the A operand is not loaded but GENERATED — layer 0 of the network,
+  // a0 = sin(w0 (W0 x + b0)) from in-kernel coordinates (siren.py:62,66 with is_first) — by four extra
+  // warps straight into the A ring, and stored to the activation stash from there.
+  CoordSrc gen_coord;
+  const float* gen_w0;  // [KDIM, 2] fp32
+  const float* gen_b0;  // [KDIM]
+  float gen_omega;
+  long long* gen_tl;  // SIRENB200_TIMELINE: clock64 stamps of block 0 (debug)
 };
 
-template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1>
+// timeline slots of the GEN variant: tl[(role * 8 + tile) * 8 + k], block 0, first 8 tiles;
+// roles 0..3 = generator warps, 4 = MMA issuer, 5 = epilogue
+#define SB_DBG_G(role, tile_i, k)                                                   \
+  do {                                                                              \
+    if (GEN && args.gen_tl && blockIdx.x == 0 && (tile_i) < 8)                      \
+      args.gen_tl[((role) * 8 + (tile_i)) * 8 + (k)] = clock64();                   \
+  } while (0)
+
+template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false>
 // 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue-input producer, 3 = spare, 4..11 = epilogue
-// (two warps per TMEM lane quadrant; each takes 32 of the 64 columns of every output chunk).
-__global__ void __launch_bounds__(384, 1)
+// (two warps per TMEM lane quadrant; each takes 32 of the 64 columns of every output chunk);
+// GEN: warps 0, 2, 3 and 12..16 = A-operand generators (network layer 0), two per 64-wide k-block; the
+// weight load moves to warp 1.
+__global__ void __launch_bounds__(GEN ? 544 : 384, 1)
 rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
                const RowGemmArgs args, const uint32_t idesc) {
@@ -172,7 +218,113 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  // generator index (GEN only): warps 0, 2, 3, 12, 13, 14, 15, 16 -> 0..7
+  const int gi = !GEN ? -1 : (warp == 0 ? 0 : (warp == 2 || warp == 3) ? warp - 1 : (warp >= 12 ? warp - 9 : -1));
+  if (GEN && warp == 1 && lane == 0) {
+    mbar_expect_tx(b_full, C::KB * C::B_KB_BYTES);
+    for (int kb = 0; kb < C::KB; ++kb)
+      tma_load_2d(smem + C::OFF_B + kb * C::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
+  }
+  if (GEN && gi >= 0) {
+    // ===================== A generator: layer 0 of the network -> A ring (+ stash) =====================
+    // Two warps per 64-wide k-block (16 of the 32 four-row iterations each): the 8 column groups x 3
+    // layer-0 parameters of a lane stay in registers for the kernel's lifetime; lane = (column group,
+    // row group).
+    static_assert(!GEN || (NPARTS == 1 && !C::STREAM_B && MODE == MODE_FWD && C::KB <= 4 && C::SA % C::KB == 0),
+                  "GEN: resident-B forward only");
+    const int kb = gi >> 1, half = gi & 1;
+    if (kb < C::KB) {
+      const int cg = lane & 7;   // 16-byte column group inside the k-block
+      const int rg = lane >> 3;  // rows rg + 4 i
+      const bool issuer_g = (half == 0 && lane == 0);
+      const CoordSrc& cs = args.gen_coord;
+      float wa[8], wb[8], bb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = kb * 64 + cg * 8 + j;
+        wa[j] = __ldg(args.gen_w0 + col * 2 + 0) * args.gen_omega;
+        wb[j] = __ldg(args.gen_w0 + col * 2 + 1) * args.gen_omega;
+        bb[j] = __ldg(args.gen_b0 + col) * args.gen_omega;
+      }
+      const unsigned width = unsigned(cs.width);
+      const bool has_coords = cs.coords != nullptr;
+      uint32_t ig = kb;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ig += C::KB) {
+        const uint32_t s = ig % C::SA, ph = (ig / C::SA) & 1u;
+        const uint32_t stage = smem_u32(smem + C::OFF_A + s * C::A_STAGE);
+        // image (row, col) of this lane's first pixel; later rows advance by 4 pixels
+        const int r_first = rg + 64 * half;
+        const uint64_t g0 = uint64_t(int64_t(t) * kRowsPerTile + r_first + cs.p_offset);
+        unsigned irow = unsigned(g0 / width), icol = unsigned(g0 % width);
+        // every lane waits (no divergent region in front of the arithmetic); only the issuer owns bulk groups
+        if (issuer_g) SB_DBG_G(kb, ig / C::KB, 0);
+        mbar_wait(&a_empty[s], ph ^ 1u);                   // the MMAs that read this stage are done
+        tma_store_wait_read<C::SA / C::KB - 1>();          // ... and so is the stash store issued from it
+        named_bar_sync(2 + kb, 64);
+        if (issuer_g) SB_DBG_G(kb, ig / C::KB, 1);
+        // batches of 8 rows: all coordinate loads first, then the arithmetic, then the stores (the shared
+        // stores are asm volatile with a memory clobber; interleaving them would serialise the loads)
+#pragma unroll 1
+        for (int ib = 0; ib < 16; ib += 8) {
+          float xh[8], xw[8];
+          uint32_t keep[8];  // all-ones for a real pixel row, 0 for the padding rows of the last tile
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = t * kRowsPerTile + r_first + 4 * (ib + i);
+            const bool ok = r < args.valid_rows;
+            keep[i] = ok ? 0xFFFFFFFFu : 0u;
+            if (has_coords) {
+              const float2 v = ok ? __ldg(reinterpret_cast<const float2*>(cs.coords) + r + cs.p_offset)
+                                  : make_float2(0.5f, 0.5f);
+              xh[i] = v.x;
+              xw[i] = v.y;
+            } else {
+              xh[i] = ok ? __ldg(cs.lin_h + cs.row_begin + irow) : 0.5f;
+              xw[i] = ok ? __ldg(cs.lin_w + icol) : 0.5f;
+              icol += 4;
+              if (icol >= width) {
+                icol -= width;
+                ++irow;
+                while (icol >= width) {  // images narrower than 4 pixels
+                  icol -= width;
+                  ++irow;
+                }
+              }
+            }
+          }
+          uint32_t o[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = (xh[i] - 0.5f) * 2.0f, x1 = (xw[i] - 0.5f) * 2.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float t0 = fmaf(x0, wa[2 * j], fmaf(x1, wb[2 * j], bb[2 * j]));
+              const float t1 = fmaf(x0, wa[2 * j + 1], fmaf(x1, wb[2 * j + 1], bb[2 * j + 1]));
+              o[i][j] = sine_signed_half2(t0, t1) & keep[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rt = r_first + 4 * (ib + i);
+            st_shared_v4(stage + rt * 128 + ((uint32_t(cg) ^ uint32_t(rt & 7)) << 4), o[i][0], o[i][1],
+                         o[i][2], o[i][3]);
+          }
+        }
+        if (issuer_g) SB_DBG_G(kb, ig / C::KB, 2);
+        fence_proxy_async_smem();
+        named_bar_sync(2 + kb, 64);
+        if (issuer_g) {
+          SB_DBG_G(kb, ig / C::KB, 3);
+          tma_store_2d(&tmA, smem + C::OFF_A + s * C::A_STAGE, kb * 64, args.a_row0 + t * kRowsPerTile);
+          tma_store_commit();
+          mbar_arrive(&a_full[s]);
+          SB_DBG_G(kb, ig / C::KB, 4);
+        }
+        __syncwarp();
+      }
+      if (issuer_g) tma_store_wait_all<0>();
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer: B once, then A k-blocks =====================
     if (lane == 0) {
       if (!C::STREAM_B) {
@@ -181,7 +333,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(smem + C::OFF_B + kb * C::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
       }
       uint32_t ia = 0;
-      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      for (int it = blockIdx.x; !GEN && it < num_items; it += gridDim.x) {
         const int t = it / NPARTS, part = it % NPARTS;
         const int row = args.a_row0 + t * kRowsPerTile;
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
@@ -203,12 +355,15 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ia = 0, it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+        SB_DBG_G(4, it, 0);
         mbar_wait(&tm_empty[acc], aph ^ 1u);
+        SB_DBG_G(4, it, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * NDIM;
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
           mbar_wait(&a_full[s], ph);
+          SB_DBG_G(4, it, 2 + (kb & 3));
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + C::OFF_A + s * C::A_STAGE);
           const uint32_t b_addr = C::STREAM_B ? a_addr + kChunkBytes
@@ -222,6 +377,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_commit(&a_empty[s]);
         }
         umma_commit(&tm_full[acc]);
+        SB_DBG_G(4, it, 6);
       }
     }
   } else if (warp == 2) {
@@ -251,7 +407,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int t = item / NPARTS, part = item % NPARTS;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
+      if (issuer) SB_DBG_G(5, it, 0);
       mbar_wait(&tm_full[acc], aph);
+      if (issuer) SB_DBG_G(5, it, 1);
       tc_fence_after();
       const bool row_valid = (t * kRowsPerTile + r_in_tile) < args.valid_rows;
       for (int nb = 0; nb < C::NB; ++nb, ++ic) {
@@ -317,6 +475,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tm_empty[acc]);
+      if (issuer) SB_DBG_G(5, it, 2);
     }
     if (issuer) tma_store_wait_all<0>();
   }
