@@ -606,10 +606,11 @@ struct ReduceDesc {
   int n;             // elements
   int nsplit;
   int64_t split_stride;
+  int vec;           // 1: few splits of a large tensor -> a thread owns 4 consecutive elements (n % 4 == 0)
 };
 struct ReduceArgs {
   ReduceDesc d[kMaxTensors];
-  int chunk_begin[kMaxTensors + 1];  // prefix sums of ceil(n / 32)
+  int chunk_begin[kMaxTensors + 1];  // prefix sums of ceil(n / 32) (vec: ceil(n / 1024))
   int ndesc;
   float scale;               // host-known factor
   const float* gscale;       // device seed scale G (grads are divided by it) or null
@@ -621,6 +622,32 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
   while (t + 1 < a.ndesc && int(blockIdx.x) >= a.chunk_begin[t + 1]) ++t;
   const ReduceDesc d = a.d[t];
   const float scale = a.gscale ? a.scale / *a.gscale : a.scale;
+  if (d.vec) {
+    // split-K partials of a weight gradient: every thread sums its float4 over the splits in order,
+    // all loads independent
+    const int e4 = (blockIdx.x - a.chunk_begin[t]) * 1024 + threadIdx.x * 4;
+    bool bad4 = false;
+    if (e4 < d.n) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = d.src + e4;
+#pragma unroll 8
+      for (int sp = 0; sp < d.nsplit; ++sp) {
+        const float4 v = *reinterpret_cast<const float4*>(src + int64_t(sp) * d.split_stride);
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+      }
+      acc.x *= scale;
+      acc.y *= scale;
+      acc.z *= scale;
+      acc.w *= scale;
+      *reinterpret_cast<float4*>(d.dst + e4) = acc;
+      bad4 = !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+    }
+    if (__syncthreads_or(bad4) && threadIdx.x == 0) a.stats[2] = 1.0f;
+    return;
+  }
   const int e = (blockIdx.x - a.chunk_begin[t]) * 32 + (threadIdx.x & 31);
   const int lane = threadIdx.x >> 5;
   float s = 0.f;

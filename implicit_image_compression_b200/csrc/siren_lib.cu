@@ -599,6 +599,10 @@ int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats,
     ra.d[nd].n = n;
     ra.d[nd].nsplit = nsplit;
     ra.d[nd].split_stride = stride;
+    // weight-gradient partials (few splits, many elements, 16-byte aligned rows): vectorised path
+    ra.d[nd].vec = (n >= 4096 && n % 4 == 0 && stride % 4 == 0 && nsplit <= 64 &&
+                    (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0)
+                       ? 1 : 0;
     ++nd;
   };
   add(grads[0], p->l0_part, 2 * W, p->l0_grid * nchunks, 3 * W);
@@ -615,7 +619,7 @@ int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats,
   int chunks = 0;
   for (int i = 0; i < nd; ++i) {
     ra.chunk_begin[i] = chunks;
-    chunks += cdiv(ra.d[i].n, 32);
+    chunks += cdiv(ra.d[i].n, ra.d[i].vec ? 1024 : 32);
   }
   ra.chunk_begin[nd] = chunks;
   ra.scale = scale;
@@ -750,8 +754,8 @@ int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads
     int rc = launch_simt<OP_TN_PART>(a, p->simt_splits, st);
     if (rc) return rc;
     ReduceArgs ra{};
-    ra.d[0] = {grads[2 * l], p->part32, gdim * xdim, p->simt_splits, int64_t(gdim) * xdim};
-    ra.d[1] = {grads[2 * l + 1], a.ColSum, gdim, p->simt_splits, int64_t(gdim)};
+    ra.d[0] = {grads[2 * l], p->part32, gdim * xdim, p->simt_splits, int64_t(gdim) * xdim, 0};
+    ra.d[1] = {grads[2 * l + 1], a.ColSum, gdim, p->simt_splits, int64_t(gdim), 0};
     ra.ndesc = 2;
     ra.chunk_begin[0] = 0;
     ra.chunk_begin[1] = cdiv(gdim * xdim, 32);

@@ -232,7 +232,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // row group).
     static_assert(!GEN || (NPARTS == 1 && !C::STREAM_B && MODE == MODE_FWD && C::KB <= 4 && C::SA % C::KB == 0),
                   "GEN: resident-B forward only");
-    const int kb = gi >> 1, half = gi & 1;
+    const int kb = GEN ? (gi >> 1) : 0, half = gi & 1;  // (GEN ? :) keeps the dead non-GEN instantiation warning-free
     if (kb < C::KB) {
       const int cg = lane & 7;   // 16-byte column group inside the k-block
       const int rg = lane >> 3;  // rows rg + 4 i
@@ -248,7 +248,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const unsigned width = unsigned(cs.width);
       const bool has_coords = cs.coords != nullptr;
-      uint32_t ig = kb;
+      uint32_t ig = uint32_t(kb);
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ig += C::KB) {
         const uint32_t s = ig % C::SA, ph = (ig / C::SA) & 1u;
         const uint32_t stage = smem_u32(smem + C::OFF_A + s * C::A_STAGE);
