@@ -94,6 +94,9 @@ struct sirenb200_plan {
   __half* wlt16 = nullptr;  // [W, 64]
   CUtensorMap tm_wl{}, tm_wlt{};
   bool last_tc = false;
+  bool fuse_l0 = true;      // layer-0 gradient reduced inside the dX GEMM of the first hidden layer (SIRENB200_FUSE_L0=0: own kernel)
+  int l0_used = 0;          // partial rows of l0_part written by the last backward
+  int last_rowgemm_grid = 0;
   bool gen_first = true;    // layer 0 generated inside the first hidden GEMM (SIRENB200_GEN_FIRST=0: own kernel)
   long long* dbg_timeline = nullptr;  // SIRENB200_TIMELINE=1: 3*4*8*16 clock64 slots (debug)
   std::vector<CUtensorMap> tm_w, tm_wt, tm_wt_half;
@@ -182,14 +185,14 @@ int check_ready(const sirenb200_plan* p) {
 // ---------------------------------------------------------------------------------------
 // rowgemm / colgemm launch helpers
 // ---------------------------------------------------------------------------------------
-template <int W, int MODE, bool GEN = false>
+template <int W, int MODE, bool GEN = false, bool RED = false>
 int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap& tmE, const CUtensorMap& tmO, const RowGemmArgs& args,
                    cudaStream_t st) {
   constexpr int NT = W < 256 ? W : 256;  // output columns per work item
   constexpr int NPARTS = W / NT;
   using Cfg = RowGemmCfg<W, NT, MODE, NPARTS>;
-  auto kfn = rowgemm_kernel<W, NT, MODE, false, NPARTS, GEN>;
+  auto kfn = rowgemm_kernel<W, NT, MODE, false, NPARTS, GEN, RED>;
   static bool attr_set[64] = {};
   if (!attr_set[p->device & 63]) {
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -202,9 +205,10 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
-    kfn<<<grid, GEN ? 544 : 384, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
+    kfn<<<grid, GEN ? 544 : (RED ? 640 : 384), Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
   }
   LAUNCH_CHECK();
+  p->last_rowgemm_grid = grid;
   return 0;
 }
 
@@ -504,6 +508,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
       tc_layer0_grad_kernel<W><<<p->l0_grid, 256, L0GradCfg<W>::SMEM_BYTES, st>>>(
           cs, p->dz + ch.p0 * W, p->l0_part + size_t(ch.index) * p->l0_grid * 3 * W, ch.npix);
     }
+    p->l0_used = p->l0_grid * p->nchunks;
     LAUNCH_CHECK();
     return 0;
   }
@@ -529,6 +534,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     jobs.interleave = interleave;
   };
   const bool overlap = p->bwd_overlap && nh > 0 && p->st2;
+  const bool fuse_l0 = p->fuse_l0 && W <= 256 && nh >= 1 && p->nchunks == 1 && !overlap;
   // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
   for (int l = nh; l >= 1; --l) {
     if (overlap) {
@@ -543,7 +549,19 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     ra.o_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.valid_rows = int(ch.npix);
     p->grid_override = overlap ? p->dx_grid : 0;
-    int rc = launch_rowgemm<W, MODE_DX>(p, p->tm_dz, p->tm_wt[l - 1], p->tm_act, p->tm_dz, ra, st);
+    int rc;
+    bool done = false;
+    if constexpr (W <= 256) {
+      if (l == 1 && fuse_l0) {
+        ra.gen_coord = p->coord;
+        ra.gen_coord.p_offset = ch.p0;
+        ra.red_part = p->l0_part;
+        rc = launch_rowgemm<W, MODE_DX, false, true>(p, p->tm_dz, p->tm_wt[0], p->tm_act, p->tm_dz, ra, st);
+        p->l0_used = 2 * p->last_rowgemm_grid;  // two reducer warps (pixel halves) per chunk
+        done = true;
+      }
+    }
+    if (!done) rc = launch_rowgemm<W, MODE_DX>(p, p->tm_dz, p->tm_wt[l - 1], p->tm_act, p->tm_dz, ra, st);
     p->grid_override = 0;
     if (rc) return rc;
     if (overlap) {
@@ -563,10 +581,11 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     int rc = launch_colgemm<W>(p, jobs, st);
     if (rc) return rc;
   }
-  {
+  if (!fuse_l0) {
     CoordSrc cs = p->coord;
     cs.p_offset = ch.p0;
     int grid = p->l0_grid;
+    p->l0_used = p->l0_grid * p->nchunks;
     ProfScope ps(p, PK_L0_GRAD, st);
     static bool l0_attr[64] = {};
     if (!l0_attr[p->device & 63]) {
@@ -605,8 +624,8 @@ int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats,
                        ? 1 : 0;
     ++nd;
   };
-  add(grads[0], p->l0_part, 2 * W, p->l0_grid * nchunks, 3 * W);
-  add(grads[1], p->l0_part + 2 * W, W, p->l0_grid * nchunks, 3 * W);
+  add(grads[0], p->l0_part, 2 * W, p->l0_used, 3 * W);
+  add(grads[1], p->l0_part + 2 * W, W, p->l0_used, 3 * W);
   for (int l = 1; l <= nh; ++l) {
     add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, W * W, p->active_splits,
         int64_t(nh) * W * W);
@@ -981,6 +1000,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->last_tc = (W == 128 || W == 256) && nh > 0 && !(env && atoi(env) == 0);
       env = getenv("SIRENB200_GEN_FIRST");
       p->gen_first = !(env && atoi(env) == 0);
+      env = getenv("SIRENB200_FUSE_L0");
+      p->fuse_l0 = !(env && atoi(env) == 0);
     }
     p->last_grid = p->nsm * 2;
     if (int64_t(p->last_grid) * 8 > chunk_pad) p->last_grid = cdiv(chunk_pad, 8);
@@ -991,7 +1012,11 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     ALLOC(p->last_part, int64_t(p->nchunks) * p->last_grid * (C * W + C + 1));
     p->l0_grid = p->nsm * 2;
     if (p->l0_grid > p->chunk_tiles) p->l0_grid = p->chunk_tiles;
-    ALLOC(p->l0_part, int64_t(p->nchunks) * p->l0_grid * 3 * W);
+    {  // room for the stand-alone kernel's l0_grid rows or the dX-fused reducer's 2 rows per CTA
+      int rows = 2 * (p->chunk_tiles < p->nsm ? p->chunk_tiles : p->nsm);
+      if (rows < p->l0_grid) rows = p->l0_grid;
+      ALLOC(p->l0_part, int64_t(p->nchunks) * rows * 3 * W);
+    }
     cudaError_t e = cudaMemset(p->dz, 0, size_t(D - 1) * p->npix_pad * W * sizeof(__half));
     if (e == cudaSuccess) e = cudaMemset(p->act, 0, size_t(D - 1) * p->npix_pad * W * sizeof(__half));
     if (e != cudaSuccess) {

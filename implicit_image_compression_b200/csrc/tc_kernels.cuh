@@ -126,7 +126,7 @@ struct RowGemmCfg {
   static constexpr uint32_t OFF_CONST = OFF_EO + SEO * kChunkBytes;
   static constexpr uint32_t CONST_BYTES = (MODE == MODE_FWD) ? NDIM * NPARTS * 4 : 0;
   static constexpr uint32_t OFF_BAR = OFF_CONST + CONST_BYTES;
-  static constexpr int NUM_BARS = 2 * SA + 1 + 2 * SEO + 4;
+  static constexpr int NUM_BARS = 2 * SA + 1 + 2 * SEO + 4 + 4;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;  // + align slack
   static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * NDIM);
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
@@ -143,7 +143,12 @@ struct RowGemmArgs {
   // GEN (first hidden layer): the A operand is not loaded but GENERATED — layer 0 of the network,
   // a0 = sin(w0 (W0 x + b0)) from in-kernel coordinates (siren.py:62,66 with is_first) — by four extra
   // warps straight into the A ring, and stored to the activation stash from there.
-  CoordSrc gen_coord;
+  // RED (dX of the first hidden layer): four extra warps read every finished dz[0] chunk back from the
+  // staging buffer and accumulate layer 0's weight / bias gradient (dW0 = dz0^T x, db0 = sum dz0; autograd of
+  // siren.py:62 for the is_first layer), so dz[0] is never re-read from HBM.  red_part: [2 * gridDim.x][3 * NDIM]
+  // = per-CTA partials {dW0 [NDIM, 2], db0 [NDIM]}.
+  float* red_part;
+  CoordSrc gen_coord;   // GEN and RED: coordinates of this launch's pixels
   const float* gen_w0;  // [KDIM, 2] fp32
   const float* gen_b0;  // [KDIM]
   float gen_omega;
@@ -158,12 +163,12 @@ struct RowGemmArgs {
       args.gen_tl[((role) * 8 + (tile_i)) * 8 + (k)] = clock64();                   \
   } while (0)
 
-template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false>
+template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
 // 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue-input producer, 3 = spare, 4..11 = epilogue
 // (two warps per TMEM lane quadrant; each takes 32 of the 64 columns of every output chunk);
 // GEN: warps 0, 2, 3 and 12..16 = A-operand generators (network layer 0), two per 64-wide k-block; the
 // weight load moves to warp 1.
-__global__ void __launch_bounds__(GEN ? 544 : 384, 1)
+__global__ void __launch_bounds__(GEN ? 544 : (RED ? 640 : 384), 1)
 rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
                const RowGemmArgs args, const uint32_t idesc) {
@@ -178,7 +183,8 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* b_full = a_empty + C::SA;
   uint64_t* eo_full = b_full + 1;
   uint64_t* eo_empty = eo_full + C::SEO;
-  uint64_t* tm_full = eo_empty + C::SEO;
+  uint64_t* red_full = eo_empty + C::SEO;
+  uint64_t* tm_full = red_full + 4;  // red_full: one per 64-column chunk index (RED)
   uint64_t* tm_empty = tm_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
 
@@ -193,8 +199,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(b_full, 1);
     for (int i = 0; i < C::SEO; ++i) {
       mbar_init(&eo_full[i], 1);
-      mbar_init(&eo_empty[i], 1);
+      mbar_init(&eo_empty[i], RED ? 3 : 1);  // RED: the store has read the chunk AND both reducer warps have
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&red_full[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tm_full[i], 1);
       mbar_init(&tm_empty[i], 8);
@@ -396,6 +403,61 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+  } else if (RED && warp >= 12) {
+    // ===================== layer-0 gradient: reduce each finished dz[0] chunk over its 128 pixels =========
+    static_assert(!RED || (MODE == MODE_DX && NPARTS == 1 && C::NB <= 4), "RED: dX of the first hidden layer");
+    // two warps per 64-column chunk (64 pixel rows each); lane -> columns nb*64 + 2*lane, +1
+    const int nb = (warp - 12) >> 1, half = (warp - 12) & 1;
+    if (nb < C::NB) {
+      const CoordSrc& cs = args.gen_coord;
+      float sh0 = 0.f, sw0 = 0.f, sb0 = 0.f, sh1 = 0.f, sw1 = 0.f, sb1 = 0.f;
+      const uint32_t lane_off = (uint32_t(lane) & 3u) * 4u;
+      // red_full[nb] belongs to this warp alone and is waited on once per tile, so its parity cannot alias
+      // (a barrier shared between the chunk indices could be probed more than one phase ahead)
+      uint32_t ic = uint32_t(nb), tl = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ic += C::NB, ++tl) {
+        // coordinates of rows lane + 32 q (zero for the padding rows: their dz is zero anyway)
+        float xh[2], xw[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int r = t * kRowsPerTile + half * 64 + lane + 32 * q;
+          xh[q] = xw[q] = 0.f;
+          if (r < args.valid_rows) load_xy(cs, r, xh[q], xw[q]);
+        }
+        const uint32_t s = ic % C::SEO;
+        const uint32_t buf = smem_u32(smem + C::OFF_EO + s * kChunkBytes);
+        mbar_wait(&red_full[nb], tl & 1u);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r = half * 64 + q * 32 + rr;
+            const uint32_t addr = buf + r * 128 + (((uint32_t(lane) >> 2) ^ uint32_t(r & 7)) << 4) + lane_off;
+            const uint32_t hv = ld_shared_u32(addr);
+            const float v0 = __half2float(__ushort_as_half(static_cast<unsigned short>(hv & 0xFFFFu)));
+            const float v1 = __half2float(__ushort_as_half(static_cast<unsigned short>(hv >> 16)));
+            const float ch = __shfl_sync(0xffffffffu, xh[q], rr);
+            const float cw = __shfl_sync(0xffffffffu, xw[q], rr);
+            sh0 = fmaf(v0, ch, sh0);
+            sw0 = fmaf(v0, cw, sw0);
+            sb0 += v0;
+            sh1 = fmaf(v1, ch, sh1);
+            sw1 = fmaf(v1, cw, sw1);
+            sb1 += v1;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&eo_empty[s]);
+      }
+      float* part = args.red_part + (size_t(blockIdx.x) * 2 + half) * 3 * NDIM;
+      const int c0 = nb * 64 + 2 * lane;
+      part[c0 * 2 + 0] = sh0;
+      part[c0 * 2 + 1] = sw0;
+      part[c0 * 2 + 2] = sh1;
+      part[c0 * 2 + 3] = sw1;
+      part[2 * NDIM + c0] = sb0;
+      part[2 * NDIM + c0 + 1] = sb1;
+    }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> f() -> smem -> TMA store =====================
     const int q = warp & 3;
@@ -465,6 +527,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, part * NDIM + nb * 64,
                        args.o_row0 + t * kRowsPerTile);
           tma_store_commit();
+          if (RED) mbar_arrive(&red_full[nb]);
           if (ic > 0) {
             // all but the newest store have finished reading shared memory
             tma_store_wait_read<1>();
