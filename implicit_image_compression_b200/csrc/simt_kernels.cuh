@@ -1150,4 +1150,83 @@ __global__ void kmeans_linspace_kernel(const float* mm, int k, float* cent) {
   cent[j] = (j < k / 2) ? lo + step * float(j) : hi - step * float(k - 1 - j);
 }
 
+// ------------------------------------------------------------------------------------------
+// Gradient exchange of a pixel-sharded fit over NVLink peer memory: in-place sum of a flat
+// fp32 buffer over the ranks of ONE node.  Every rank owns a peer-mapped region {signals, two data
+// buffers}.  Block b of every rank: (1) copies its slice of `io` into the local data buffer of this epoch's
+// parity, (2) tells block b of every peer that the slice is there and waits for theirs (one system-scope
+// flag per (parity, block, source rank)), (3) sums the slice over the ranks' buffers IN RANK ORDER — the
+// same order on every rank, so the replicated weights stay bit-identical — and writes it back to `io`.
+// No trailing barrier: the next exchange uses the other parity, and a rank can only be one exchange ahead
+// of a peer because step (2) needs that peer's flag for the new epoch.  Epochs live in device memory
+// (per block), so the launch is identical every step and can be captured in a CUDA graph.
+// ------------------------------------------------------------------------------------------
+constexpr int kCommMaxRanks = 8;
+constexpr int kCommBlocks = 144;   // one CTA per SM (<= 148): a 1 MB buffer moves in a single pass of float4s
+constexpr int kCommThreads = 512;
+struct CommPeers {
+  float* data[kCommMaxRanks];      // rank r's data region: [2][max_floats]
+  uint32_t* sig[kCommMaxRanks];    // rank r's signal region: [2][kCommBlocks][kCommMaxRanks]
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(kCommThreads) p2p_allreduce_kernel(const CommPeers cp, uint32_t* epoch_b, float* io,
+                                                            int64_t n, int64_t max_floats, int rank,
+                                                            int world) {
+  const int b = blockIdx.x;
+  const uint32_t epoch = epoch_b[b] + 1u;
+  const uint32_t par = epoch & 1u;
+  // slice of this block in units of 4 floats (n is padded to a multiple of 4 by the caller's buffer)
+  const int64_t n4 = (n + 3) / 4;
+  const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = int64_t(b) * per, hi = (lo + per < n4) ? lo + per : n4;
+  float* mine = cp.data[rank] + int64_t(par) * max_floats;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+    reinterpret_cast<float4*>(mine)[i] = reinterpret_cast<const float4*>(io)[i];
+  __syncthreads();
+  if (int(threadIdx.x) < world) {
+    const int r = threadIdx.x;
+    const int64_t slot = (int64_t(par) * kCommBlocks + b) * kCommMaxRanks;
+    __threadfence_system();
+    st_release_sys(cp.sig[r] + slot + rank, epoch);
+    const uint32_t* flag = cp.sig[rank] + slot + r;
+    uint32_t spins = 0;
+    while (ld_acquire_sys(flag) != epoch) {
+      if (++spins > (1u << 26)) {  // seconds: a peer died or never launched; fail loudly instead of hanging
+        printf("sirenb200: gradient exchange timeout: rank %d block %d waiting for rank %d epoch %u\n", rank, b, r,
+               epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      const float4 v = ld_volatile_f4(cp.data[r] + int64_t(par) * max_floats + 4 * i);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(io)[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) epoch_b[b] = epoch;
+}
+
 }  // namespace sb

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <new>
 #include <vector>
 
 #include "../../include/siren_b200.h"
@@ -1390,6 +1391,107 @@ int sirenb200_kmeans_quantize(const float* w, int64_t n, int32_t bits, int32_t i
                         "k-means: top clusters are empty (the reference raises a shape mismatch here, "
                         "quant/kmeans_helper.py:91)"));
   return cleanup(0);
+}
+
+// ---------------------------------------------------------------------------------------
+// gradient exchange over peer memory
+// ---------------------------------------------------------------------------------------
+}  // extern "C" (the comm struct is C++)
+
+struct sirenb200_comm {
+  int rank = 0, world = 1, device = 0;
+  int64_t max_floats = 0;
+  char* base = nullptr;          // local region: signals | epochs | data
+  void* peer_base[kCommMaxRanks] = {};
+  bool connected = false;
+  CommPeers peers{};
+  uint32_t* epoch_b = nullptr;
+};
+static constexpr size_t kCommSigBytes = size_t(2) * kCommBlocks * kCommMaxRanks * sizeof(uint32_t);
+static constexpr size_t kCommEpochBytes = kCommBlocks * sizeof(uint32_t);
+static constexpr size_t kCommHeader = (kCommSigBytes + kCommEpochBytes + 255) / 256 * 256;
+
+extern "C" {
+
+int sirenb200_comm_create(int32_t rank, int32_t world, int64_t max_floats, sirenb200_comm_t* out) {
+  if (!out || world < 1 || world > kCommMaxRanks || rank < 0 || rank >= world || max_floats < 1)
+    return fail(SIRENB200_ERR_INVALID, "comm_create: bad argument (1 <= world <= %d)", kCommMaxRanks);
+  auto* c = new (std::nothrow) sirenb200_comm();
+  if (!c) return fail(SIRENB200_ERR_CUDA, "out of host memory");
+  c->rank = rank;
+  c->world = world;
+  c->max_floats = (max_floats + 3) / 4 * 4;
+  cudaGetDevice(&c->device);
+  const size_t bytes = kCommHeader + size_t(2) * c->max_floats * sizeof(float);
+  if (cudaMalloc(reinterpret_cast<void**>(&c->base), bytes) != cudaSuccess ||
+      cudaMemset(c->base, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    const int rc = fail(SIRENB200_ERR_CUDA, "comm_create: %s", cudaGetErrorString(cudaGetLastError()));
+    if (c->base) cudaFree(c->base);
+    delete c;
+    return rc;
+  }
+  c->epoch_b = reinterpret_cast<uint32_t*>(c->base + kCommSigBytes);
+  c->peer_base[rank] = c->base;
+  if (world == 1) c->connected = true;
+  *out = c;
+  return 0;
+}
+
+int sirenb200_comm_handle(sirenb200_comm_t c, void* handle_out) {
+  if (!c || !handle_out) return fail(SIRENB200_ERR_INVALID, "comm_handle: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c->base));
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int sirenb200_comm_connect(sirenb200_comm_t c, const void* handles) {
+  if (!c || !handles) return fail(SIRENB200_ERR_INVALID, "comm_connect: null argument");
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + size_t(r) * sizeof(h), sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SIRENB200_ERR_CUDA, "comm_connect: cannot map rank %d's buffer (%s) - is peer access available?",
+                  r, cudaGetErrorString(e));
+    }
+  }
+  for (int r = 0; r < c->world; ++r) {
+    char* b = static_cast<char*>(c->peer_base[r]);
+    c->peers.sig[r] = reinterpret_cast<uint32_t*>(b);
+    c->peers.data[r] = reinterpret_cast<float*>(b + kCommHeader);
+  }
+  c->connected = true;
+  return 0;
+}
+
+int sirenb200_comm_allreduce(sirenb200_comm_t c, float* data, int64_t n, sirenb200_stream_t stream) {
+  if (!c || !data || n < 1) return fail(SIRENB200_ERR_INVALID, "comm_allreduce: bad argument");
+  if (!c->connected) return fail(SIRENB200_ERR_STATE, "comm_allreduce before comm_connect");
+  if (n > c->max_floats) return fail(SIRENB200_ERR_INVALID, "comm_allreduce: n exceeds max_floats");
+  if (reinterpret_cast<uintptr_t>(data) & 15u) return fail(SIRENB200_ERR_INVALID, "comm_allreduce: data must be 16-byte aligned");
+  if (c->world == 1) return 0;
+  if (c->peers.data[c->rank] == nullptr) {  // world > 1 needs connect() even though peer_base[rank] is set
+    return fail(SIRENB200_ERR_STATE, "comm_allreduce before comm_connect");
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  p2p_allreduce_kernel<<<kCommBlocks, kCommThreads, 0, st>>>(c->peers, c->epoch_b, data, n, c->max_floats, c->rank,
+                                                    c->world);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int sirenb200_comm_destroy(sirenb200_comm_t c) {
+  if (!c) return 0;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  if (c->base) cudaFree(c->base);
+  delete c;
+  return 0;
 }
 
 }  // extern "C"

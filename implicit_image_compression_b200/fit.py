@@ -41,6 +41,9 @@ class Fitter:
         self.engine = model.engine_for(self.grid, self.row_begin, self.row_end, height=H)
         self.flat = FlatGrads(model.hot_parameters())
         self.flat.attach()
+        # sharded fits exchange gradients with the library's peer-memory kernel when every rank can map
+        # every peer (one node); otherwise through torch.distributed
+        self.peer_exchange = world_size > 1 and self.flat.use_peer_exchange(group)
         self.inv_count = 1.0 / float(img.numel())
         self.step_index = 0
         if use_graph is None:

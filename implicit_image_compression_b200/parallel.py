@@ -8,7 +8,12 @@ makes them the full-image gradients on every rank, and every rank applies the id
 weights stay bit-identical without a broadcast.  Sweeps (config c5) run one independent fit per GPU with no
 communication ("replicas only").
 """
+import ctypes
+import os
+
 import torch
+
+from . import _lib
 
 
 def shard_rows(height, world_size, rank):
@@ -27,7 +32,8 @@ class FlatGrads:
         self.params = list(params)
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total + 4, dtype=torch.float32, device=dev)
+        # padded to a multiple of 4 floats: the peer-memory exchange moves float4s
+        self.flat = torch.zeros((total + 4 + 3) // 4 * 4, dtype=torch.float32, device=dev)
         self.views, off = [], 0
         for p in self.params:
             v = self.flat[off:off + p.numel()].view_as(p)
@@ -35,6 +41,7 @@ class FlatGrads:
             off += p.numel()
         self.stats = self.flat[total:total + 4]
         self.numel = total
+        self.comm = None  # PeerExchange (one kernel over NVLink peer memory) or None (torch.distributed)
 
     def attach(self):
         for p, v in zip(self.params, self.views):
@@ -44,7 +51,61 @@ class FlatGrads:
         """Sum gradients and stats over ranks (no-op without an initialised process group)."""
         if torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size(group) > 1:
-            torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM, group=group)
+            if self.comm is not None:
+                self.comm.all_reduce(self.flat)
+            else:
+                torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.SUM, group=group)
+
+    def use_peer_exchange(self, group=None):
+        """Switch the exchange to the library's peer-memory kernel (CUDA tensors, one node, <= 8 ranks).
+        Returns True when every rank could map every peer; otherwise all ranks keep torch.distributed."""
+        dist = torch.distributed
+        if not (self.flat.is_cuda and dist.is_available() and dist.is_initialized()):
+            return False
+        world = dist.get_world_size(group)
+        if world < 2 or world > 8 or os.environ.get("SIRENB200_PEER_EXCHANGE", "1") == "0":
+            return False
+        comm, ok = None, 1
+        try:
+            comm = PeerExchange(self.flat.numel(), group)
+        except _lib.SirenB200Error:
+            ok = 0
+        flag = torch.tensor([ok], device=self.flat.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 1:
+            self.comm = comm
+            return True
+        return False
+
+
+class PeerExchange:
+    """sirenb200_comm_*: every rank allocates a peer-visible region, the 64-byte CUDA IPC handles travel
+    through torch.distributed (any transport would do), and from then on one kernel per step sums the flat
+    gradient buffer over NVLink (include/siren_b200.h)."""
+
+    def __init__(self, max_floats, group=None):
+        dist = torch.distributed
+        self.lib = _lib.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.handle = ctypes.c_void_p()
+        _lib.check(self.lib.sirenb200_comm_create(self.rank, self.world, int(max_floats),
+                                                  ctypes.byref(self.handle)))
+        mine = ctypes.create_string_buffer(64)
+        _lib.check(self.lib.sirenb200_comm_handle(self.handle, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=group)
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
+        _lib.check(self.lib.sirenb200_comm_connect(self.handle, blob))
+        dist.barrier(group=group)
+
+    def all_reduce(self, flat):
+        _lib.check(self.lib.sirenb200_comm_allreduce(self.handle, flat.data_ptr(), flat.numel(),
+                                                     torch.cuda.current_stream().cuda_stream))
+
+    def close(self):
+        if self.handle:
+            self.lib.sirenb200_comm_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
 
 
 def assign_replicas(num_jobs, world_size, rank):

@@ -154,6 +154,24 @@ int sirenb200_profile_read(sirenb200_handle_t h, float* h_total_ms, int32_t* h_c
  * SIRENB200_TIMELINE environment variable at create time) to a HOST array of n int64. */
 int sirenb200_debug_timeline(sirenb200_handle_t h, long long* h_out, int32_t n);
 
+/* ---- gradient exchange for pixel-sharded fits (SURVEY.md §8e "allreduce_grads") ---------------------------
+ * One process per GPU of ONE node.  The reference has no distributed code; this is the exchange step of the
+ * row-sharded fit: an in-place SUM of a flat fp32 buffer [all dW | all db | sum_sq_err, -, nonfinite, -] over
+ * the ranks, done by one kernel over NVLink peer memory (P2P loads of every rank's buffer, summed in rank
+ * order so all ranks get bit-identical results).  Setup: every rank calls comm_create (allocates its
+ * peer-visible region) and comm_handle (64-byte CUDA IPC handle); the caller exchanges the handles by any
+ * means (torch.distributed all_gather in the Python mirror) and passes all of them, in rank order, to
+ * comm_connect.  comm_allreduce is asynchronous on `stream`, takes no per-step host state (epochs live on the
+ * device) and can be captured in a CUDA graph; `data` must be 16-byte aligned with room for n rounded up to a
+ * multiple of 4 floats, n <= max_floats.  A peer that never arrives makes the kernel trap after a few
+ * seconds (sticky CUDA error) rather than hang. */
+typedef struct sirenb200_comm* sirenb200_comm_t;
+int sirenb200_comm_create(int32_t rank, int32_t world, int64_t max_floats, sirenb200_comm_t* out);
+int sirenb200_comm_handle(sirenb200_comm_t c, void* handle_out_64_bytes);
+int sirenb200_comm_connect(sirenb200_comm_t c, const void* handles_world_x_64_bytes);
+int sirenb200_comm_allreduce(sirenb200_comm_t c, float* data, int64_t n, sirenb200_stream_t stream);
+int sirenb200_comm_destroy(sirenb200_comm_t c);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t sirenb200_launch_count(void);
 
