@@ -40,10 +40,10 @@ def f_step(n_pix, depth=None, w=None):
     return 2.0 * n_pix * (3 * (depth - 2) * w * w + 13 * w)
 
 
-def workload_config(n_gpus, exchange="NCCL all-reduce"):
+def workload_config(n_gpus):
     return {
         "workload": f"{'c2' if HIDDEN == 256 else 'c3'}: SIREN hidden {HIDDEN} depth {DEPTH}, {H}x{W} synthetic 16-bit RGB, dense Adam fit step"
-                    + ("" if n_gpus == 1 else f", rows sharded over {n_gpus} ranks + gradient exchange by {exchange}"),
+                    + ("" if n_gpus == 1 else f", rows sharded over {n_gpus} ranks + one gradient all-reduce per step"),
         "hidden_size": HIDDEN, "depth": DEPTH, "height": H, "width": W, "pixels": H * W,
         "optimizer": "adam lr 3e-4 + StepLR(2000, 0.5)", "precision_mode": "f16tc",
         "l2": "no flush: each step streams ~2 GB of activation stash (>> 126 MB L2)",
@@ -381,9 +381,9 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
-        "data": "synthetic",
-        "config": workload_config(world, "the library's peer-memory kernel (NVLink P2P)" if fitter.peer_exchange
-                                  else "NCCL all-reduce"),
+        "data": "synthetic", "config": workload_config(world),
+        "exchange": None if world == 1 else ("library peer-memory kernel (NVLink P2P, CUDA IPC)"
+                                             if fitter.peer_exchange else "NCCL all-reduce"),
         "final_loss": float(losses[-1].item()), "cuda_graph": bool(graph_mode and fitter._graph is not None),
         "ms_per_step_eager_profiled": ms_eager / args.steps,
         "roofline": roofline, "roofline_step": roofline_step, "kernel_ms": kernel_ms,
