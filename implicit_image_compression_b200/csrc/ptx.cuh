@@ -86,6 +86,17 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 // ----------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start while its
+// predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed and
+// its writes are visible (a no-op for a normally launched kernel); pdl_launch_dependents() lets the
+// successor's CTAs be scheduled as SMs free up.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

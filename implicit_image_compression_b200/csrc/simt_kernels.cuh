@@ -1215,14 +1215,20 @@ __global__ void __launch_bounds__(kCommThreads) p2p_allreduce_kernel(const CommP
   }
   __syncthreads();
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {
-      const float4 v = ld_volatile_f4(cp.data[r] + int64_t(par) * max_floats + 4 * i);
-      acc.x += v.x;
-      acc.y += v.y;
-      acc.z += v.z;
-      acc.w += v.w;
-    }
+    // all peers' loads in flight together (NVLink round trips overlap), then the rank-ordered sum
+    float4 v[kCommMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kCommMaxRanks; ++r)
+      if (r < world) v[r] = ld_volatile_f4(cp.data[r] + int64_t(par) * max_floats + 4 * i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < kCommMaxRanks; ++r)
+      if (r < world) {
+        acc.x += v[r].x;
+        acc.y += v[r].y;
+        acc.z += v[r].z;
+        acc.w += v[r].w;
+      }
     reinterpret_cast<float4*>(io)[i] = acc;
   }
   __syncthreads();

@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/siren_b200.h"
@@ -95,6 +96,7 @@ struct sirenb200_plan {
   __half* wlt16 = nullptr;  // [W, 64]
   CUtensorMap tm_wl{}, tm_wlt{};
   bool last_tc = false;
+  bool pdl = true;          // programmatic dependent launch of the GEMM kernels (SIRENB200_PDL=0: off)
   bool fuse_l0 = true;      // layer-0 gradient reduced inside the dX GEMM of the first hidden layer (SIRENB200_FUSE_L0=0: own kernel)
   int l0_used = 0;          // partial rows of l0_part written by the last backward
   int last_rowgemm_grid = 0;
@@ -186,6 +188,25 @@ int check_ready(const sirenb200_plan* p) {
 // ---------------------------------------------------------------------------------------
 // rowgemm / colgemm launch helpers
 // ---------------------------------------------------------------------------------------
+// Launch with (pdl) or without programmatic stream serialisation.  A kernel launched with it may begin while
+// its predecessor is still draining; every such kernel calls griddepcontrol.wait before it touches anything
+// the predecessor produced.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <int W, int MODE, bool GEN = false, bool RED = false>
 int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap& tmE, const CUtensorMap& tmO, const RowGemmArgs& args,
@@ -206,7 +227,8 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
-    kfn<<<grid, GEN ? 544 : (RED ? 640 : 384), Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmE, tmO, args, idesc);
+    launch_ex(kfn, dim3(grid), dim3(GEN ? 544 : (RED ? 640 : 384)), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, tmA,
+              tmB, tmE, tmO, args, idesc);
   }
   LAUNCH_CHECK();
   p->last_rowgemm_grid = grid;
@@ -227,9 +249,8 @@ int launch_colgemm(sirenb200_plan* p, const ColGemmJobs& jobs, cudaStream_t st) 
   const int grid = jobs.num_problems * jobs.mblocks * jobs.nparts * jobs.splits;
   {
     ProfScope ps(p, PK_DW_GEMM, st);
-    kfn<<<grid, 256, Cfg::SMEM_BYTES, st>>>(p->tm_dz, p->tm_act, jobs,
-                                            umma_idesc(128, NT, 0, 0, 1, 1),
-                                            umma_idesc(128, 16, 0, 0, 1, 1));
+    launch_ex(kfn, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_dz, p->tm_act, jobs,
+              umma_idesc(128, NT, 0, 0, 1, 1), umma_idesc(128, 16, 0, 0, 1, 1));
   }
   LAUNCH_CHECK();
   return 0;
@@ -369,6 +390,7 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     ra.valid_rows = int(ch.npix);
     ra.omega = omega_of(p, l);
     ra.bias = prm[2 * l + 1];
+    ra.b_early = (l >= 2) ? 1 : 0;  // layer 1 follows the weight-staging kernel directly
     int rc;
     if constexpr (kCanGen) {
       if (l == 1 && gen_first) {
@@ -418,7 +440,8 @@ int launch_last_tc(sirenb200_plan* p, const float* const* prm, int mode, const f
     la.dbg = p->dbg_timeline ? p->dbg_timeline + 3 * 4 * 8 * 16 : nullptr;
     {
       ProfScope ps(p, PK_LAST, st);
-      kfn<<<p->last_grid, 384, Cfg::SMEM_BYTES, st>>>(p->tm_act, p->tm_dz, p->tm_wl, p->wlt16, la);
+      launch_ex(kfn, dim3(p->last_grid), dim3(384), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_act, p->tm_dz,
+                p->tm_wl, static_cast<const __half*>(p->wlt16), la);
     }
     LAUNCH_CHECK();
     return 0;
@@ -549,6 +572,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     ra.e_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.o_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.valid_rows = int(ch.npix);
+    ra.b_early = 1;  // omega W^T was staged at the start of the step, at least two kernels ago
     p->grid_override = overlap ? p->dx_grid : 0;
     int rc;
     bool done = false;
@@ -1001,6 +1025,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->last_tc = (W == 128 || W == 256) && nh > 0 && !(env && atoi(env) == 0);
       env = getenv("SIRENB200_GEN_FIRST");
       p->gen_first = !(env && atoi(env) == 0);
+      env = getenv("SIRENB200_PDL");
+      p->pdl = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_FUSE_L0");
       p->fuse_l0 = !(env && atoi(env) == 0);
     }

@@ -152,6 +152,9 @@ struct RowGemmArgs {
   const float* gen_w0;  // [KDIM, 2] fp32
   const float* gen_b0;  // [KDIM]
   float gen_omega;
+  // 1: the resident B operand was written at least two kernels ago, so it may be fetched BEFORE waiting for
+  // the predecessor kernel (programmatic dependent launch); 0: fetch it after the wait
+  int b_early;
   long long* gen_tl;  // SIRENB200_TIMELINE: clock64 stamps of block 0 (debug)
 };
 
@@ -225,13 +228,23 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // generator index (GEN only): warps 0, 2, 3, 12, 13, 14, 15, 16 -> 0..7
-  const int gi = !GEN ? -1 : (warp == 0 ? 0 : (warp == 2 || warp == 3) ? warp - 1 : (warp >= 12 ? warp - 9 : -1));
-  if (GEN && warp == 1 && lane == 0) {
+  // resident B: issued before the dependency wait when it does not depend on the predecessor kernel
+  const bool b_loader = !C::STREAM_B && lane == 0 && warp == (GEN ? 1 : 0);
+  if (b_loader && args.b_early) {
     mbar_expect_tx(b_full, C::KB * C::B_KB_BYTES);
     for (int kb = 0; kb < C::KB; ++kb)
       tma_load_2d(smem + C::OFF_B + kb * C::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
   }
+  pdl_wait();
+  pdl_launch_dependents();
+  if (b_loader && !args.b_early) {
+    mbar_expect_tx(b_full, C::KB * C::B_KB_BYTES);
+    for (int kb = 0; kb < C::KB; ++kb)
+      tma_load_2d(smem + C::OFF_B + kb * C::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
+  }
+
+  // generator index (GEN only): warps 0, 2, 3, 12, 13, 14, 15, 16 -> 0..7
+  const int gi = !GEN ? -1 : (warp == 0 ? 0 : (warp == 2 || warp == 3) ? warp - 1 : (warp >= 12 ? warp - 9 : -1));
   if (GEN && gi >= 0) {
     // ===================== A generator: layer 0 of the network -> A ring (+ stash) =====================
     // Two warps per 64-wide k-block (16 of the 32 four-row iterations each): the 8 column groups x 3
@@ -334,11 +347,6 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 0) {
     // ===================== TMA producer: B once, then A k-blocks =====================
     if (lane == 0) {
-      if (!C::STREAM_B) {
-        mbar_expect_tx(b_full, C::KB * C::B_KB_BYTES);
-        for (int kb = 0; kb < C::KB; ++kb)
-          tma_load_2d(smem + C::OFF_B + kb * C::B_KB_BYTES, &tmB, b_full, kb * 64, 0);
-      }
       uint32_t ia = 0;
       for (int it = blockIdx.x; !GEN && it < num_items; it += gridDim.x) {
         const int t = it / NPARTS, part = it % NPARTS;
@@ -653,6 +661,8 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything below reads what the preceding kernels of the step produced
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1408,6 +1418,8 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything below reads what the preceding kernels of the step produced
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== producer =====================
