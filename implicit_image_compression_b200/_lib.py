@@ -72,7 +72,7 @@ def load():
     lib.sirenb200_adam_step.argtypes = [c_int32, vpp, vpp, vpp, vpp, vpp, POINTER(c_int64), c_float,
                                         c_float, c_float, c_float, c_int32, c_float, vp, c_int32, vp]
     lib.sirenb200_apply_mask.argtypes = [vp, vp, c_int64, vp]
-    lib.sirenb200_sched_step.argtypes = [vp, vp, c_float, vp, c_int32, vp]
+    lib.sirenb200_sched_step.argtypes = [vp, vp, c_float, vp, c_int32, vp, vp]
     lib.sirenb200_adam_step_dev.argtypes = [c_int32, vpp, vpp, vpp, vpp, vpp, POINTER(c_int64), c_float,
                                             c_float, c_float, vp, c_float, vp, c_int32, vp]
     lib.sirenb200_comm_create.argtypes = [c_int32, c_int32, c_int64, vpp]

@@ -838,6 +838,7 @@ struct SchedArgs {
   float inv_count;      // >0: loss = stats[0] * inv_count (pixel-sharded fits), else stats[1]
   float* loss_ring;
   int ring_len;
+  float* loss_host;     // optional: host-mapped (pinned) float that also receives the loss
 };
 __global__ void sched_step_kernel(const SchedArgs a) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -848,7 +849,9 @@ __global__ void sched_step_kernel(const SchedArgs a) {
   const double bc2 = 1.0 - pow(double(float(a.state[5])), double(step + 1));  // on the eager path too
   a.state[6] = lr / bc1;
   a.state[7] = sqrt(bc2);
-  if (a.loss_ring) a.loss_ring[step % a.ring_len] = a.inv_count > 0.f ? a.stats[0] * a.inv_count : a.stats[1];
+  const float loss = a.inv_count > 0.f ? a.stats[0] * a.inv_count : a.stats[1];
+  if (a.loss_ring) a.loss_ring[step % a.ring_len] = loss;
+  if (a.loss_host) *a.loss_host = loss;
   a.state[0] = double(step + 1);
 }
 

@@ -1283,9 +1283,9 @@ int sirenb200_adam_step(int32_t nt, float* const* prm, float* const* grads, floa
 }
 
 int sirenb200_sched_step(double* state, const float* stats, float inv_count, float* loss_ring,
-                         int32_t ring_len, sirenb200_stream_t stream) {
+                         int32_t ring_len, float* loss_host, sirenb200_stream_t stream) {
   if (!state || !stats) return fail(SIRENB200_ERR_INVALID, "null argument");
-  SchedArgs a{state, stats, inv_count, loss_ring, ring_len > 0 ? ring_len : 1};
+  SchedArgs a{state, stats, inv_count, loss_ring, ring_len > 0 ? ring_len : 1, loss_host};
   sched_step_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   LAUNCH_CHECK();
   return 0;

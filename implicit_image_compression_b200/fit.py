@@ -99,7 +99,7 @@ class Fitter:
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.sirenb200_sched_step(g["state"].data_ptr(), flat.stats.data_ptr(),
                                             self.inv_count if self.world > 1 else 0.0,
-                                            g["ring"].data_ptr(), _RING, stream))
+                                            g["ring"].data_ptr(), _RING, g["host_loss"].data_ptr(), stream))
         _lib.check(lib.sirenb200_adam_step_dev(
             g["n"], g["p"], g["g"], g["m"], g["v"], g["mask"], g["numel"], g["beta1"], g["beta2"],
             g["eps"], g["state"].data_ptr(), 1.0, flat.stats[2:3].data_ptr(), 0, stream))
@@ -125,6 +125,9 @@ class Fitter:
         self._g = {
             "state": torch.zeros(8, dtype=torch.float64, device=dev),
             "ring": torch.zeros(_RING, dtype=torch.float32, device=dev),
+            # pinned host float the schedule kernel also writes the loss to (unified addressing: the device
+            # uses the host pointer), read by step_loss() after a stream synchronisation
+            "host_loss": torch.zeros(1, dtype=torch.float32).pin_memory(),
             "n": n, "p": _lib.ptr_array([p.data for p in params]),
             "g": _lib.ptr_array([p.grad for p in params]),
             "m": _lib.ptr_array([opt.state[p]["exp_avg"] for p in params]),
@@ -200,7 +203,8 @@ class Fitter:
             done += 1
         value = None
         if losses is None:
-            value = g["ring"][step0 % _RING].item()
+            torch.cuda.current_stream().synchronize()
+            value = float(g["host_loss"][0])
         elif k == 1:
             losses[offset:offset + 1] = g["ring"][step0 % _RING:step0 % _RING + 1]
         else:

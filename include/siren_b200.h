@@ -109,10 +109,12 @@ int sirenb200_adam_step(int32_t n_tensors, float* const* h_params, float* const*
  * [2] StepLR gamma, [3] StepLR period, [4] beta1, [5] beta2, [6]/[7] outputs (step size, sqrt(1-beta2^t)).
  * sirenb200_sched_step computes [6],[7] for the step about to run (train_helper.py:80-84 StepLR + Adam bias
  * correction), stores the loss of the step that just ran into loss_ring[step % ring_len] (stats[1], or
- * stats[0]*inv_count when inv_count > 0, i.e. after an all-reduce of pixel shards) and increments [0];
+ * stats[0]*inv_count when inv_count > 0, i.e. after an all-reduce of pixel shards) and, when loss_host is not
+ * NULL, also into that host-mapped (pinned, device-accessible) float - train_epoch's "return loss.item()"
+ * then costs a stream synchronisation and a host read instead of a copy kernel + cudaMemcpy - and increments [0];
  * sirenb200_adam_step_dev is sirenb200_adam_step reading the schedule from sched_state. */
 int sirenb200_sched_step(double* sched_state, const float* stats, float inv_count, float* loss_ring,
-                         int32_t ring_len, sirenb200_stream_t stream);
+                         int32_t ring_len, float* loss_host, sirenb200_stream_t stream);
 int sirenb200_adam_step_dev(int32_t n_tensors, float* const* h_params, float* const* h_grads,
                             float* const* h_exp_avg, float* const* h_exp_avg_sq,
                             const float* const* h_mask, const int64_t* h_numel, float beta1, float beta2,
