@@ -96,6 +96,7 @@ struct sirenb200_plan {
   __half* wlt16 = nullptr;  // [W, 64]
   CUtensorMap tm_wl{}, tm_wlt{};
   bool last_tc = false;
+  bool tail_fused = true;   // last hidden GEMM + output layer + loss + dZ in one kernel (SIRENB200_TAIL=0: two kernels)
   bool pdl = true;          // programmatic dependent launch of the GEMM kernels (SIRENB200_PDL=0: off)
   bool fuse_l0 = true;      // layer-0 gradient reduced inside the dX GEMM of the first hidden layer (SIRENB200_FUSE_L0=0: own kernel)
   int l0_used = 0;          // partial rows of l0_part written by the last backward
@@ -363,7 +364,8 @@ int launch_fused_fwd(sirenb200_plan* p, const Chunk& ch, cudaStream_t st) {
 }
 
 template <int W>
-int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
+int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st,
+                     bool skip_last_hidden = false) {
   const int nh = p->D - 2;
   if (p->fused_fwd && ch.index == 0 && p->nchunks == 1) return launch_fused_fwd<W>(p, ch, st);
   // Layer 0 runs inside the first hidden layer's GEMM (its A operand is generated in the kernel) when
@@ -381,7 +383,7 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
                                                   p->act + ch.p0 * W, ch.npix, ch.npix_pad);
   }
   LAUNCH_CHECK();
-  for (int l = 1; l <= nh; ++l) {
+  for (int l = 1; l <= (skip_last_hidden ? nh - 1 : nh); ++l) {
     RowGemmArgs ra{};
     ra.num_tiles = ch.ntiles;
     ra.a_row0 = int((l - 1) * p->npix_pad + ch.p0);
@@ -447,6 +449,48 @@ int launch_last_tc(sirenb200_plan* p, const float* const* prm, int mode, const f
     return 0;
   } else {
     return fail(SIRENB200_ERR_INVALID, "tensor-core last layer needs hidden 128 or 256");
+  }
+}
+
+// training step: last hidden layer's GEMM + output layer + loss + dZ in one kernel (tail_tc_kernel)
+template <int W>
+int launch_tail(sirenb200_plan* p, const float* const* prm, const float* img, float* pred, const Chunk& ch,
+                cudaStream_t st) {
+  if constexpr (W == 128 || W == 256) {
+    using Cfg = TailCfg<W>;
+    auto kfn = tail_tc_kernel<W>;
+    static bool attr_set[64] = {};
+    if (!attr_set[p->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(Cfg::SMEM_BYTES)));
+      attr_set[p->device & 63] = true;
+    }
+    const int D = p->D, C = p->C, nh = D - 2;
+    TailArgs ta{};
+    ta.num_tiles = ch.ntiles;
+    ta.a_row0 = int((nh - 1) * p->npix_pad + ch.p0);
+    ta.dz_row0 = int(nh * p->npix_pad + ch.p0);
+    ta.npix = ch.npix;
+    ta.omega = omega_of(p, nh);
+    ta.bias = prm[2 * nh + 1];
+    ta.b_last = prm[2 * (D - 1) + 1];
+    ta.img = img + ch.p0 * C;
+    ta.pred = pred ? pred + ch.p0 * C : nullptr;
+    ta.part = p->last_part + size_t(ch.index) * p->last_grid * (C * W + C + 1);
+    ta.gscale = p->gstate;
+    ta.C = C;
+    ta.outermost_linear = p->cfg.outermost_linear;
+    ta.omega_last = omega_of(p, D - 1);
+    ta.dbg = p->dbg_timeline ? p->dbg_timeline + 3 * 4 * 8 * 16 : nullptr;
+    {
+      ProfScope ps(p, PK_LAST, st);
+      launch_ex(kfn, dim3(p->last_grid), dim3(640), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_act,
+                p->tm_w[nh - 1], p->tm_dz, p->tm_wl, static_cast<const __half*>(p->wlt16), ta);
+    }
+    LAUNCH_CHECK();
+    return 0;
+  } else {
+    return fail(SIRENB200_ERR_INVALID, "tail kernel needs hidden 128 or 256");
   }
 }
 
@@ -686,8 +730,12 @@ int tc_run(sirenb200_plan* p, const float* const* prm, int mode, const float* im
   if (mode != 2) rc = tc_prep<W>(p, prm, st, mode == 1 ? stats : nullptr);
   for (const Chunk& ch : chunks) {
     if (rc) return rc;
-    if (mode != 2) rc = tc_forward_chunk<W>(p, prm, ch, st);
-    if (!rc) rc = tc_last_chunk<W>(p, prm, mode, img_or_dpred, pred, ch, st);
+    // training step with at least two hidden GEMM layers: the last one is fused with the output layer
+    const bool tail = mode == 1 && p->tail_fused && p->last_tc && p->D - 2 >= 2 && p->nchunks == 1 &&
+                      !p->fused_fwd && img_or_dpred;
+    if (mode != 2) rc = tc_forward_chunk<W>(p, prm, ch, st, tail);
+    if (!rc) rc = tail ? launch_tail<W>(p, prm, img_or_dpred, pred, ch, st)
+                       : tc_last_chunk<W>(p, prm, mode, img_or_dpred, pred, ch, st);
     if (!rc && mode != 0) rc = tc_backward_chunk<W>(p, prm, ch, st);
   }
   if (!rc && mode != 0) rc = tc_reduce<W>(p, grads, scale, stats, int(chunks.size()), st);
@@ -1025,6 +1073,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->last_tc = (W == 128 || W == 256) && nh > 0 && !(env && atoi(env) == 0);
       env = getenv("SIRENB200_GEN_FIRST");
       p->gen_first = !(env && atoi(env) == 0);
+      env = getenv("SIRENB200_TAIL");
+      p->tail_fused = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_PDL");
       p->pdl = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_FUSE_L0");

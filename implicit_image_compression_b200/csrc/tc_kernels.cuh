@@ -1675,4 +1675,489 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// tail kernel (training step, hidden 128 / 256, at least two hidden GEMM layers): the LAST hidden layer's
+// forward GEMM fused with everything last_layer_tc_kernel does, so that the last hidden activation is never
+// written to (or re-read from) HBM.  Per 128-pixel tile:
+//   z  = act[D-3] . W^T            UMMA M=128, N=W, K=W (A and W k-blocks streamed through a 2-stage ring)
+//   a  = sin(omega (z + b))        epilogue 1 -> signed-half tile T in shared memory (never stored)
+//   y  = a . W_last^T              UMMA N=16 -> pred, squared error, seed g           (epilogue 2)
+//   dW_last^T += a^T . g           UMMA M=128 features, N=16, K=128 pixels (T read MN-major)
+//   dA = g . (omega W_last)        UMMA K=16, two N=W/2 halves through one TMEM region
+//   dz[D-2] = dA (*) +-sqrt(1-a^2) epilogue 3, in place over T, TMA-stored chunk by chunk
+// One thread issues every MMA from a small event loop, so the next tile's GEMM k-blocks are issued
+// between the short dependent steps of the current tile and overlap its epilogues.
+// (reference: siren.py:56-68,110-118,131; train_helper.py:151-161 mse + backward)
+// ------------------------------------------------------------------------------------------
+struct TailArgs {
+  int num_tiles;
+  int a_row0;            // first row of act[D-3] (GEMM input) inside the activation tensor map
+  int dz_row0;           // first row of dz[D-2] inside the dz tensor map
+  int64_t npix;
+  float omega;           // omega of the last hidden layer
+  const float* bias;     // [W] bias of the last hidden layer
+  const float* b_last;   // [C]
+  const float* img;      // target [npix, C]
+  float* pred;           // optional
+  float* part;           // per-CTA partials [grid][C*W + C + 1]
+  const float* gscale;
+  int C;
+  int outermost_linear;
+  float omega_last;
+  long long* dbg;        // optional timeline (block 0): dbg[tile * 16 + k], first 12 tiles
+};
+
+#define SB_DBG_T(tile_i, k)                                                 \
+  do {                                                                      \
+    if (args.dbg && blockIdx.x == 0 && (tile_i) < 12)                       \
+      args.dbg[(tile_i) * 16 + (k)] = clock64();                            \
+  } while (0)
+
+template <int W>
+struct TailCfg {
+  static_assert(W == 128 || W == 256, "tail kernel: hidden 128 or 256");
+  static constexpr int NCH = W / 64;   // 64-wide chunks of the tile == k-blocks of the GEMM
+  static constexpr int CPH = NCH / 2;  // chunks per half of T (dA and the dz stores go half by half)
+  static constexpr int S = 2;          // ring stages
+  static constexpr uint32_t B_KB_BYTES = W * 128;
+  static constexpr uint32_t STAGE_BYTES = kChunkBytes + B_KB_BYTES;
+  static constexpr uint32_t OFF_T = 0;
+  static constexpr uint32_t OFF_ST = NCH * kChunkBytes;
+  static constexpr uint32_t OFF_WL = OFF_ST + S * STAGE_BYTES;
+  static constexpr uint32_t OFF_WLT = OFF_WL + NCH * 2048;
+  static constexpr uint32_t WLT_BYTES = W * 32;
+  static constexpr uint32_t OFF_G = OFF_WLT + WLT_BYTES;
+  static constexpr uint32_t OFF_CONST = OFF_G + 4096;  // omega * bias [W] fp32
+  static constexpr uint32_t OFF_RED = OFF_CONST + W * 4;
+  static constexpr uint32_t OFF_BAR = OFF_RED + 16 * 8 * 4;
+  static constexpr int NUM_BARS = 2 * S + 8 + 4;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+  static constexpr uint32_t TM_ACC = 0, TM_DA = W, TM_Y = W + W / 2, TM_DW = W + W / 2 + 16;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(TM_DW + (W / 128) * 16 <= 512, "TMEM columns");
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
+};
+
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_dyn(int n) {
+  // cp.async.bulk.wait_group.read takes an immediate: n in [0, N]
+  if constexpr (N > 0) {
+    if (n == N) {
+      tma_store_wait_read<N>();
+      return;
+    }
+    tma_store_wait_read_dyn<N - 1>(n);
+  } else {
+    tma_store_wait_read<0>();
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(640, 1)
+tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmWl,
+               const __half* __restrict__ wlt_interleaved, const TailArgs args) {
+  using C = TailCfg<W>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* st_full = bars;              // [S]
+  uint64_t* st_empty = st_full + C::S;   // [S]
+  uint64_t* w_full = st_empty + C::S;
+  uint64_t* acc_full = w_full + 1;   // GEMM of the tile retired
+  uint64_t* acc_free = acc_full + 1; // epilogue 1 has drained the accumulator (8 warps)
+  uint64_t* t_ready = acc_free + 1;  // [4, two used] half of T written and fenced (16 warps each)
+  uint64_t* y_full = t_ready + 4;
+  uint64_t* g_ready = y_full + 1;    // seed tile written (4 warps)
+  uint64_t* da_full = g_ready + 1;   // two phases per tile: dA half 0 (+ dW_last), dA half 1
+  uint64_t* da_free = da_full + 1;   // half 0 has been read out of TMEM (8 warps)
+  uint64_t* fin_done = da_free + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::S; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, 16);
+    for (int i = 0; i < 4; ++i) mbar_init(&t_ready[i], 16);
+    mbar_init(y_full, 1);
+    mbar_init(g_ready, 4);
+    mbar_init(da_full, 1);
+    mbar_init(da_free, 16);
+    mbar_init(fin_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAct);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmDz);
+    tma_prefetch_desc(&tmWl);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    float* cst = reinterpret_cast<float*>(smem + C::OFF_CONST);
+    for (int i = threadIdx.x - 128; i < W; i += 512) cst[i] = args.omega * args.bias[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // the small weight operands were staged at the start of the step: fetch them before the dependency wait
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(w_full, C::NCH * 2048 + C::WLT_BYTES);
+    for (int kb = 0; kb < C::NCH; ++kb)
+      tma_load_2d(smem + C::OFF_WL + kb * 2048, &tmWl, w_full, kb * 64, 0);
+    bulk_load_1d(smem + C::OFF_WLT, wlt_interleaved, C::WLT_BYTES, w_full);
+  }
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== producer: A and W k-blocks =====================
+    if (lane == 0) {
+      uint32_t ia = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < C::NCH; ++kb, ++ia) {
+          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
+          mbar_wait(&st_empty[s], ph ^ 1u);
+          mbar_expect_tx(&st_full[s], C::STAGE_BYTES);
+          uint8_t* stage = smem + C::OFF_ST + s * C::STAGE_BYTES;
+          tma_load_2d(stage, &tmAct, &st_full[s], kb * 64, args.a_row0 + t * kRowsPerTile);
+          tma_load_2d(stage + kChunkBytes, &tmW, &st_full[s], kb * 64, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: event loop over {tile chain, next GEMM k-block} =====================
+    if (lane == 0) {
+      const uint32_t id_gemm = umma_idesc(128, W, 0, 0, 0, 0);
+      const uint32_t id_y = umma_idesc(128, 16, 0, 0, 0, 0);
+      const uint32_t id_da = umma_idesc(128, W / 2, 0, 0, 0, 0);
+      const uint32_t id_dw = umma_idesc(128, 16, 0, 0, 1, 1);
+      const uint32_t t_addr = smem_u32(smem + C::OFF_T);
+      const uint32_t wl_addr = smem_u32(smem + C::OFF_WL);
+      const uint32_t wlt_addr = smem_u32(smem + C::OFF_WLT);
+      const uint32_t g_addr = smem_u32(smem + C::OFF_G);
+      int my_tiles = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) ++my_tiles;
+      mbar_wait(w_full, 0);
+      uint32_t ig = 0, kbg = 0, ia = 0;  // GEMM: tile index (local), next k-block, ring counter
+      uint32_t ic = 0, cst = 0, ykb = 0;  // chain: tile index (local), state 0 y (per chunk) / 1 dW+dA0 / 2 dA1
+      uint32_t idle = 0;
+      while (ic < uint32_t(my_tiles)) {
+        bool did = false;
+        if (cst == 0) {
+          // y accumulates half by half, as soon as epilogue 1 has written each half of T
+          if (mbar_try_wait(&t_ready[ykb / C::CPH], ic & 1u)) {
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < C::CPH; ++cc, ++ykb)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = umma_smem_desc(t_addr + ykb * kChunkBytes + k * 32, 0, 1024, 2);
+                const uint64_t db = umma_smem_desc(wl_addr + ykb * 2048 + k * 32, 0, 1024, 2);
+                umma_f16(tmem_base + C::TM_Y, da, db, id_y, (ykb | uint32_t(k)) != 0 ? 1u : 0u);
+              }
+            if (ykb == uint32_t(C::NCH)) {
+              umma_commit(y_full);
+              ykb = 0;
+              cst = 1;
+            }
+            did = true;
+          }
+        } else if (cst == 1) {
+          if (mbar_try_wait(g_ready, ic & 1u)) {
+            tc_fence_after();
+            // dW_last^T[feature, channel] += T^T . g (T read MN-major).  Epilogue 3 overwrites T in place half
+            // by half, so only the feature blocks living in the first half of T have to retire before dA
+            // half 0 is handed over; the others ride with dA half 1.
+            auto dw_block = [&](int mb) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t da = umma_smem_desc(t_addr + 2 * mb * kChunkBytes + k * 2048, kChunkBytes, 1024, 2);
+                const uint64_t db = umma_smem_desc(g_addr + k * 512, 256, 128, 0);
+                umma_f16(tmem_base + C::TM_DW + mb * 16, da, db, id_dw, (ic | uint32_t(k)) != 0 ? 1u : 0u);
+              }
+            };
+            if (W == 128) dw_block(0);            // one feature block spans both halves of T
+            if (W == 256) dw_block(0);            // chunks 0,1 = half 0
+            umma_f16(tmem_base + C::TM_DA, umma_smem_desc(g_addr, 128, 256, 0),
+                     umma_smem_desc(wlt_addr, 128, 256, 0), id_da, 0u);
+            umma_commit(da_full);
+            if (W == 256) dw_block(1);            // chunks 2,3 = half 1: retires before the next commit
+            cst = 2;
+            did = true;
+          }
+        } else {
+          if (mbar_try_wait(da_free, ic & 1u)) {
+            tc_fence_after();
+            umma_f16(tmem_base + C::TM_DA, umma_smem_desc(g_addr, 128, 256, 0),
+                     umma_smem_desc(wlt_addr + W * 16, 128, 256, 0), id_da, 0u);
+            umma_commit(da_full);
+            cst = 0;
+            ++ic;
+            did = true;
+          }
+        }
+        if (!did && ig < uint32_t(my_tiles)) {
+          // next GEMM k-block: the accumulator must have been drained by epilogue 1 of the previous tile
+          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
+          if ((kbg > 0 || mbar_try_wait(acc_free, (ig & 1u) ^ 1u)) && mbar_try_wait(&st_full[s], ph)) {
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + C::OFF_ST + s * C::STAGE_BYTES);
+            const uint32_t b_addr = a_addr + kChunkBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = umma_smem_desc(a_addr + k * 32, 0, 1024, 2);
+              const uint64_t db = umma_smem_desc(b_addr + k * 32, 0, 1024, 2);
+              umma_f16(tmem_base + C::TM_ACC, da, db, id_gemm, (kbg | uint32_t(k)) != 0 ? 1u : 0u);
+            }
+            umma_commit(&st_empty[s]);
+            ++ia;
+            if (kbg == 0) SB_DBG_T(ig, 9);
+            if (++kbg == uint32_t(C::NCH)) {
+              umma_commit(acc_full);
+              SB_DBG_T(ig, 10);
+              kbg = 0;
+              ++ig;
+            }
+            did = true;
+          }
+        }
+        if (did) {
+          idle = 0;
+        } else if (++idle > (1u << 27)) {
+          printf("sirenb200: tail kernel MMA loop stalled block %d (gemm tile %u kb %u, chain tile %u state %u)\n",
+                 blockIdx.x, ig, kbg, ic, cst);
+          __trap();
+        }
+      }
+      umma_commit(fin_done);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogues (16 warps: four per TMEM lane quadrant, 16 of the 64 columns of a
+    // chunk each - enough warps per scheduler to hide the FFMA -> MUFU -> F2FP chains) =====================
+    const int q = warp & 3;
+    const int hb = (warp - 4) >> 2;  // 0..3
+    const int r_in_tile = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 128);
+    const float G = *args.gscale;
+    const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
+    const uint32_t t_addr = smem_u32(smem + C::OFF_T);
+    const uint32_t lane_tm = uint32_t(q * 32) << 16;
+    float bias[kMaxOutTc];
+#pragma unroll
+    for (int c = 0; c < kMaxOutTc; ++c) bias[c] = c < args.C ? args.b_last[c] : 0.f;
+    float sse = 0.f, dbs[kMaxOutTc] = {};
+    float tgt_next[kMaxOutTc] = {};
+    auto fetch_target = [&](int tile) {
+      const int64_t pn = int64_t(tile) * kRowsPerTile + r_in_tile;
+#pragma unroll
+      for (int c = 0; c < kMaxOutTc; ++c)
+        tgt_next[c] = (hb == 0 && tile < args.num_tiles && pn < args.npix && c < args.C) ? args.img[pn * args.C + c]
+                                                                                       : 0.f;
+    };
+    fetch_target(blockIdx.x);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+      const int64_t p = int64_t(t) * kRowsPerTile + r_in_tile;
+      const bool row_valid = p < args.npix;
+      float tgt[kMaxOutTc];
+#pragma unroll
+      for (int c = 0; c < kMaxOutTc; ++c) tgt[c] = tgt_next[c];
+      fetch_target(t + gridDim.x);
+      // ---- epilogue 1: accumulator -> sin -> T.  The TMEM load of the next chunk is in flight while this
+      // one is computed; T is handed to the y MMA half by half; a half of T may only be overwritten once
+      // the previous tile's dz store out of it has been read (one bulk group per half).
+      if (issuer) SB_DBG_T(it, 0);
+      mbar_wait(acc_full, it & 1u);
+      if (issuer) SB_DBG_T(it, 1);
+      tc_fence_after();
+      {
+        uint32_t v[2][16];
+        tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC + hb * 16, v[0]);
+#pragma unroll
+        for (int nb = 0; nb < C::NCH; ++nb) {
+          if (it > 0 && nb % C::CPH == 0) {
+            if (issuer) {
+              if (nb == 0) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+            }
+            named_bar_sync(1, 512);
+          }
+          tmem_ld_wait();
+          if (nb + 1 < C::NCH)
+            tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC + (nb + 1) * 64 + hb * 16, v[(nb + 1) & 1]);
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = nb * 64 + hb * 16 + 2 * j;
+            const float t0 = fmaf(__uint_as_float(v[nb & 1][2 * j]), args.omega, cst[col]);
+            const float t1 = fmaf(__uint_as_float(v[nb & 1][2 * j + 1]), args.omega, cst[col + 1]);
+            o[j] = sine_signed_half2(t0, t1);
+          }
+          const uint32_t row_addr = t_addr + nb * kChunkBytes + r_in_tile * 128;
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const uint32_t chunk = uint32_t(hb * 2 + c2) ^ uint32_t(r_in_tile & 7);
+            st_shared_v4(row_addr + (chunk << 4), o[4 * c2], o[4 * c2 + 1], o[4 * c2 + 2], o[4 * c2 + 3]);
+          }
+          if (nb % C::CPH == C::CPH - 1) {
+            fence_proxy_async_smem();
+            if (nb == C::NCH - 1) tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (nb == C::NCH - 1) mbar_arrive(acc_free);
+              mbar_arrive(&t_ready[nb / C::CPH]);
+            }
+          }
+        }
+      }
+      if (issuer) SB_DBG_T(it, 2);
+      // ---- epilogue 2: y -> pred, squared error, seed ----
+      if (hb == 0) {
+        mbar_wait(y_full, it & 1u);
+        if (issuer) SB_DBG_T(it, 3);
+        tc_fence_after();
+        uint32_t yv[8];
+        tmem_ld_32x8(tmem_base + lane_tm + C::TM_Y, yv);
+        tmem_ld_wait();
+        float g[kMaxOutTc];
+#pragma unroll
+        for (int c = 0; c < kMaxOutTc; ++c) {
+          g[c] = 0.f;
+          if (c < args.C && row_valid) {
+            const float z = __uint_as_float(yv[c]) + bias[c];
+            const float o = args.outermost_linear ? z : sinf(z * args.omega_last);
+            const float pr = o / 2 + 0.5f;
+            if (args.pred) args.pred[p * args.C + c] = pr;
+            const float d = pr - tgt[c];
+            sse += d * d;
+            g[c] = d * G;
+            if (!args.outermost_linear) g[c] *= args.omega_last * cosf(z * args.omega_last);
+            dbs[c] += g[c];
+          }
+        }
+        const uint32_t ga = smem_u32(smem + C::OFF_G) + (r_in_tile & 7) * 16 + (r_in_tile >> 3) * 256;
+        st_shared_v4(ga, pack_f16x2(g[0], g[1]), pack_f16x2(g[2], g[3]), 0u, 0u);
+        st_shared_v4(ga + 128, 0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_ready);
+        if (issuer) SB_DBG_T(it, 4);
+      }
+      // ---- epilogue 3: dz = dA (*) cos, in place over T, stored half by half ----
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(da_full, uint32_t(half));
+        if (issuer) SB_DBG_T(it, 5 + 2 * half);
+        tc_fence_after();
+        uint32_t v[2][16];
+        tmem_ld_32x16(tmem_base + lane_tm + C::TM_DA + hb * 16, v[0]);
+#pragma unroll
+        for (int nbl = 0; nbl < C::CPH; ++nbl) {
+          const int nb = half * C::CPH + nbl;
+          const uint32_t row_addr = t_addr + nb * kChunkBytes + r_in_tile * 128;
+          uint32_t e[8];
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const uint32_t chunk = uint32_t(hb * 2 + c2) ^ uint32_t(r_in_tile & 7);
+            const uint4 ld = ld_shared_v4(row_addr + (chunk << 4));
+            e[4 * c2 + 0] = ld.x;
+            e[4 * c2 + 1] = ld.y;
+            e[4 * c2 + 2] = ld.z;
+            e[4 * c2 + 3] = ld.w;
+          }
+          tmem_ld_wait();
+          if (nbl + 1 < C::CPH)
+            tmem_ld_32x16(tmem_base + lane_tm + C::TM_DA + (nbl + 1) * 64 + hb * 16, v[(nbl + 1) & 1]);
+          if (half == 0 && nbl == C::CPH - 1) {
+            // half 0 is out of TMEM: the second half of dA may overwrite the region while we do the math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(da_free);
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g0 = __uint_as_float(v[nbl & 1][2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
+            float g1 = __uint_as_float(v[nbl & 1][2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
+            if (!row_valid) g0 = g1 = 0.0f;
+            o[j] = pack_f16x2(g0, g1);
+          }
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const uint32_t chunk = uint32_t(hb * 2 + c2) ^ uint32_t(r_in_tile & 7);
+            st_shared_v4(row_addr + (chunk << 4), o[4 * c2], o[4 * c2 + 1], o[4 * c2 + 2], o[4 * c2 + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 512);
+        if (issuer) {
+          for (int nbl = 0; nbl < C::CPH; ++nbl) {
+            const int nb = half * C::CPH + nbl;
+            tma_store_2d(&tmDz, smem + C::OFF_T + nb * kChunkBytes, nb * 64, args.dz_row0 + t * kRowsPerTile);
+          }
+          tma_store_commit();
+          SB_DBG_T(it, 6 + 2 * half);
+        }
+      }
+      tc_fence_before();
+    }
+    if (issuer) tma_store_wait_all<0>();
+    // ---- per-CTA partials: db_last / squared error (block reduction), dW_last from TMEM ----
+    float* out = args.part + int64_t(blockIdx.x) * (args.C * W + args.C + 1);
+    float* red = reinterpret_cast<float*>(smem + C::OFF_RED);  // [16 warps][8]
+    float vals[kMaxOutTc + 1];
+#pragma unroll
+    for (int c = 0; c < kMaxOutTc; ++c) vals[c] = dbs[c];
+    vals[kMaxOutTc] = sse;
+#pragma unroll
+    for (int k = 0; k <= kMaxOutTc; ++k) {
+      float x = vals[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) red[(warp - 4) * 8 + k] = x;
+    }
+    named_bar_sync(1, 512);
+    if (threadIdx.x - 128 <= unsigned(args.C)) {
+      const int k = int(threadIdx.x) - 128;
+      const int idx = k < args.C ? k : kMaxOutTc;
+      float x = 0.f;
+      for (int w8 = 0; w8 < 16; ++w8) x += red[w8 * 8 + idx];
+      out[args.C * W + k] = x;  // db_last[0..C-1], then the squared error
+    }
+    if (hb == 0) {
+      const bool any = int(blockIdx.x) < args.num_tiles;
+      if (any) {
+        mbar_wait(fin_done, 0);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int mb = 0; mb < W / 128; ++mb) {
+        uint32_t dv[8] = {};
+        if (any) {
+          tmem_ld_32x8(tmem_base + lane_tm + C::TM_DW + mb * 16, dv);
+          tmem_ld_wait();
+        }
+        for (int c = 0; c < args.C; ++c) out[c * W + mb * 128 + r_in_tile] = __uint_as_float(dv[c]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
 }  // namespace sb
