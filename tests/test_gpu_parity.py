@@ -427,3 +427,42 @@ def test_deepcopy_and_rebinding_weight_data():
         ref = O.siren_forward([p.detach().cpu() for p in m2.parameters()], grid.cpu(), 50.0, 30.0)
     assert (c.cpu() - ref).abs().max().item() <= 5e-4
     assert not torch.equal(a, c)
+
+
+@pytest.mark.parametrize("hidden,depth,H,W", [(256, 5, 40, 56), (128, 4, 33, 47)])
+def test_fused_kernel_variants_match_the_kernels_they_replace(monkeypatch, hidden, depth, H, W):
+    """The fused kernels of the tensor-core path against the stand-alone kernels they replace (selected by
+    environment switches read at handle creation), same weights, same image:
+      tail kernel (last hidden GEMM + output layer + loss + dZ)  -> every gradient and the loss bit-identical
+      layer 0 generated inside the first hidden GEMM              -> bit-identical (same arithmetic per element)
+      layer-0 gradient reduced inside the first dX GEMM           -> dW0 / db0 differ by summation order only
+    """
+    _, get_grid, synth_image, Siren, _ = _pkg()
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+
+    def run(env):
+        for k in ("SIRENB200_TAIL", "SIRENB200_GEN_FIRST", "SIRENB200_FUSE_L0", "SIRENB200_PDL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        torch.manual_seed(0)
+        model = Siren(depth=depth, hidden_size=hidden, first_omega_0=50, hidden_omega_0=30,
+                      precision="f16tc").cuda()
+        eng = model.engine_for(grid)
+        grads = [torch.zeros_like(p) for p in model.hot_parameters()]
+        stats = torch.zeros(4, device="cuda")
+        for _ in range(2):
+            eng.forward_backward(model.kernel_parameters(), img, grads, stats)
+        torch.cuda.synchronize()
+        return [g.clone() for g in grads], stats.clone()
+
+    base_g, base_s = run({})
+    for env, exact_from in (({"SIRENB200_TAIL": "0"}, 0), ({"SIRENB200_GEN_FIRST": "0"}, 0),
+                            ({"SIRENB200_PDL": "0"}, 0), ({"SIRENB200_FUSE_L0": "0"}, 2)):
+        g, s = run(env)
+        assert torch.equal(s[:2], base_s[:2]), env
+        for i, (a, b) in enumerate(zip(g, base_g)):
+            if i >= exact_from:
+                assert torch.equal(a, b), (env, i)
+            else:
+                assert _rel(a, b) <= 1e-5, (env, i, _rel(a, b))
