@@ -52,7 +52,6 @@ class Fitter:
         self._graph = None
         self._graph_key = None
         self._warmed = False
-        self._dev_state = None  # schedule state the device holds (skip the upload when unchanged)
         self.launches_per_step = 0  # library kernels per fit step (measured on the eager capture run)
 
     # ------------------------------------------------------------------ eager path
@@ -122,12 +121,23 @@ class Fitter:
                 mask_bufs[w] = self.mask.mask_dict[n].clone()
             masks = _lib.ptr_array([mask_bufs.get(p) for p in params])
         n = len(params)
+        # The device-side schedule (step counter, lr, bias corrections), the loss ring and its pinned host
+        # mirror belong to the OPTIMIZER: every Fitter stepping it (e.g. train_epoch alternating between two
+        # image buffers) shares them, so the device's step counter never has to be re-uploaded.
+        shared = opt.__dict__.get("_sirenb200_sched")
+        if shared is None or shared["state"].device != dev:
+            shared = {
+                "state": torch.zeros(8, dtype=torch.float64, device=dev),
+                "ring": torch.zeros(_RING, dtype=torch.float32, device=dev),
+                # pinned host float the schedule kernel also writes the loss to (unified addressing: the
+                # device uses the host pointer), read by step_loss() after a stream synchronisation
+                "host_loss": torch.zeros(1, dtype=torch.float32).pin_memory(),
+                "dev_state": None,  # what the device holds (skip the upload when unchanged)
+            }
+            opt.__dict__["_sirenb200_sched"] = shared
+        self._shared = shared
         self._g = {
-            "state": torch.zeros(8, dtype=torch.float64, device=dev),
-            "ring": torch.zeros(_RING, dtype=torch.float32, device=dev),
-            # pinned host float the schedule kernel also writes the loss to (unified addressing: the device
-            # uses the host pointer), read by step_loss() after a stream synchronisation
-            "host_loss": torch.zeros(1, dtype=torch.float32).pin_memory(),
+            "state": shared["state"], "ring": shared["ring"], "host_loss": shared["host_loss"],
             "n": n, "p": _lib.ptr_array([p.data for p in params]),
             "g": _lib.ptr_array([p.grad for p in params]),
             "m": _lib.ptr_array([opt.state[p]["exp_avg"] for p in params]),
@@ -136,7 +146,6 @@ class Fitter:
             "numel": (ctypes.c_int64 * n)(*[p.numel() for p in params]),
             "beta1": float(beta1), "beta2": float(beta2), "eps": float(group["eps"]),
         }
-        self._dev_state = None
         self._sync_sched_state()
         # one eager run of the body (a real step) initialises everything lazily created, then capture
         self._graph = None
@@ -151,9 +160,9 @@ class Fitter:
             lr0, gamma, period = group["lr"], 1.0, 1 << 30
         beta1, beta2 = group["betas"]
         want = (float(steps_done), lr0, gamma, float(period), beta1, beta2)
-        if want != self._dev_state:
+        if want != self._shared["dev_state"]:
             self._g["state"].copy_(torch.tensor(want + (0.0, 0.0), dtype=torch.float64))
-            self._dev_state = want
+            self._shared["dev_state"] = want
 
     def _advance_host(self, k):
         group = self.optim.param_groups[0]
@@ -211,8 +220,9 @@ class Fitter:
             idx = (torch.arange(k, device=losses.device) + step0) % _RING
             losses[offset:offset + k] = g["ring"][idx]
         self._advance_host(k)
-        if self._dev_state is not None:  # the device advanced its own step counter
-            self._dev_state = (self._dev_state[0] + k,) + self._dev_state[1:]
+        ds = self._shared["dev_state"]
+        if ds is not None:  # the device advanced its own step counter
+            self._shared["dev_state"] = (ds[0] + k,) + ds[1:]
         return value
 
     def step_loss(self):
