@@ -96,6 +96,7 @@ struct sirenb200_plan {
   __half* wlt16 = nullptr;  // [W, 64]
   CUtensorMap tm_wl{}, tm_wlt{};
   bool last_tc = false;
+  bool fwd_pair = false;    // two hidden layers per forward kernel (SIRENB200_FWD_PAIR=1)
   bool tail_fused = true;   // last hidden GEMM + output layer + loss + dZ in one kernel (SIRENB200_TAIL=0: two kernels)
   bool pdl = true;          // programmatic dependent launch of the GEMM kernels (SIRENB200_PDL=0: off)
   bool fuse_l0 = true;      // layer-0 gradient reduced inside the dX GEMM of the first hidden layer (SIRENB200_FUSE_L0=0: own kernel)
@@ -363,6 +364,41 @@ int launch_fused_fwd(sirenb200_plan* p, const Chunk& ch, cudaStream_t st) {
   }
 }
 
+// two consecutive hidden layers (l, l + 1) in one kernel: act[l] is stashed but not read back
+template <int W>
+int launch_fwd_pair(sirenb200_plan* p, const float* const* prm, int l, const Chunk& ch, cudaStream_t st) {
+  if constexpr (W == 128 || W == 256) {
+    using Cfg = FwdPairCfg<W>;
+    auto kfn = fwd_pair_kernel<W>;
+    static bool attr_set[64] = {};
+    if (!attr_set[p->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(Cfg::SMEM_BYTES)));
+      attr_set[p->device & 63] = true;
+    }
+    FwdPairArgs fa{};
+    fa.num_tiles = ch.ntiles;
+    fa.a_row0 = int((l - 1) * p->npix_pad + ch.p0);
+    fa.t_row0 = int(l * p->npix_pad + ch.p0);
+    fa.o_row0 = int((l + 1) * p->npix_pad + ch.p0);
+    fa.omega_a = omega_of(p, l);
+    fa.omega_b = omega_of(p, l + 1);
+    fa.bias_a = prm[2 * l + 1];
+    fa.bias_b = prm[2 * (l + 1) + 1];
+    fa.dbg = p->dbg_timeline ? p->dbg_timeline + 3 * 4 * 8 * 16 : nullptr;
+    const int grid = ch.ntiles < p->nsm ? ch.ntiles : p->nsm;
+    {
+      ProfScope ps(p, PK_FWD_GEMM, st);
+      launch_ex(kfn, dim3(grid), dim3(640), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_act, p->tm_w[l - 1],
+                p->tm_w[l], fa);
+    }
+    LAUNCH_CHECK();
+    return 0;
+  } else {
+    return fail(SIRENB200_ERR_INVALID, "forward pair kernel needs hidden 128 or 256");
+  }
+}
+
 template <int W>
 int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st,
                      bool skip_last_hidden = false) {
@@ -383,7 +419,17 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
                                                   p->act + ch.p0 * W, ch.npix, ch.npix_pad);
   }
   LAUNCH_CHECK();
-  for (int l = 1; l <= (skip_last_hidden ? nh - 1 : nh); ++l) {
+  const int l_end = skip_last_hidden ? nh - 1 : nh;
+  for (int l = 1; l <= l_end; ++l) {
+    if constexpr (W == 128 || W == 256) {
+      // two plain hidden layers at a time when there are two left (layer 1 stays with the generator kernel)
+      if (p->fwd_pair && p->nchunks == 1 && !(l == 1 && gen_first) && l + 1 <= l_end) {
+        int rc = launch_fwd_pair<W>(p, prm, l, ch, st);
+        if (rc) return rc;
+        ++l;
+        continue;
+      }
+    }
     RowGemmArgs ra{};
     ra.num_tiles = ch.ntiles;
     ra.a_row0 = int((l - 1) * p->npix_pad + ch.p0);
@@ -1073,6 +1119,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->last_tc = (W == 128 || W == 256) && nh > 0 && !(env && atoi(env) == 0);
       env = getenv("SIRENB200_GEN_FIRST");
       p->gen_first = !(env && atoi(env) == 0);
+      env = getenv("SIRENB200_FWD_PAIR");
+      p->fwd_pair = env && atoi(env) != 0;
       env = getenv("SIRENB200_TAIL");
       p->tail_fused = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_PDL");

@@ -2160,4 +2160,284 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// forward pair kernel (hidden 128 / 256): TWO consecutive hidden layers per 128-pixel tile,
+//   T   = sin(w (A . W_a^T + b_a))   -> signed-half tile in shared memory, TMA-stored to the stash
+//   out = sin(w (T . W_b^T + b_b))   -> TMA-stored to the stash
+// so the intermediate activation is written once and never read back by the forward pass.  Operands are
+// streamed as in the tail kernel ({A k-block, W_a k-block} then {W_b k-block} stages from L2); the
+// second GEMM reads its A operand straight from T.  16 epilogue warps, next chunk's tcgen05.ld in flight.
+// (reference: SineLayer.forward x 2, implicit_image/models/siren.py:56-68)
+// ------------------------------------------------------------------------------------------
+struct FwdPairArgs {
+  int num_tiles;
+  int a_row0;          // rows of the input activation inside the activation tensor map
+  int t_row0;          // rows of the first layer's output (stash)
+  int o_row0;          // rows of the second layer's output (stash)
+  float omega_a, omega_b;
+  const float* bias_a;
+  const float* bias_b;
+  long long* dbg;      // optional timeline (block 0): dbg[tile * 16 + k], first 12 tiles
+};
+
+template <int W>
+struct FwdPairCfg {
+  static_assert(W == 128 || W == 256, "forward pair kernel: hidden 128 or 256");
+  static constexpr int NCH = W / 64;
+  static constexpr int CPH = NCH / 2;
+  static constexpr int S = 3;  // ring depth: the second GEMM sits on the epilogues' critical path, so the L2
+                               // latency of its weight k-blocks must be covered by stages in flight
+  static constexpr uint32_t B_KB_BYTES = W * 128;
+  static constexpr uint32_t STAGE_BYTES = kChunkBytes + B_KB_BYTES;
+  static constexpr uint32_t OFF_T = 0;
+  static constexpr uint32_t OFF_ST = NCH * kChunkBytes;
+  static constexpr uint32_t OFF_CONST = OFF_ST + S * STAGE_BYTES;  // omega*bias of both layers
+  static constexpr uint32_t OFF_BAR = OFF_CONST + 2 * W * 4;
+  static constexpr int NUM_BARS = 2 * S + 6;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+  static constexpr uint32_t TM_ACC1 = 0, TM_ACC2 = W;
+  static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * W);
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
+};
+
+template <int W>
+__global__ void __launch_bounds__(640, 1)
+fwd_pair_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmWa,
+                const __grid_constant__ CUtensorMap tmWb, const FwdPairArgs args) {
+  using C = FwdPairCfg<W>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* st_full = bars;
+  uint64_t* st_empty = st_full + C::S;
+  uint64_t* acc1_full = st_empty + C::S;
+  uint64_t* acc1_free = acc1_full + 1;  // epilogue 1 drained accumulator 1 (16 warps)
+  uint64_t* t_ready = acc1_free + 1;    // [2] half of T written and fenced (16 warps each)
+  uint64_t* acc2_full = t_ready + 2;    // second GEMM retired (it has also finished reading T)
+  uint64_t* acc2_free = acc2_full + 1;  // epilogue 2 drained accumulator 2 (16 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::S; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1);
+    }
+    mbar_init(acc1_full, 1);
+    mbar_init(acc1_free, 16);
+    mbar_init(&t_ready[0], 16);
+    mbar_init(&t_ready[1], 16);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_free, 16);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAct);
+    tma_prefetch_desc(&tmWa);
+    tma_prefetch_desc(&tmWb);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    float* cst = reinterpret_cast<float*>(smem + C::OFF_CONST);
+    for (int i = threadIdx.x - 128; i < W; i += 512) {
+      cst[i] = args.omega_a * args.bias_a[i];
+      cst[W + i] = args.omega_b * args.bias_b[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== producer: per tile {A, W_a} x NCH then {W_b} x NCH =====================
+    if (lane == 0) {
+      uint32_t ia = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < 2 * C::NCH; ++kb, ++ia) {
+          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
+          mbar_wait(&st_empty[s], ph ^ 1u);
+          uint8_t* stage = smem + C::OFF_ST + s * C::STAGE_BYTES;
+          if (kb < C::NCH) {
+            mbar_expect_tx(&st_full[s], C::STAGE_BYTES);
+            tma_load_2d(stage, &tmAct, &st_full[s], kb * 64, args.a_row0 + t * kRowsPerTile);
+            tma_load_2d(stage + kChunkBytes, &tmWa, &st_full[s], kb * 64, 0);
+          } else {
+            mbar_expect_tx(&st_full[s], C::B_KB_BYTES);
+            tma_load_2d(stage + kChunkBytes, &tmWb, &st_full[s], (kb - C::NCH) * 64, 0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, W, 0, 0, 0, 0);
+      const uint32_t t_addr = smem_u32(smem + C::OFF_T);
+      uint32_t ia = 0, it = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        // GEMM 1 (accumulator 1 was drained by epilogue 1 of the previous tile)
+        mbar_wait(acc1_free, (it & 1u) ^ 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < C::NCH; ++kb, ++ia) {
+          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
+          mbar_wait(&st_full[s], ph);
+          if (kb == 0) SB_DBG_T(it, 5);
+          if (kb == 2) SB_DBG_T(it, 9);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + C::OFF_ST + s * C::STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + C::TM_ACC1, umma_smem_desc(a_addr + k * 32, 0, 1024, 2),
+                     umma_smem_desc(a_addr + kChunkBytes + k * 32, 0, 1024, 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&st_empty[s]);
+        }
+        umma_commit(acc1_full);
+        SB_DBG_T(it, 6);
+        // GEMM 2: A = T, half by half as epilogue 1 hands it over
+        mbar_wait(acc2_free, (it & 1u) ^ 1u);
+        for (int kb = 0; kb < C::NCH; ++kb, ++ia) {
+          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
+          if (kb % C::CPH == 0) mbar_wait(&t_ready[kb / C::CPH], it & 1u);
+          mbar_wait(&st_full[s], ph);
+          if (kb == 0) SB_DBG_T(it, 7);
+          if (kb == 2) SB_DBG_T(it, 10);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(smem + C::OFF_ST + s * C::STAGE_BYTES) + kChunkBytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + C::TM_ACC2, umma_smem_desc(t_addr + kb * kChunkBytes + k * 32, 0, 1024, 2),
+                     umma_smem_desc(b_addr + k * 32, 0, 1024, 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&st_empty[s]);
+        }
+        umma_commit(acc2_full);
+        SB_DBG_T(it, 8);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogues (16 warps) =====================
+    const int q = warp & 3;
+    const int hb = (warp - 4) >> 2;  // 0..3: 16 of the 64 columns of a chunk
+    const int r_in_tile = q * 32 + lane;
+    const bool issuer = (threadIdx.x == 128);
+    const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
+    const uint32_t t_addr = smem_u32(smem + C::OFF_T);
+    const uint32_t lane_tm = uint32_t(q * 32) << 16;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+      // ---- epilogue 1: accumulator 1 -> sin -> T (+ stash store, half by half) ----
+      if (issuer) SB_DBG_T(it, 0);
+      mbar_wait(acc1_full, it & 1u);
+      if (issuer) SB_DBG_T(it, 1);
+      tc_fence_after();
+      {
+        uint32_t v[2][16];
+        tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC1 + hb * 16, v[0]);
+#pragma unroll
+        for (int nb = 0; nb < C::NCH; ++nb) {
+          if (it > 0 && nb % C::CPH == 0) {
+            // a half of T may be overwritten once the previous tile's output stores out of it (epilogue 2
+            // writes in place, one bulk group per chunk) have been read; the second GEMM that read T has
+            // retired (this warp waited for acc2_full in the previous epilogue 2)
+            if (issuer) {
+              if (nb == 0) tma_store_wait_read<C::CPH>(); else tma_store_wait_read<0>();
+            }
+            named_bar_sync(1, 512);
+          }
+          tmem_ld_wait();
+          if (nb + 1 < C::NCH)
+            tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC1 + (nb + 1) * 64 + hb * 16, v[(nb + 1) & 1]);
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = nb * 64 + hb * 16 + 2 * j;
+            const float t0 = fmaf(__uint_as_float(v[nb & 1][2 * j]), args.omega_a, cst[col]);
+            const float t1 = fmaf(__uint_as_float(v[nb & 1][2 * j + 1]), args.omega_a, cst[col + 1]);
+            o[j] = sine_signed_half2(t0, t1);
+          }
+          const uint32_t row_addr = t_addr + nb * kChunkBytes + r_in_tile * 128;
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const uint32_t chunk = uint32_t(hb * 2 + c2) ^ uint32_t(r_in_tile & 7);
+            st_shared_v4(row_addr + (chunk << 4), o[4 * c2], o[4 * c2 + 1], o[4 * c2 + 2], o[4 * c2 + 3]);
+          }
+          if (nb % C::CPH == C::CPH - 1) {
+            const int half = nb / C::CPH;
+            fence_proxy_async_smem();
+            if (nb == C::NCH - 1) tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (nb == C::NCH - 1) mbar_arrive(acc1_free);
+              mbar_arrive(&t_ready[half]);
+            }
+            named_bar_sync(1, 512);  // the whole half is in T: stash it
+            if (issuer) {
+              for (int c = half * C::CPH; c < (half + 1) * C::CPH; ++c)
+                tma_store_2d(&tmAct, smem + C::OFF_T + c * kChunkBytes, c * 64, args.t_row0 + t * kRowsPerTile);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+      // ---- epilogue 2: accumulator 2 -> sin -> T in place (the second GEMM has finished reading it) ->
+      // stash store, chunk by chunk ----
+      if (issuer) SB_DBG_T(it, 2);
+      mbar_wait(acc2_full, it & 1u);
+      if (issuer) SB_DBG_T(it, 3);
+      tc_fence_after();
+      if (issuer) tma_store_wait_read<0>();  // the stash stores of T issued in epilogue 1 have read it
+      named_bar_sync(1, 512);
+      {
+        uint32_t v[2][16];
+        tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC2 + hb * 16, v[0]);
+#pragma unroll
+        for (int nb = 0; nb < C::NCH; ++nb) {
+          tmem_ld_wait();
+          if (nb + 1 < C::NCH)
+            tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC2 + (nb + 1) * 64 + hb * 16, v[(nb + 1) & 1]);
+          if (nb == C::NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc2_free);
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = nb * 64 + hb * 16 + 2 * j;
+            const float t0 = fmaf(__uint_as_float(v[nb & 1][2 * j]), args.omega_b, cst[W + col]);
+            const float t1 = fmaf(__uint_as_float(v[nb & 1][2 * j + 1]), args.omega_b, cst[W + col + 1]);
+            o[j] = sine_signed_half2(t0, t1);
+          }
+          const uint32_t row_addr = t_addr + nb * kChunkBytes + r_in_tile * 128;
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const uint32_t chunk = uint32_t(hb * 2 + c2) ^ uint32_t(r_in_tile & 7);
+            st_shared_v4(row_addr + (chunk << 4), o[4 * c2], o[4 * c2 + 1], o[4 * c2 + 2], o[4 * c2 + 3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 512);
+          if (issuer) {
+            tma_store_2d(&tmAct, smem + C::OFF_T + nb * kChunkBytes, nb * 64, args.o_row0 + t * kRowsPerTile);
+            tma_store_commit();
+            if (nb == C::NCH - 1) SB_DBG_T(it, 4);
+          }
+        }
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
 }  // namespace sb

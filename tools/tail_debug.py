@@ -1,8 +1,9 @@
-"""Dev tool: fused tail kernel (SIRENB200_TAIL=1) vs the two-kernel path, gradients and loss."""
+"""Dev tool: a fused kernel variant (env switch given as argv[1], default SIRENB200_TAIL) on vs off: gradients, loss, time."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
+VAR = sys.argv[1] if len(sys.argv) > 1 else "SIRENB200_TAIL"
 from implicit_image_compression_b200.data import get_grid, synth_image
 from implicit_image_compression_b200.models import Siren
 
@@ -10,7 +11,7 @@ for hidden, depth, H, W in ((256, 4, 64, 96), (128, 5, 40, 56), (256, 6, 512, 76
     grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
     out = {}
     for mode in ("1", "0"):
-        os.environ["SIRENB200_TAIL"] = mode
+        os.environ[VAR] = mode
         torch.manual_seed(0)
         model = Siren(depth=depth, hidden_size=hidden, first_omega_0=50, hidden_omega_0=30, precision="f16tc").cuda()
         eng = model.engine_for(grid)
