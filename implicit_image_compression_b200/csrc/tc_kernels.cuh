@@ -266,61 +266,53 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         wb[j] = __ldg(args.gen_w0 + col * 2 + 1) * args.gen_omega;
         bb[j] = __ldg(args.gen_b0 + col) * args.gen_omega;
       }
-      const unsigned width = unsigned(cs.width);
-      const bool has_coords = cs.coords != nullptr;
       uint32_t ig = uint32_t(kb);
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ig += C::KB) {
         const uint32_t s = ig % C::SA, ph = (ig / C::SA) & 1u;
         const uint32_t stage = smem_u32(smem + C::OFF_A + s * C::A_STAGE);
-        // image (row, col) of this lane's first pixel; later rows advance by 4 pixels
         const int r_first = rg + 64 * half;
-        const uint64_t g0 = uint64_t(int64_t(t) * kRowsPerTile + r_first + cs.p_offset);
-        unsigned irow = unsigned(g0 / width), icol = unsigned(g0 % width);
+        // Coordinates once per tile: lane L owns rows 64*half + L and 64*half + 32 + L of the tile (already
+        // mapped to [-1, 1]); the row loop below fetches them with two shuffles instead of recomputing
+        // (row, column) and reloading the tables for every row.
+        float own_h[2], own_w[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int r = t * kRowsPerTile + 64 * half + 32 * q + lane;
+          own_h[q] = own_w[q] = 0.f;
+          if (r < args.valid_rows) load_xy(cs, r, own_h[q], own_w[q]);
+        }
+        // rows >= valid_rows exist only in the last tile: their activations are written as zero
+        const bool full_tile = (t + 1) * kRowsPerTile <= args.valid_rows;
         // every lane waits (no divergent region in front of the arithmetic); only the issuer owns bulk groups
         if (issuer_g) SB_DBG_G(kb, ig / C::KB, 0);
         mbar_wait(&a_empty[s], ph ^ 1u);                   // the MMAs that read this stage are done
         tma_store_wait_read<C::SA / C::KB - 1>();          // ... and so is the stash store issued from it
         named_bar_sync(2 + kb, 64);
         if (issuer_g) SB_DBG_G(kb, ig / C::KB, 1);
-        // batches of 8 rows: all coordinate loads first, then the arithmetic, then the stores (the shared
-        // stores are asm volatile with a memory clobber; interleaving them would serialise the loads)
-#pragma unroll 1
-        for (int ib = 0; ib < 16; ib += 8) {
-          float xh[8], xw[8];
-          uint32_t keep[8];  // all-ones for a real pixel row, 0 for the padding rows of the last tile
+        // batches of 8 rows: the arithmetic of a batch, then its stores (the shared stores are asm volatile
+        // with a memory clobber; interleaving them with the arithmetic would serialise it)
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = t * kRowsPerTile + r_first + 4 * (ib + i);
-            const bool ok = r < args.valid_rows;
-            keep[i] = ok ? 0xFFFFFFFFu : 0u;
-            if (has_coords) {
-              const float2 v = ok ? __ldg(reinterpret_cast<const float2*>(cs.coords) + r + cs.p_offset)
-                                  : make_float2(0.5f, 0.5f);
-              xh[i] = v.x;
-              xw[i] = v.y;
-            } else {
-              xh[i] = ok ? __ldg(cs.lin_h + cs.row_begin + irow) : 0.5f;
-              xw[i] = ok ? __ldg(cs.lin_w + icol) : 0.5f;
-              icol += 4;
-              if (icol >= width) {
-                icol -= width;
-                ++irow;
-                while (icol >= width) {  // images narrower than 4 pixels
-                  icol -= width;
-                  ++irow;
-                }
-              }
-            }
-          }
+        for (int ib = 0; ib < 16; ib += 8) {
           uint32_t o[8][4];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float x0 = (xh[i] - 0.5f) * 2.0f, x1 = (xw[i] - 0.5f) * 2.0f;
+            // row rg + 4 (ib + i) of this half: owner lane (rg + 4 (ib+i)) & 31, slot (ib + i) >> 3 (rg < 4)
+            const int src = (rg + 4 * (ib + i)) & 31;
+            const float x0 = __shfl_sync(0xffffffffu, own_h[(ib + i) >> 3], src);
+            const float x1 = __shfl_sync(0xffffffffu, own_w[(ib + i) >> 3], src);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float t0 = fmaf(x0, wa[2 * j], fmaf(x1, wb[2 * j], bb[2 * j]));
               const float t1 = fmaf(x0, wa[2 * j + 1], fmaf(x1, wb[2 * j + 1], bb[2 * j + 1]));
-              o[i][j] = sine_signed_half2(t0, t1) & keep[i];
+              o[i][j] = sine_signed_half2(t0, t1);
+            }
+          }
+          if (!full_tile) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t keep = (t * kRowsPerTile + r_first + 4 * (ib + i) < args.valid_rows) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[i][j] &= keep;
             }
           }
 #pragma unroll
