@@ -2079,10 +2079,13 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
           uint32_t o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float g0 = __uint_as_float(v[nbl & 1][2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
-            float g1 = __uint_as_float(v[nbl & 1][2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
-            if (!row_valid) g0 = g1 = 0.0f;
+            const float g0 = __uint_as_float(v[nbl & 1][2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
+            const float g1 = __uint_as_float(v[nbl & 1][2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
             o[j] = pack_f16x2(g0, g1);
+          }
+          if (!row_valid) {  // padding rows of the last tile (their seed is zero, but keep dz exactly zero)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0u;
           }
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
