@@ -1722,7 +1722,7 @@ struct TailCfg {
   static constexpr uint32_t OFF_CONST = OFF_G + 4096;  // omega * bias [W] fp32
   static constexpr uint32_t OFF_RED = OFF_CONST + W * 4;
   static constexpr uint32_t OFF_BAR = OFF_RED + 16 * 8 * 4;
-  static constexpr int NUM_BARS = 2 * S + 8 + 4;
+  static constexpr int NUM_BARS = 2 * S + 8 + 4 + 4;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
   static constexpr uint32_t TM_ACC = 0, TM_DA = W, TM_Y = W + W / 2, TM_DW = W + W / 2 + 16;
   static constexpr uint32_t TMEM_COLS = 512;
@@ -1764,6 +1764,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
   uint64_t* da_full = g_ready + 1;   // two phases per tile: dA half 0 (+ dW_last), dA half 1
   uint64_t* da_free = da_full + 1;   // half 0 has been read out of TMEM (8 warps)
   uint64_t* fin_done = da_free + 1;
+  uint64_t* dz_done = fin_done + 1;  // [2] half of dz written over T and fenced (16 warps each)
+  uint64_t* t_free = dz_done + 2;    // [2] the dz store of that half has been read out of T (store warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -1783,6 +1785,10 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
     mbar_init(da_full, 1);
     mbar_init(da_free, 16);
     mbar_init(fin_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&dz_done[i], 16);
+      mbar_init(&t_free[i], 1);
+    }
     fence_barrier_init();
     tma_prefetch_desc(&tmAct);
     tma_prefetch_desc(&tmW);
@@ -1933,6 +1939,26 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
       }
       umma_commit(fin_done);
     }
+  } else if (warp == 2) {
+    // ===================== store warp: dz halves -> HBM, then hand the half of T back =====================
+    // (a dedicated thread instead of CTA-wide named barriers: the epilogue warps never wait for each other)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&dz_done[half], it & 1u);
+          for (int nbl = 0; nbl < C::CPH; ++nbl) {
+            const int nb = half * C::CPH + nbl;
+            tma_store_2d(&tmDz, smem + C::OFF_T + nb * kChunkBytes, nb * 64, args.dz_row0 + t * kRowsPerTile);
+          }
+          tma_store_commit();
+          SB_DBG_T(it, 6 + 2 * half);
+          tma_store_wait_read<0>();
+          mbar_arrive(&t_free[half]);
+        }
+      }
+      tma_store_wait_all<0>();
+    }
   } else if (warp >= 4) {
     // ===================== epilogues (16 warps: four per TMEM lane quadrant, 16 of the 64 columns of a
     // chunk each - enough warps per scheduler to hide the FFMA -> MUFU -> F2FP chains) =====================
@@ -1977,12 +2003,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
         tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC + hb * 16, v[0]);
 #pragma unroll
         for (int nb = 0; nb < C::NCH; ++nb) {
-          if (it > 0 && nb % C::CPH == 0) {
-            if (issuer) {
-              if (nb == 0) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-            }
-            named_bar_sync(1, 512);
-          }
+          if (it > 0 && nb % C::CPH == 0) mbar_wait(&t_free[nb / C::CPH], (it - 1) & 1u);
           tmem_ld_wait();
           if (nb + 1 < C::NCH)
             tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC + (nb + 1) * 64 + hb * 16, v[(nb + 1) & 1]);
@@ -2094,19 +2115,11 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 512);
-        if (issuer) {
-          for (int nbl = 0; nbl < C::CPH; ++nbl) {
-            const int nb = half * C::CPH + nbl;
-            tma_store_2d(&tmDz, smem + C::OFF_T + nb * kChunkBytes, nb * 64, args.dz_row0 + t * kRowsPerTile);
-          }
-          tma_store_commit();
-          SB_DBG_T(it, 6 + 2 * half);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&dz_done[half]);
       }
       tc_fence_before();
     }
-    if (issuer) tma_store_wait_all<0>();
     // ---- per-CTA partials: db_last / squared error (block reduction), dW_last from TMEM ----
     float* out = args.part + int64_t(blockIdx.x) * (args.C * W + args.C + 1);
     float* red = reinterpret_cast<float*>(smem + C::OFF_RED);  // [16 warps][8]
