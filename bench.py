@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 # default workload = BASELINE.json configs[1]; --workload c3 (configs[2]: hidden 512, depth 8, 2048x2048) is a
 # developer option for the pixel-sharded large-image case and is NOT what the driver's contract line measures
-WORKLOADS = {"c2": (6, 256, 512, 768), "c3": (8, 512, 2048, 2048)}
+WORKLOADS = {"c2": (6, 256, 512, 768), "c3": (8, 512, 2048, 2048), "c5w": (6, 512, 512, 768)}  # c5w: the wide half of the sweep
 DEPTH, HIDDEN, H, W, C = 6, 256, 512, 768, 3
 OMEGA0, OMEGA = 50.0, 30.0
 LR = 3e-4

@@ -461,7 +461,7 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
 template <int W>
 int launch_last_tc(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
                    float* pred, const Chunk& ch, cudaStream_t st) {
-  if constexpr (W == 128 || W == 256) {
+  if constexpr (W == 128 || W == 256 || W == 512) {
     using Cfg = LastTcCfg<W>;
     auto kfn = last_layer_tc_kernel<W>;
     static bool attr_set[64] = {};
@@ -777,7 +777,7 @@ int tc_run(sirenb200_plan* p, const float* const* prm, int mode, const float* im
   for (const Chunk& ch : chunks) {
     if (rc) return rc;
     // training step with at least two hidden GEMM layers: the last one is fused with the output layer
-    const bool tail = mode == 1 && p->tail_fused && p->last_tc && p->D - 2 >= 2 && p->nchunks == 1 &&
+    const bool tail = W <= 256 && mode == 1 && p->tail_fused && p->last_tc && p->D - 2 >= 2 && p->nchunks == 1 &&
                       !p->fused_fwd && img_or_dpred;
     if (mode != 2) rc = tc_forward_chunk<W>(p, prm, ch, st, tail);
     if (!rc) rc = tail ? launch_tail<W>(p, prm, img_or_dpred, pred, ch, st)
@@ -1116,7 +1116,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
     {
       const char* env = getenv("SIRENB200_LAST_TC");
-      p->last_tc = (W == 128 || W == 256) && nh > 0 && !(env && atoi(env) == 0);
+      p->last_tc = (W == 128 || W == 256 || W == 512) && nh > 0 && !(env && atoi(env) == 0);
       env = getenv("SIRENB200_GEN_FIRST");
       p->gen_first = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_FWD_PAIR");

@@ -1348,9 +1348,13 @@ struct LastTcArgs {
 
 template <int W>
 struct LastTcCfg {
-  static_assert(W == 128 || W == 256, "tensor-core last layer: hidden 128 or 256");
+  static_assert(W == 128 || W == 256 || W == 512, "tensor-core last layer: hidden 128, 256 or 512");
   static constexpr int NCH = W / 64;
-  static constexpr int STAGES = 3;
+  // hidden 512: one 128 KiB activation tile at a time, and dA goes through TMEM in two N = 256 halves
+  static constexpr int STAGES = W <= 256 ? 3 : 1;
+  static constexpr int DA_N = W <= 256 ? W : 256;   // columns of one dA MMA
+  static constexpr int DA_HALVES = W / DA_N;
+  static constexpr int CH_PER_HALF = DA_N / 64;
   static constexpr uint32_t STAGE_BYTES = NCH * kChunkBytes;       // act tile
   static constexpr uint32_t OFF_ACT = 0;
   static constexpr uint32_t OFF_WL = STAGES * STAGE_BYTES;          // [16 x W] fp16, NCH k-blocks of 2 KiB
@@ -1359,9 +1363,9 @@ struct LastTcCfg {
   static constexpr uint32_t OFF_G = OFF_WLT + WLT_BYTES;            // seed tile 128 x 16 fp16
   static constexpr uint32_t OFF_RED = OFF_G + 4096;                 // block reduction scratch
   static constexpr uint32_t OFF_BAR = OFF_RED + 8 * 8 * 4;
-  static constexpr int NUM_BARS = 2 * STAGES + 5;
+  static constexpr int NUM_BARS = 2 * STAGES + 6;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
-  static constexpr uint32_t TM_Y = 0, TM_DW = 32, TM_DA = 64;       // TMEM columns
+  static constexpr uint32_t TM_Y = 0, TM_DW = 32, TM_DA = 32 + (W / 128) * 16;  // TMEM columns
   static constexpr uint32_t TMEM_COLS = 512;
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
 };
@@ -1382,6 +1386,7 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
   uint64_t* g_ready = y_full + 1;  // seed tile written (4 warps)
   uint64_t* mma_done = g_ready + 1;  // dA and dW MMAs of the tile retired
   uint64_t* fin_done = mma_done + 1;
+  uint64_t* da_free = fin_done + 1;  // hidden 512: the first dA half has been read out of TMEM (8 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -1398,6 +1403,7 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
     mbar_init(g_ready, 4);
     mbar_init(mma_done, 1);
     mbar_init(fin_done, 1);
+    mbar_init(da_free, 8);
     fence_barrier_init();
     tma_prefetch_desc(&tmAct);
     tma_prefetch_desc(&tmDz);
@@ -1435,7 +1441,7 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t id_y = umma_idesc(128, 16, 0, 0, 0, 0);
-      const uint32_t id_da = umma_idesc(128, W, 0, 0, 0, 0);
+      const uint32_t id_da = umma_idesc(128, C::DA_N, 0, 0, 0, 0);
       const uint32_t id_dw = umma_idesc(128, 16, 0, 0, 1, 1);
       const uint32_t wl_addr = smem_u32(smem + C::OFF_WL);
       const uint32_t wlt_addr = smem_u32(smem + C::OFF_WLT);
@@ -1482,6 +1488,14 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
             }
           umma_commit(mma_done);
           SB_DBG_L(it, 9);
+          if (C::DA_HALVES == 2) {
+            // second half of dA into the same TMEM region once the epilogue has read the first one out
+            mbar_wait(da_free, it & 1u);
+            tc_fence_after();
+            umma_f16(tmem_base + C::TM_DA, umma_smem_desc(g_addr, 128, 256, 0),
+                     umma_smem_desc(wlt_addr + C::DA_N * 32, 128, 256, 0), id_da, 0u);
+            umma_commit(mma_done);
+          }
         }
       }
       umma_commit(fin_done);
@@ -1565,15 +1579,19 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
       }
       if (dbgw) SB_DBG_L(it, 2);
       mbar_wait(&act_full[s], ph);  // the act tile read below was written by TMA
-      mbar_wait(mma_done, it & 1u);
+      mbar_wait(mma_done, (it * C::DA_HALVES) & 1u);
       if (dbgw) SB_DBG_L(it, 3);
       tc_fence_after();
       const uint32_t tile_addr = smem_u32(smem + C::OFF_ACT + s * C::STAGE_BYTES);
 #pragma unroll 1
       for (int nb = 0; nb < C::NCH; ++nb) {
+        if (C::DA_HALVES == 2 && nb == C::CH_PER_HALF) {
+          mbar_wait(mma_done, (it * C::DA_HALVES + 1) & 1u);
+          tc_fence_after();
+        }
         const uint32_t row_addr = tile_addr + nb * kChunkBytes + r_in_tile * 128;
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DA + nb * 64 + hb * 32, v);
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DA + (nb % C::CH_PER_HALF) * 64 + hb * 32, v);
         uint32_t e[16];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
@@ -1585,6 +1603,11 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
           e[4 * c4 + 3] = ld.w;
         }
         tmem_ld_wait();
+        if (C::DA_HALVES == 2 && nb == C::CH_PER_HALF - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(da_free);
+        }
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -1609,8 +1632,12 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
           tma_store_2d(&tmDz, smem + C::OFF_ACT + s * C::STAGE_BYTES + nb * kChunkBytes, nb * 64,
                        args.dz_row0 + t * kRowsPerTile);
         tma_store_commit();
-        // the previous tile's stores have been read out of their stage: hand it back to the producer
-        if (it > 0) {
+        if (C::STAGES == 1) {
+          // single stage (hidden 512): hand it back as soon as this tile's own stores have been read
+          tma_store_wait_read<0>();
+          mbar_arrive(&act_empty[0]);
+        } else if (it > 0) {
+          // the previous tile's stores have been read out of their stage: hand it back to the producer
           tma_store_wait_read<1>();
           mbar_arrive(&act_empty[(it - 1) % C::STAGES]);
         }
