@@ -1060,7 +1060,17 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     ALLOC(p->wlt16, int64_t(W) * 64);
     ALLOC(p->bias_w, int64_t(nh > 0 ? nh : 1) * W);
     ALLOC(p->bias_raw, int64_t(nh > 0 ? nh : 1) * W);
-    int splits = nh > 0 ? p->nsm / (nh * (W / 128) * (W / (W < 256 ? W : 256))) : 1;
+    // pixel splits of the weight-gradient GEMM: one CTA per (layer, 128-row block, column part, split).
+    // One wave of CTAs when that fills the machine (>= 93 % of the SMs), otherwise two balanced waves
+    // (hidden 512, depth 6: 32 x 4 = 128 jobs would leave 20 SMs idle; 32 x 9 = 288 = 2 x 144 does not).
+    int splits = 1;
+    if (nh > 0) {
+      const int base = nh * (W / 128) * (W / (W < 256 ? W : 256));
+      splits = p->nsm / base;
+      if (splits < 1) splits = 1;
+      const int two = (2 * p->nsm) / base;
+      if (base * splits * 100 < p->nsm * 93 && two > splits && base * two * 100 >= 2 * p->nsm * 93) splits = two;
+    }
     if (splits < 1) splits = 1;
     if (splits > p->ntiles) splits = p->ntiles;
     p->col_splits = splits;  // (re-clamped to the chunk size below)
