@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "sirenb200_fakequant_per_channel", "sirenb200_launch_count", "sirenb200_profile_enable",
     "sirenb200_profile_read", "sirenb200_debug_timeline", "sirenb200_sched_step", "sirenb200_adam_step_dev",
     "sirenb200_comm_create", "sirenb200_comm_handle", "sirenb200_comm_connect", "sirenb200_comm_allreduce",
-    "sirenb200_comm_destroy",
+    "sirenb200_comm_destroy", "sirenb200_fit_steps",
 ]
 
 PROFILE_KINDS = ["weight_staging", "first_layer", "fwd_gemm", "last_layer_loss", "dx_gemm", "dw_gemm",
@@ -35,6 +35,18 @@ class Config(ctypes.Structure):
         ("first_omega", c_float), ("hidden_omega", c_float), ("outermost_linear", c_int32),
         ("height", c_int32), ("width", c_int32), ("row_begin", c_int32), ("row_end", c_int32),
         ("precision", c_int32), ("reserved", c_int32 * 4),
+    ]
+
+
+class FitArgs(ctypes.Structure):
+    """sirenb200_fit_t (include/siren_b200.h)."""
+    _fields_ = [
+        ("n_tensors", c_int32), ("h_params", POINTER(c_void_p)), ("h_grads", POINTER(c_void_p)),
+        ("h_exp_avg", POINTER(c_void_p)), ("h_exp_avg_sq", POINTER(c_void_p)), ("h_mask", POINTER(c_void_p)),
+        ("h_numel", POINTER(c_int64)), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+        ("sched_state", c_void_p), ("stats", c_void_p), ("loss_ring", c_void_p), ("ring_len", c_int32),
+        ("loss_host", c_void_p), ("comm", c_void_p), ("flat", c_void_p), ("flat_n", c_int64),
+        ("inv_count", c_float),
     ]
 
 
@@ -80,6 +92,7 @@ def load():
     lib.sirenb200_comm_connect.argtypes = [vp, vp]
     lib.sirenb200_comm_allreduce.argtypes = [vp, vp, c_int64, vp]
     lib.sirenb200_comm_destroy.argtypes = [vp]
+    lib.sirenb200_fit_steps.argtypes = [vp, c_int32, vp, POINTER(FitArgs), vp]
     lib.sirenb200_kmeans_quantize.argtypes = [vp, c_int64, c_int32, c_int32, c_float, vp, vp, vp, vp,
                                               vp, vp]
     lib.sirenb200_fakequant_per_channel.argtypes = [vp, c_int32, c_int32, vp, vp, c_float, c_float, vp, vp,

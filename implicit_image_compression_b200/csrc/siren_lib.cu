@@ -1618,6 +1618,28 @@ int sirenb200_comm_allreduce(sirenb200_comm_t c, float* data, int64_t n, sirenb2
   return 0;
 }
 
+int sirenb200_fit_steps(sirenb200_handle_t h, int32_t k, const float* img, const sirenb200_fit_t* f,
+                        sirenb200_stream_t stream) {
+  if (!h || !img || !f || k < 0) return fail(SIRENB200_ERR_INVALID, "fit_steps: bad argument");
+  if (!f->h_params || !f->h_grads || !f->h_exp_avg || !f->h_exp_avg_sq || !f->h_numel || !f->sched_state ||
+      !f->stats)
+    return fail(SIRENB200_ERR_INVALID, "fit_steps: null field");
+  if (f->comm && (!f->flat || f->flat_n < 1)) return fail(SIRENB200_ERR_INVALID, "fit_steps: comm without flat");
+  for (int i = 0; i < k; ++i) {
+    int rc = sirenb200_forward_backward(h, f->h_params, img, 1.0f, f->h_grads, f->stats, stream);
+    if (!rc && f->comm) rc = sirenb200_comm_allreduce(f->comm, f->flat, f->flat_n, stream);
+    if (!rc)
+      rc = sirenb200_sched_step(f->sched_state, f->stats, f->comm ? f->inv_count : 0.0f, f->loss_ring,
+                                f->ring_len, f->loss_host, stream);
+    if (!rc)
+      rc = sirenb200_adam_step_dev(f->n_tensors, f->h_params, f->h_grads, f->h_exp_avg, f->h_exp_avg_sq, f->h_mask,
+                                   f->h_numel, f->beta1, f->beta2, f->eps, f->sched_state, 1.0f, f->stats + 2, 0,
+                                   stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int sirenb200_comm_destroy(sirenb200_comm_t c) {
   if (!c) return 0;
   cudaDeviceSynchronize();

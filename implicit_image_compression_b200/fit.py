@@ -235,6 +235,48 @@ class Fitter:
         self.step_index += 1
         return value
 
+    def native_steps(self, k):
+        """k dense steps through ONE C call (sirenb200_fit_steps: the whole loop lives in the library, nothing
+        per step on the Python side; what a non-Python host would call).  Same device-side schedule as the
+        graph path; returns the k losses as a device tensor.  No masks' topology updates, no transforms."""
+        if not self._graph_eligible() or self.masking_cfg is not None:
+            raise _lib.SirenB200Error("native_steps needs a graph-eligible (dense / dense-gradient) fit")
+        if not self.model.training:
+            self.model.train()
+        self._prepare_graph()
+        g = self._g
+        if self.mask is not None:
+            for n, w in self.mask._masked_parameters():
+                g["mask_bufs"][w].copy_(self.mask.mask_dict[n])
+        self._sync_sched_state()
+        step0 = self.optim.param_groups[0].get("_fused_step", 0)
+        cast = lambda arr: ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))  # noqa: E731
+        flat = self.flat
+        fa = _lib.FitArgs(
+            n_tensors=g["n"], h_params=cast(g["p"]), h_grads=cast(g["g"]), h_exp_avg=cast(g["m"]),
+            h_exp_avg_sq=cast(g["v"]), h_mask=cast(g["mask"]) if g["mask"] is not None else None,
+            h_numel=g["numel"], beta1=g["beta1"], beta2=g["beta2"], eps=g["eps"],
+            sched_state=g["state"].data_ptr(), stats=flat.stats.data_ptr(), loss_ring=g["ring"].data_ptr(),
+            ring_len=_RING, loss_host=g["host_loss"].data_ptr(),
+            comm=flat.comm.handle if (self.world > 1 and flat.comm is not None) else None,
+            flat=flat.flat.data_ptr(), flat_n=flat.flat.numel(),
+            inv_count=self.inv_count if self.world > 1 else 0.0)
+        if self.world > 1 and flat.comm is None:
+            raise _lib.SirenB200Error("native_steps on a sharded fit needs the peer-memory exchange")
+        k = min(int(k), _RING)
+        _lib.check(self.engine.lib.sirenb200_fit_steps(self.engine.handle, k, self.img.data_ptr(),
+                                                       ctypes.byref(fa),
+                                                       torch.cuda.current_stream().cuda_stream))
+        self._warmed = True
+        idx = (torch.arange(k, device=self.img.device) + step0) % _RING
+        losses = g["ring"][idx]
+        self._advance_host(k)
+        ds = self._shared["dev_state"]
+        if ds is not None:
+            self._shared["dev_state"] = (ds[0] + k,) + ds[1:]
+        self.step_index += k
+        return losses
+
     # ------------------------------------------------------------------ public
     def steps(self, k):
         """Run k fit steps; returns a device tensor [k] with each step's (pre-update) loss."""

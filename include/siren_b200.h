@@ -156,6 +156,38 @@ int sirenb200_profile_read(sirenb200_handle_t h, float* h_total_ms, int32_t* h_c
  * SIRENB200_TIMELINE environment variable at create time) to a HOST array of n int64. */
 int sirenb200_debug_timeline(sirenb200_handle_t h, long long* h_out, int32_t n);
 
+/* ---- k fit steps in one call (SURVEY.md §8b "fit_steps(k) fused driver") ---------------------------------
+ * The loop of compress.py:137-143 for a host language that has no per-step work of its own: k times
+ *   forward_backward (gradients into h_grads, stats)  ->  [comm_allreduce of the flat gradient buffer when
+ *   comm != NULL]  ->  sched_step  ->  adam_step_dev (masks applied when h_mask != NULL),
+ * all enqueued on `stream` with no host synchronisation; the per-step losses land in loss_ring (and
+ * loss_host).  For a sharded fit the caller lays the gradients out as views of ONE flat buffer `flat`
+ * (flat_n floats: [all gradients | stats[4]], stats = flat + flat_n - 4 rounded as the caller chose) and
+ * passes inv_count = 1 / (H*W*C) of the FULL image; for a single-GPU fit comm = NULL, flat = NULL,
+ * inv_count = 0.  Pointer tables are HOST arrays of device pointers (as everywhere in this ABI). */
+typedef struct sirenb200_comm* sirenb200_comm_t;
+typedef struct {
+  int32_t n_tensors;
+  float* const* h_params;
+  float* const* h_grads;
+  float* const* h_exp_avg;
+  float* const* h_exp_avg_sq;
+  const float* const* h_mask; /* NULL: no masks */
+  const int64_t* h_numel;
+  float beta1, beta2, eps;
+  double* sched_state;        /* 8 doubles, see sirenb200_sched_step */
+  float* stats;               /* device float[4] */
+  float* loss_ring;           /* device, may be NULL */
+  int32_t ring_len;
+  float* loss_host;           /* host-mapped, may be NULL */
+  sirenb200_comm_t comm;      /* NULL for a single-GPU fit */
+  float* flat;                /* flat gradient buffer (sharded fits) */
+  int64_t flat_n;
+  float inv_count;            /* > 0: loss = stats[0] * inv_count (after the exchange) */
+} sirenb200_fit_t;
+int sirenb200_fit_steps(sirenb200_handle_t h, int32_t k, const float* img, const sirenb200_fit_t* fit,
+                        sirenb200_stream_t stream);
+
 /* ---- gradient exchange for pixel-sharded fits (SURVEY.md §8e "allreduce_grads") ---------------------------
  * One process per GPU of ONE node.  The reference has no distributed code; this is the exchange step of the
  * row-sharded fit: an in-place SUM of a flat fp32 buffer [all dW | all db | sum_sq_err, -, nonfinite, -] over
@@ -167,7 +199,6 @@ int sirenb200_debug_timeline(sirenb200_handle_t h, long long* h_out, int32_t n);
  * device) and can be captured in a CUDA graph; `data` must be 16-byte aligned with room for n rounded up to a
  * multiple of 4 floats, n <= max_floats.  A peer that never arrives makes the kernel trap after a few
  * seconds (sticky CUDA error) rather than hang. */
-typedef struct sirenb200_comm* sirenb200_comm_t;
 int sirenb200_comm_create(int32_t rank, int32_t world, int64_t max_floats, sirenb200_comm_t* out);
 int sirenb200_comm_handle(sirenb200_comm_t c, void* handle_out_64_bytes);
 int sirenb200_comm_connect(sirenb200_comm_t c, const void* handles_world_x_64_bytes);

@@ -166,3 +166,24 @@ def test_fitter_graph_with_masks_matches_reference_loop(monkeypatch):
         for n in out[0][1]:
             assert torch.equal(out[0][1][n], other[1][n]), n
         assert out[0][2] == other[2] and out[0][3] == other[3]
+
+
+def test_native_fit_steps_entry_point_matches_fitter():
+    """sirenb200_fit_steps (the k-step loop inside the library, what a non-Python host would call) runs the
+    same kernels in the same order as Fitter.steps: identical losses and weights."""
+    get_grid, synth_image, Fitter, Siren, th = _pkg()
+    H, W = 64, 96
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    out = []
+    for native in (False, True):
+        torch.manual_seed(0)
+        model = Siren(depth=4, hidden_size=128, first_omega_0=50, hidden_omega_0=30).cuda()
+        optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
+        f = Fitter(model, optim, grid, img, sched)
+        losses = (f.native_steps(12) if native else f.steps(12)).tolist()
+        more = f.steps(3).tolist()  # the two paths share the device-side schedule state
+        out.append((losses + more, [p.detach().clone() for p in model.parameters()],
+                    optim.param_groups[0]["_fused_step"], sched.last_epoch))
+    assert out[0][0] == out[1][0]
+    assert all(torch.equal(a, b) for a, b in zip(out[0][1], out[1][1]))
+    assert out[0][2:] == out[1][2:] == (15, 15)
