@@ -648,7 +648,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     jobs.interleave = interleave;
   };
   const bool overlap = p->bwd_overlap && nh > 0 && p->st2;
-  const bool fuse_l0 = p->fuse_l0 && W <= 256 && nh >= 1 && p->nchunks == 1 && !overlap;
+  const bool fuse_l0 = p->fuse_l0 && nh >= 1 && p->nchunks == 1 && !overlap;
   // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
   for (int l = nh; l >= 1; --l) {
     if (overlap) {
@@ -666,7 +666,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     p->grid_override = overlap ? p->dx_grid : 0;
     int rc;
     bool done = false;
-    if constexpr (W <= 256) {
+    {
       if (l == 1 && fuse_l0) {
         ra.gen_coord = p->coord;
         ra.gen_coord.p_offset = ch.p0;
@@ -1148,7 +1148,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     p->l0_grid = p->nsm * 2;
     if (p->l0_grid > p->chunk_tiles) p->l0_grid = p->chunk_tiles;
     {  // room for the stand-alone kernel's l0_grid rows or the dX-fused reducer's 2 rows per CTA
-      int rows = 2 * (p->chunk_tiles < p->nsm ? p->chunk_tiles : p->nsm);
+      int rows = 2 * p->nsm;
       if (rows < p->l0_grid) rows = p->l0_grid;
       ALLOC(p->l0_part, int64_t(p->nchunks) * rows * 3 * W);
     }

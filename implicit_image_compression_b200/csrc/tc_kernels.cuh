@@ -145,7 +145,7 @@ struct RowGemmArgs {
   // warps straight into the A ring, and stored to the activation stash from there.
   // RED (dX of the first hidden layer): four extra warps read every finished dz[0] chunk back from the
   // staging buffer and accumulate layer 0's weight / bias gradient (dW0 = dz0^T x, db0 = sum dz0; autograd of
-  // siren.py:62 for the is_first layer), so dz[0] is never re-read from HBM.  red_part: [2 * gridDim.x][3 * NDIM]
+  // siren.py:62 for the is_first layer), so dz[0] is never re-read from HBM.  red_part: [2 * gridDim.x][3 * hidden]
   // = per-CTA partials {dW0 [NDIM, 2], db0 [NDIM]}.
   float* red_part;
   CoordSrc gen_coord;   // GEN and RED: coordinates of this launch's pixels
@@ -405,17 +405,24 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (RED && warp >= 12) {
     // ===================== layer-0 gradient: reduce each finished dz[0] chunk over its 128 pixels =========
-    static_assert(!RED || (MODE == MODE_DX && NPARTS == 1 && C::NB <= 4), "RED: dX of the first hidden layer");
-    // two warps per 64-column chunk (64 pixel rows each); lane -> columns nb*64 + 2*lane, +1
+    static_assert(!RED || (MODE == MODE_DX && NPARTS <= 2 && C::NB <= 4), "RED: dX of the first hidden layer");
+    // two warps per 64-column chunk (64 pixel rows each); lane -> columns part*NDIM + nb*64 + 2*lane, +1.
+    // With two output parts (hidden 512) every tile is visited twice, once per part; each part has its own
+    // accumulators.
     const int nb = (warp - 12) >> 1, half = (warp - 12) & 1;
     if (nb < C::NB) {
       const CoordSrc& cs = args.gen_coord;
-      float sh0 = 0.f, sw0 = 0.f, sb0 = 0.f, sh1 = 0.f, sw1 = 0.f, sb1 = 0.f;
+      float acc[NPARTS][6];
+#pragma unroll
+      for (int pp = 0; pp < NPARTS; ++pp)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[pp][j] = 0.f;
       const uint32_t lane_off = (uint32_t(lane) & 3u) * 4u;
-      // red_full[nb] belongs to this warp alone and is waited on once per tile, so its parity cannot alias
-      // (a barrier shared between the chunk indices could be probed more than one phase ahead)
-      uint32_t ic = uint32_t(nb), tl = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ic += C::NB, ++tl) {
+      // red_full[nb] belongs to this chunk index alone and is waited on once per work item, so its parity
+      // cannot alias (a barrier shared between the chunk indices could be probed more than one phase ahead)
+      uint32_t ic = uint32_t(nb), il = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ic += C::NB, ++il) {
+        const int t = item / NPARTS, part = item % NPARTS;
         // coordinates of rows lane + 32 q (zero for the padding rows: their dz is zero anyway)
         float xh[2], xw[2];
 #pragma unroll
@@ -426,7 +433,8 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const uint32_t s = ic % C::SEO;
         const uint32_t buf = smem_u32(smem + C::OFF_EO + s * kChunkBytes);
-        mbar_wait(&red_full[nb], tl & 1u);
+        mbar_wait(&red_full[nb], il & 1u);
+        float sh0 = 0.f, sw0 = 0.f, sb0 = 0.f, sh1 = 0.f, sw1 = 0.f, sb1 = 0.f;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
 #pragma unroll 8
@@ -448,15 +456,29 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&eo_empty[s]);
+#pragma unroll
+        for (int pp = 0; pp < NPARTS; ++pp)
+          if (pp == part) {
+            acc[pp][0] += sh0;
+            acc[pp][1] += sw0;
+            acc[pp][2] += sb0;
+            acc[pp][3] += sh1;
+            acc[pp][4] += sw1;
+            acc[pp][5] += sb1;
+          }
       }
-      float* part = args.red_part + (size_t(blockIdx.x) * 2 + half) * 3 * NDIM;
-      const int c0 = nb * 64 + 2 * lane;
-      part[c0 * 2 + 0] = sh0;
-      part[c0 * 2 + 1] = sw0;
-      part[c0 * 2 + 2] = sh1;
-      part[c0 * 2 + 3] = sw1;
-      part[2 * NDIM + c0] = sb0;
-      part[2 * NDIM + c0 + 1] = sb1;
+      constexpr int WFULL = NDIM * NPARTS;
+      float* part_out = args.red_part + (size_t(blockIdx.x) * 2 + half) * 3 * WFULL;
+#pragma unroll
+      for (int pp = 0; pp < NPARTS; ++pp) {
+        const int c0 = pp * NDIM + nb * 64 + 2 * lane;
+        part_out[c0 * 2 + 0] = acc[pp][0];
+        part_out[c0 * 2 + 1] = acc[pp][1];
+        part_out[c0 * 2 + 2] = acc[pp][3];
+        part_out[c0 * 2 + 3] = acc[pp][4];
+        part_out[2 * WFULL + c0] = acc[pp][2];
+        part_out[2 * WFULL + c0 + 1] = acc[pp][5];
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> f() -> smem -> TMA store =====================

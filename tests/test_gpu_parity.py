@@ -429,7 +429,7 @@ def test_deepcopy_and_rebinding_weight_data():
     assert not torch.equal(a, c)
 
 
-@pytest.mark.parametrize("hidden,depth,H,W", [(256, 5, 40, 56), (128, 4, 33, 47)])
+@pytest.mark.parametrize("hidden,depth,H,W", [(256, 5, 40, 56), (128, 4, 33, 47), (512, 4, 20, 36)])
 def test_fused_kernel_variants_match_the_kernels_they_replace(monkeypatch, hidden, depth, H, W):
     """The fused kernels of the tensor-core path against the stand-alone kernels they replace (selected by
     environment switches read at handle creation), same weights, same image:
