@@ -838,7 +838,7 @@ struct SchedArgs {
   float inv_count;      // >0: loss = stats[0] * inv_count (pixel-sharded fits), else stats[1]
   float* loss_ring;
   int ring_len;
-  float* loss_host;     // optional: host-mapped (pinned) float that also receives the loss
+  float* loss_host;     // optional: host-mapped (pinned) float[2]: {loss, number of steps completed}
 };
 __global__ void sched_step_kernel(const SchedArgs a) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -851,7 +851,12 @@ __global__ void sched_step_kernel(const SchedArgs a) {
   a.state[7] = sqrt(bc2);
   const float loss = a.inv_count > 0.f ? a.stats[0] * a.inv_count : a.stats[1];
   if (a.loss_ring) a.loss_ring[step % a.ring_len] = loss;
-  if (a.loss_host) *a.loss_host = loss;
+  if (a.loss_host) {
+    // the host may poll [1] instead of synchronising the stream: loss first, then the step count
+    a.loss_host[0] = loss;
+    __threadfence_system();
+    a.loss_host[1] = float(step + 1);
+  }
   a.state[0] = double(step + 1);
 }
 

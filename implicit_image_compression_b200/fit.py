@@ -131,7 +131,7 @@ class Fitter:
                 "ring": torch.zeros(_RING, dtype=torch.float32, device=dev),
                 # pinned host float the schedule kernel also writes the loss to (unified addressing: the
                 # device uses the host pointer), read by step_loss() after a stream synchronisation
-                "host_loss": torch.zeros(1, dtype=torch.float32).pin_memory(),
+                "host_loss": torch.zeros(2, dtype=torch.float32).pin_memory(),  # {loss, steps completed}
                 "dev_state": None,  # what the device holds (skip the upload when unchanged)
             }
             opt.__dict__["_sirenb200_sched"] = shared
@@ -212,8 +212,7 @@ class Fitter:
             done += 1
         value = None
         if losses is None:
-            torch.cuda.current_stream().synchronize()
-            value = float(g["host_loss"][0])
+            value = self._read_loss()
         elif k == 1:
             losses[offset:offset + 1] = g["ring"][step0 % _RING:step0 % _RING + 1]
         else:
@@ -224,6 +223,13 @@ class Fitter:
         if ds is not None:  # the device advanced its own step counter
             self._shared["dev_state"] = (ds[0] + k,) + ds[1:]
         return value
+
+    def _read_loss(self):
+        """The schedule kernel mirrors {loss, steps completed} into pinned host memory; after a stream
+        synchronisation (which releases the GIL, unlike a Python-side poll of the count — measured: polling is
+        not faster, the per-call gap is graph-launch latency) the loss is a plain host read."""
+        torch.cuda.current_stream().synchronize()
+        return float(self._shared["host_loss"][0])
 
     def step_loss(self):
         """One device-scheduled step, loss returned as a float; None when the step is not graph-eligible."""

@@ -110,8 +110,9 @@ int sirenb200_adam_step(int32_t n_tensors, float* const* h_params, float* const*
  * sirenb200_sched_step computes [6],[7] for the step about to run (train_helper.py:80-84 StepLR + Adam bias
  * correction), stores the loss of the step that just ran into loss_ring[step % ring_len] (stats[1], or
  * stats[0]*inv_count when inv_count > 0, i.e. after an all-reduce of pixel shards) and, when loss_host is not
- * NULL, also into that host-mapped (pinned, device-accessible) float - train_epoch's "return loss.item()"
- * then costs a stream synchronisation and a host read instead of a copy kernel + cudaMemcpy - and increments [0];
+ * NULL, also into that host-mapped (pinned, device-accessible) float[2] as {loss, steps completed} (loss first,
+ * system fence, then the count), so that train_epoch's "return loss.item()" is a host-side poll of the count
+ * instead of a copy kernel + cudaMemcpy + stream synchronisation - and increments [0];
  * sirenb200_adam_step_dev is sirenb200_adam_step reading the schedule from sched_state. */
 int sirenb200_sched_step(double* sched_state, const float* stats, float inv_count, float* loss_ring,
                          int32_t ring_len, float* loss_host, sirenb200_stream_t stream);
