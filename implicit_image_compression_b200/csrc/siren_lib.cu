@@ -90,13 +90,11 @@ struct sirenb200_plan {
   float4* tab0 = nullptr; // [W] layer-0 epilogue table (fused forward)
   float* bias_w = nullptr;  // [(D-2)][W] omega * bias
   float* bias_raw = nullptr;  // [(D-2)][W] bias (contiguous copy for the fused forward)
-  CUtensorMap tm_act{}, tm_dz{}, tm_wstack{};
-  bool fused_fwd = false;
+  CUtensorMap tm_act{}, tm_dz{};
   __half* wl16 = nullptr;   // [16, W] last-layer weights for the tensor-core last layer
   __half* wlt16 = nullptr;  // [W, 64]
   CUtensorMap tm_wl{}, tm_wlt{};
   bool last_tc = false;
-  bool fwd_pair = false;    // two hidden layers per forward kernel (SIRENB200_FWD_PAIR=1)
   bool tail_fused = true;   // last hidden GEMM + output layer + loss + dZ in one kernel (SIRENB200_TAIL=0: two kernels)
   bool pdl = true;          // programmatic dependent launch of the GEMM kernels (SIRENB200_PDL=0: off)
   bool fuse_l0 = true;      // layer-0 gradient reduced inside the dX GEMM of the first hidden layer (SIRENB200_FUSE_L0=0: own kernel)
@@ -104,9 +102,7 @@ struct sirenb200_plan {
   int last_rowgemm_grid = 0;
   bool gen_first = true;    // layer 0 generated inside the first hidden GEMM (SIRENB200_GEN_FIRST=0: own kernel)
   long long* dbg_timeline = nullptr;  // SIRENB200_TIMELINE=1: 3*4*8*16 clock64 slots (debug)
-  std::vector<CUtensorMap> tm_w, tm_wt, tm_wt_half;
-  bool fused_bwd = false;      // one-pass dX + dW kernel per hidden layer (hidden = 256)
-  int bwd_pairs = 0;           // CTA pairs of that kernel (= partial slabs it writes)
+  std::vector<CUtensorMap> tm_w, tm_wt;
   float* dw_part = nullptr;  // [splits][D-2][W][W]
   float* db_part = nullptr;  // [splits][D-2][W]
   int col_splits = 1;
@@ -116,14 +112,6 @@ struct sirenb200_plan {
   int l0_grid = 0;
   int chunk_tiles = 0;         // 128-row tiles per L2-resident chunk (0 = whole shard)
   int nchunks = 1;
-  // backward overlap: the dW GEMM of layer l runs on a second stream concurrently with the dX GEMM of
-  // layer l (both read dz[l] and act[l-1]; whichever comes second finds them in L2)
-  bool bwd_overlap = false;
-  int dx_grid = 0;             // CTAs given to the dX GEMM when overlapping (rest goes to the dW GEMM)
-  cudaStream_t st2 = nullptr;
-  cudaEvent_t ev_fork[kMaxLayers] = {};
-  cudaEvent_t ev_join = nullptr;
-  int grid_override = 0;       // transient: rowgemm grid size for the next launch
   int active_splits = 1;       // split slabs the dW GEMM actually writes (<= col_splits)
 
   // ---- optional per-kernel timing (cudaEvent pairs recorded around tagged launches) ----
@@ -225,7 +213,6 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   }
   const int items = args.num_tiles * NPARTS;
   int grid = items < p->nsm ? items : p->nsm;
-  if (p->grid_override > 0 && p->grid_override < grid) grid = p->grid_override;
   const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
@@ -326,84 +313,9 @@ int tc_prep(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* 
 }
 
 template <int W>
-int launch_fused_fwd(sirenb200_plan* p, const Chunk& ch, cudaStream_t st) {
-  if constexpr (W == 256) {
-    using Cfg = FusedFwdCfg<W>;
-    auto kfn = fused_fwd_kernel<W>;
-    static bool attr_set[64] = {};
-    if (!attr_set[p->device & 63]) {
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    int(Cfg::SMEM_BYTES)));
-      attr_set[p->device & 63] = true;
-    }
-    FusedFwdArgs fa{};
-    fa.num_tiles = ch.ntiles;
-    fa.nh = p->D - 2;
-    fa.npix = ch.npix;
-    fa.npix_pad = p->npix_pad;
-    fa.tab0 = p->tab0;
-    fa.bias_w = p->bias_w;
-    fa.bias_raw = p->bias_raw;
-    fa.omega = p->cfg.hidden_omega;
-    fa.lin_h = p->coord.lin_h;
-    fa.lin_w = p->coord.lin_w;
-    fa.coords = p->coord.coords;
-    fa.width = p->coord.width;
-    fa.row_begin = p->coord.row_begin;
-    fa.dbg = p->dbg_timeline;
-    const int grid = ch.ntiles < p->nsm ? ch.ntiles : p->nsm;
-    {
-      ProfScope ps(p, PK_FWD_GEMM, st);
-      kfn<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(p->tm_wstack, p->tm_act, fa,
-                                                      umma_idesc(128, W, 0, 0, 0, 0));
-    }
-    LAUNCH_CHECK();
-    return 0;
-  } else {
-    return fail(SIRENB200_ERR_INVALID, "fused forward needs hidden = 256");
-  }
-}
-
-// two consecutive hidden layers (l, l + 1) in one kernel: act[l] is stashed but not read back
-template <int W>
-int launch_fwd_pair(sirenb200_plan* p, const float* const* prm, int l, const Chunk& ch, cudaStream_t st) {
-  if constexpr (W == 128 || W == 256) {
-    using Cfg = FwdPairCfg<W>;
-    auto kfn = fwd_pair_kernel<W>;
-    static bool attr_set[64] = {};
-    if (!attr_set[p->device & 63]) {
-      CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    int(Cfg::SMEM_BYTES)));
-      attr_set[p->device & 63] = true;
-    }
-    FwdPairArgs fa{};
-    fa.num_tiles = ch.ntiles;
-    fa.a_row0 = int((l - 1) * p->npix_pad + ch.p0);
-    fa.t_row0 = int(l * p->npix_pad + ch.p0);
-    fa.o_row0 = int((l + 1) * p->npix_pad + ch.p0);
-    fa.omega_a = omega_of(p, l);
-    fa.omega_b = omega_of(p, l + 1);
-    fa.bias_a = prm[2 * l + 1];
-    fa.bias_b = prm[2 * (l + 1) + 1];
-    fa.dbg = p->dbg_timeline ? p->dbg_timeline + 3 * 4 * 8 * 16 : nullptr;
-    const int grid = ch.ntiles < p->nsm ? ch.ntiles : p->nsm;
-    {
-      ProfScope ps(p, PK_FWD_GEMM, st);
-      launch_ex(kfn, dim3(grid), dim3(640), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_act, p->tm_w[l - 1],
-                p->tm_w[l], fa);
-    }
-    LAUNCH_CHECK();
-    return 0;
-  } else {
-    return fail(SIRENB200_ERR_INVALID, "forward pair kernel needs hidden 128 or 256");
-  }
-}
-
-template <int W>
 int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st,
                      bool skip_last_hidden = false) {
   const int nh = p->D - 2;
-  if (p->fused_fwd && ch.index == 0 && p->nchunks == 1) return launch_fused_fwd<W>(p, ch, st);
   // Layer 0 runs inside the first hidden layer's GEMM (its A operand is generated in the kernel) when
   // that kernel keeps its weights resident; otherwise as its own CUDA-core kernel.
   constexpr bool kCanGen = (W <= 256);
@@ -421,15 +333,6 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
   LAUNCH_CHECK();
   const int l_end = skip_last_hidden ? nh - 1 : nh;
   for (int l = 1; l <= l_end; ++l) {
-    if constexpr (W == 128 || W == 256) {
-      // two plain hidden layers at a time when there are two left (layer 1 stays with the generator kernel)
-      if (p->fwd_pair && p->nchunks == 1 && !(l == 1 && gen_first) && l + 1 <= l_end) {
-        int rc = launch_fwd_pair<W>(p, prm, l, ch, st);
-        if (rc) return rc;
-        ++l;
-        continue;
-      }
-    }
     RowGemmArgs ra{};
     ra.num_tiles = ch.ntiles;
     ra.a_row0 = int((l - 1) * p->npix_pad + ch.p0);
@@ -572,60 +475,10 @@ int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const fl
   return 0;
 }
 
-int launch_bwd_layer(sirenb200_plan* p, int l, const Chunk& ch, cudaStream_t st) {
-  auto kfn = bwd_layer_kernel;
-  static bool attr_set[64] = {};
-  if (!attr_set[p->device & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  int(BwdCfg::SMEM_BYTES)));
-    attr_set[p->device & 63] = true;
-  }
-  BwdArgs ba{};
-  ba.num_tiles = ch.ntiles;
-  ba.dz_row0 = int(l * p->npix_pad + ch.p0);
-  ba.act_row0 = int((l - 1) * p->npix_pad + ch.p0);
-  ba.out_row0 = int((l - 1) * p->npix_pad + ch.p0);
-  ba.valid_rows = int(ch.npix);
-  ba.dw_partial = p->dw_part;
-  ba.db_partial = p->db_part;
-  ba.prob = l - 1;
-  ba.prob_total = p->D - 2;
-  {
-    ProfScope ps(p, PK_DX_GEMM, st);
-    kfn<<<2 * p->bwd_pairs, 256, BwdCfg::SMEM_BYTES, st>>>(
-        p->tm_dz, p->tm_act, p->tm_wt_half[l - 1], ba, umma_idesc(128, 128, 0, 0, 0, 0),
-        umma_idesc(128, 256, 0, 0, 1, 1), umma_idesc(128, 16, 0, 0, 1, 1));
-  }
-  LAUNCH_CHECK();
-  return 0;
-}
-
 template <int W>
 int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
   const int nh = p->D - 2;
   constexpr int NPARTS = W / (W < 256 ? W : 256);
-  if (p->fused_bwd && W == 256 && p->nchunks == 1) {
-    for (int l = nh; l >= 1; --l) {
-      int rc = launch_bwd_layer(p, l, ch, st);
-      if (rc) return rc;
-    }
-    CoordSrc cs = p->coord;
-    cs.p_offset = ch.p0;
-    static bool l0_attr[64] = {};
-    if (!l0_attr[p->device & 63]) {
-      CUDA_TRY(cudaFuncSetAttribute(tc_layer0_grad_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    int(L0GradCfg<W>::SMEM_BYTES)));
-      l0_attr[p->device & 63] = true;
-    }
-    {
-      ProfScope ps(p, PK_L0_GRAD, st);
-      tc_layer0_grad_kernel<W><<<p->l0_grid, 256, L0GradCfg<W>::SMEM_BYTES, st>>>(
-          cs, p->dz + ch.p0 * W, p->l0_part + size_t(ch.index) * p->l0_grid * 3 * W, ch.npix);
-    }
-    p->l0_used = p->l0_grid * p->nchunks;
-    LAUNCH_CHECK();
-    return 0;
-  }
   auto fill_jobs = [&](ColGemmJobs& jobs, int l_first, int nprob, int splits, int interleave) {
     jobs.num_problems = nprob;
     jobs.mblocks = W / 128;
@@ -647,15 +500,9 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     jobs.prob_total = nh;
     jobs.interleave = interleave;
   };
-  const bool overlap = p->bwd_overlap && nh > 0 && p->st2;
-  const bool fuse_l0 = p->fuse_l0 && nh >= 1 && p->nchunks == 1 && !overlap;
+  const bool fuse_l0 = p->fuse_l0 && nh >= 1 && p->nchunks == 1;
   // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
   for (int l = nh; l >= 1; --l) {
-    if (overlap) {
-      // dz[l] is complete on `st` here: fork the weight-gradient GEMM of layer l onto the side stream
-      CUDA_TRY(cudaEventRecord(p->ev_fork[l], st));
-      CUDA_TRY(cudaStreamWaitEvent(p->st2, p->ev_fork[l], 0));
-    }
     RowGemmArgs ra{};
     ra.num_tiles = ch.ntiles;
     ra.a_row0 = int(l * p->npix_pad + ch.p0);
@@ -663,7 +510,6 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     ra.o_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.valid_rows = int(ch.npix);
     ra.b_early = 1;  // omega W^T was staged at the start of the step, at least two kernels ago
-    p->grid_override = overlap ? p->dx_grid : 0;
     int rc;
     bool done = false;
     {
@@ -677,20 +523,10 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
       }
     }
     if (!done) rc = launch_rowgemm<W, MODE_DX>(p, p->tm_dz, p->tm_wt[l - 1], p->tm_act, p->tm_dz, ra, st);
-    p->grid_override = 0;
     if (rc) return rc;
-    if (overlap) {
-      ColGemmJobs jobs{};
-      int splits = (p->nsm - p->dx_grid) / ((W / 128) * NPARTS);
-      if (splits < 1) splits = 1;
-      if (splits > p->col_splits) splits = p->col_splits;
-      fill_jobs(jobs, l, 1, splits, 1);
-      rc = launch_colgemm<W>(p, jobs, p->st2);
-      if (rc) return rc;
-    }
   }
   // hidden-layer weight / bias gradients: one split-K launch over all layers
-  if (nh > 0 && !overlap) {
+  if (nh > 0) {
     ColGemmJobs jobs{};
     fill_jobs(jobs, 1, nh, p->col_splits, 0);
     int rc = launch_colgemm<W>(p, jobs, st);
@@ -713,10 +549,6 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
                                                   ch.npix);
   }
   LAUNCH_CHECK();
-  if (overlap) {  // join the side stream before the partials are reduced
-    CUDA_TRY(cudaEventRecord(p->ev_join, p->st2));
-    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_join, 0));
-  }
   return 0;
 }
 
@@ -778,7 +610,7 @@ int tc_run(sirenb200_plan* p, const float* const* prm, int mode, const float* im
     if (rc) return rc;
     // training step with at least two hidden GEMM layers: the last one is fused with the output layer
     const bool tail = W <= 256 && mode == 1 && p->tail_fused && p->last_tc && p->D - 2 >= 2 && p->nchunks == 1 &&
-                      !p->fused_fwd && img_or_dpred;
+                      img_or_dpred;
     if (mode != 2) rc = tc_forward_chunk<W>(p, prm, ch, st, tail);
     if (!rc) rc = tail ? launch_tail<W>(p, prm, img_or_dpred, pred, ch, st)
                        : tc_last_chunk<W>(p, prm, mode, img_or_dpred, pred, ch, st);
@@ -1074,63 +906,19 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     if (splits < 1) splits = 1;
     if (splits > p->ntiles) splits = p->ntiles;
     p->col_splits = splits;  // (re-clamped to the chunk size below)
-    p->bwd_pairs = p->nsm / 2;
-    if (p->bwd_pairs > p->ntiles) p->bwd_pairs = p->ntiles;
-    {
-      // One-pass dX + dW kernel (tc_kernels.cuh: bwd_layer_kernel): correct, removes the split-K pass's
-      // 402 MB/layer re-read, but with a single 128 KB input buffer per CTA (smem is full) the
-      // load -> MMA -> epilogue chain is serial: measured 204 us/layer vs 174 us for dX + dW kernels.
-      // Opt-in (SIRENB200_FUSED_BWD=1) until a cta_group::2 version can double-buffer its inputs.
-      const char* env = getenv("SIRENB200_FUSED_BWD");
-      p->fused_bwd = (W == 256 && nh > 0) && (env && atoi(env) != 0);
-    }
-    const int slabs = (p->fused_bwd && p->bwd_pairs > splits) ? p->bwd_pairs : splits;
+    const int slabs = splits;
     ALLOC(p->dw_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W * W);
     ALLOC(p->db_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W);
-    {
-      // Row chunking (forward+backward per chunk so a chunk's stash is re-read from L2) is OFF by
-      // default: measured on B200 at config 2 it loses (1.56 ms/step unchunked vs 2.0 ms with two
-      // chunks, 5.9 ms with 21) because every tcgen05 kernel launch pays ~10 us of fixed cost (TMEM
-      // alloc, 128 KB weight load, pipeline fill/drain).  SIRENB200_CHUNK_TILES=<n> enables it.
-      int ct = 0;
-      const char* env = getenv("SIRENB200_CHUNK_TILES");
-      if (env) ct = atoi(env);
-      if (ct <= 0 || ct >= p->ntiles) ct = p->ntiles;
-      p->chunk_tiles = ct;
-      p->nchunks = cdiv(p->ntiles, ct);
-    }
+    p->chunk_tiles = p->ntiles;  // the whole shard is one chunk (row chunking lost to launch overheads)
+    p->nchunks = 1;
     if (p->col_splits > p->chunk_tiles) p->col_splits = p->chunk_tiles;
     p->active_splits = p->col_splits;
-    {
-      const char* env = getenv("SIRENB200_BWD_OVERLAP");
-      p->bwd_overlap = env && atoi(env) != 0 && nh > 0;
-      const char* eg = getenv("SIRENB200_DX_GRID");
-      p->dx_grid = eg ? atoi(eg) : (p->nsm * 2) / 3;
-      if (p->dx_grid < 1 || p->dx_grid >= p->nsm) p->dx_grid = (p->nsm * 2) / 3;
-      if (p->bwd_overlap) {
-        cudaError_t e = cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
-        for (int i = 0; i < kMaxLayers && e == cudaSuccess; ++i)
-          e = cudaEventCreateWithFlags(&p->ev_fork[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
-        if (e != cudaSuccess) {
-          sirenb200_destroy(p);
-          return fail(SIRENB200_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
-        }
-        int splits = (p->nsm - p->dx_grid) / ((W / 128) * (W / (W < 256 ? W : 256)));
-        if (splits < 1) splits = 1;
-        if (splits > p->col_splits) splits = p->col_splits;
-        p->active_splits = splits;
-      }
-      if (p->fused_bwd && p->nchunks == 1) p->active_splits = p->bwd_pairs;
-    }
     const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
     {
       const char* env = getenv("SIRENB200_LAST_TC");
       p->last_tc = (W == 128 || W == 256 || W == 512) && nh > 0 && !(env && atoi(env) == 0);
       env = getenv("SIRENB200_GEN_FIRST");
       p->gen_first = !(env && atoi(env) == 0);
-      env = getenv("SIRENB200_FWD_PAIR");
-      p->fwd_pair = env && atoi(env) != 0;
       env = getenv("SIRENB200_TAIL");
       p->tail_fused = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_PDL");
@@ -1162,17 +950,14 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     trc |= make_tmap_16bit(&p->tm_dz, p->dz, uint64_t(D - 1) * p->npix_pad, W, 128, false);
     p->tm_w.resize(nh > 0 ? nh : 0);
     p->tm_wt.resize(nh > 0 ? nh : 0);
-    p->tm_wt_half.resize(nh > 0 ? nh : 0);
     for (int l = 0; l < nh; ++l) {
       const uint32_t brows = W < 256 ? W : 256;  // B box rows = output columns per work item
       trc |= make_tmap_16bit(&p->tm_w[l], p->wh + size_t(l) * W * W, W, W, brows, false);
       trc |= make_tmap_16bit(&p->tm_wt[l], p->wth + size_t(l) * W * W, W, W, brows, false);
-      trc |= make_tmap_16bit(&p->tm_wt_half[l], p->wth + size_t(l) * W * W, W, W, 128, false);
     }
     if (p->last_tc) {
       trc |= make_tmap_16bit(&p->tm_wl, p->wl16, 16, W, 16, false);
     }
-    if (nh > 0) trc |= make_tmap_16bit(&p->tm_wstack, p->wh, uint64_t(nh) * W, W, W < 256 ? W : 256, false);
     if (trc) {
       sirenb200_destroy(p);
       return fail(SIRENB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", trc);
@@ -1180,14 +965,6 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     if (getenv("SIRENB200_TIMELINE")) {
       ALLOC(p->dbg_timeline, 3 * 4 * 8 * 16 + 12 * 16);
       cudaMemset(p->dbg_timeline, 0, (3 * 4 * 8 * 16 + 12 * 16) * sizeof(long long));
-    }
-    {
-      // The fused multi-layer forward (tc_kernels.cuh: fused_fwd_kernel) is correct (same tests pass)
-      // but measured SLOWER than the per-layer kernels at config 2 (0.39-0.47 ms vs 0.38 ms): with one
-      // CTA per SM its sin epilogue (~3500-4400 cycles per 128x256 tile-layer, MUFU + issue bound) does
-      // not overlap the MMAs well and the 3-stage weight ring starves.  Opt-in until the 2-CTA version.
-      const char* env = getenv("SIRENB200_FUSED_FWD");
-      p->fused_fwd = (W == 256 && nh > 0) && (env && atoi(env) != 0);
     }
   }
 #undef ALLOC
@@ -1205,10 +982,6 @@ int sirenb200_destroy(sirenb200_handle_t p) {
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
-  for (cudaEvent_t e : p->ev_fork)
-    if (e) cudaEventDestroy(e);
-  if (p->ev_join) cudaEventDestroy(p->ev_join);
-  if (p->st2) cudaStreamDestroy(p->st2);
   delete p;
   return 0;
 }

@@ -766,577 +766,6 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 
 // ------------------------------------------------------------------------------------------
-// fused forward: layer 0 (CUDA cores, in-kernel coordinates) + every hidden layer (tcgen05) for one
-// 128-pixel tile at a time, activations never leave the SM between layers.
-//
-//   smem : two 64 KiB activation buffers (K-major SW128, the epilogue's output tile of layer l IS the
-//          A operand of layer l+1 and the source of the TMA store that stashes it for the backward
-//          pass) + a 3-stage ring of 32 KiB weight k-blocks streamed from L2 by TMA.
-//   TMEM : two 128 x W fp32 accumulators (layer l drains while layer l+1 accumulates).
-//   MMA order is K-outer: layer l+1 starts on k-block c as soon as the epilogue of layer l has written
-//   column chunk c, so the tensor pipe trails the (MUFU-bound) epilogue by one chunk.
-// ------------------------------------------------------------------------------------------
-struct FusedFwdArgs {
-  int num_tiles;
-  int nh;                  // hidden (W x W) layers: 1 .. nh
-  int64_t npix;            // valid pixels of this launch
-  int64_t npix_pad;        // rows per layer inside the activation stack
-  const float4* tab0;      // [W] (omega0*w_h, omega0*w_w, omega0*b, 0) of layer 0
-  const float* bias_w;     // [nh][W] omega * bias of the hidden layers (unused by the fused kernel)
-  const float* bias_raw;   // [nh][W] bias of the hidden layers: the accumulators are INITIALISED with it
-  float omega;             // hidden omega
-  // coordinates (see CoordSrc)
-  const float* lin_h;
-  const float* lin_w;
-  const float* coords;
-  int width;
-  int row_begin;
-  long long* dbg;          // optional timeline capture (tools/fused_timeline.py); null in production
-};
-
-// timeline slots: dbg[((role * 4 + tile) * 8 + layer) * 16 + k], block 0 only, first 4 tiles
-#define SB_DBG(role, tile_i, layer, k)                                                        \
-  do {                                                                                        \
-    if (args.dbg && blockIdx.x == 0 && (tile_i) < 4)                                          \
-      args.dbg[(((role) * 4 + (tile_i)) * 8 + (layer)) * 16 + (k)] = clock64();               \
-  } while (0)
-
-template <int W>
-struct FusedFwdCfg {
-  static_assert(W == 256, "fused forward is instantiated for hidden = 256");
-  static constexpr int KB = W / 64;
-  static constexpr int SW = 3;  // weight ring depth
-  static constexpr uint32_t A_BUF = 128 * W * 2;      // 64 KiB
-  static constexpr uint32_t W_STAGE = W * 128;        // 32 KiB: [W rows x 64 K]
-  static constexpr uint32_t OFF_A = 0;
-  static constexpr uint32_t OFF_W = 2 * A_BUF;
-  static constexpr uint32_t OFF_BAR = OFF_W + SW * W_STAGE;
-  // w_full/empty[SW], chunk_done[2][KB], region_free[2][KB], acc_full[2], acc_empty[2]
-  static constexpr int NUM_BARS = 2 * SW + 4 * KB + 4;
-  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
-  static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr int THREADS = 640;  // warp 0 W-TMA, warp 1 MMA, warp 2 stash stores, warps 4-19 epilogue
-  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
-};
-
-// Epilogue warp layout: warps 4..19; quadrant q = warp & 3 owns TMEM lanes / tile rows [32q, 32q+32),
-// chunk c = (warp-4)>>2 is the 64-column slice this warp produces in every layer.  All four chunks of a
-// layer are produced concurrently (4 epilogue warps per SM sub-partition hide MUFU / TMEM latency) and
-// no block-wide barrier is needed: each warp arrives on chunk_done[buf][c] (count 4), which the MMA
-// issuer and the store thread wait on.
-template <int W>
-__global__ void __launch_bounds__(640, 1)
-fused_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmAct,
-                 const FusedFwdArgs args, const uint32_t idesc) {
-  using C = FusedFwdCfg<W>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* w_full = bars;
-  uint64_t* w_empty = w_full + C::SW;
-  uint64_t* chunk_done = w_empty + C::SW;          // [2][KB], 4 arrivals (one per quadrant warp)
-  uint64_t* region_free = chunk_done + 2 * C::KB;  // [2][KB], 1 arrival (store thread)
-  uint64_t* acc_full = region_free + 2 * C::KB;    // [2]
-  uint64_t* acc_empty = acc_full + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < C::SW; ++i) {
-      mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
-    }
-    for (int i = 0; i < 2 * C::KB; ++i) {
-      mbar_init(&chunk_done[i], 4);
-      mbar_init(&region_free[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 16);
-    }
-    fence_barrier_init();
-    tma_prefetch_desc(&tmW);
-    tma_prefetch_desc(&tmAct);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int nh = args.nh;
-
-  if (warp == 0) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t iw = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x)
-        for (int l = 1; l <= nh; ++l)
-          for (int kb = 0; kb < C::KB; ++kb, ++iw) {
-            const uint32_t s = iw % C::SW, ph = (iw / C::SW) & 1u;
-            mbar_wait(&w_empty[s], ph ^ 1u);
-            mbar_expect_tx(&w_full[s], C::W_STAGE);
-            tma_load_2d(smem + C::OFF_W + s * C::W_STAGE, &tmW, &w_full[s], kb * 64, (l - 1) * W);
-          }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t iw = 0;
-      uint32_t use_acc0 = 0, use_acc1 = 0;  // completed uses of each accumulator
-      uint32_t use_buf0 = 0, use_buf1 = 0;  // write phases of each activation buffer accounted for
-      int ti = -1;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
-        ++ti;
-        if (t != int(blockIdx.x)) {
-          // layer nh of the previous tile is not consumed by any MMA, but its chunk_done phases must
-          // still be observed: a parity wait may never run two phases ahead of the barrier
-          const uint32_t lb = nh & 1u;
-          const uint32_t ul = lb ? use_buf1 : use_buf0;
-          for (int kb = 0; kb < C::KB; ++kb) mbar_wait(&chunk_done[lb * C::KB + kb], ul & 1u);
-          if (lb) ++use_buf1; else ++use_buf0;
-        }
-        for (int l = 1; l <= nh; ++l) {
-          const uint32_t acc = l & 1u, src = (l - 1) & 1u;
-          const uint32_t ua = acc ? use_acc1 : use_acc0;
-          const uint32_t ub = src ? use_buf1 : use_buf0;
-          SB_DBG(0, ti, l, 0);
-          mbar_wait(&acc_empty[acc], ua & 1u);  // phase 0 = initial bias fill, then one per drain
-          SB_DBG(0, ti, l, 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * W;
-          for (int kb = 0; kb < C::KB; ++kb, ++iw) {
-            const uint32_t s = iw % C::SW, ph = (iw / C::SW) & 1u;
-            mbar_wait(&chunk_done[src * C::KB + kb], ub & 1u);
-            SB_DBG(0, ti, l, 2 + 2 * kb);
-            mbar_wait(&w_full[s], ph);
-            SB_DBG(0, ti, l, 3 + 2 * kb);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + C::OFF_A + src * C::A_BUF + kb * kChunkBytes);
-            const uint32_t b_addr = smem_u32(smem + C::OFF_W + s * C::W_STAGE);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = umma_smem_desc(a_addr + k * 32, 0, 1024, 2);
-              const uint64_t db = umma_smem_desc(b_addr + k * 32, 0, 1024, 2);
-              umma_f16(d_tmem, da, db, idesc, 1u);  // accumulator starts at the bias
-            }
-            umma_commit(&w_empty[s]);
-          }
-          umma_commit(&acc_full[acc]);
-          SB_DBG(0, ti, l, 10);
-          if (acc) ++use_acc1; else ++use_acc0;
-          if (src) ++use_buf1; else ++use_buf0;
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ===================== stash stores: activation chunk -> HBM, then free the region ==========
-    if (lane == 0) {
-      uint32_t use_buf0 = 0, use_buf1 = 0;
-      int pend_buf[2] = {-1, -1}, pend_c[2] = {0, 0};  // stores whose smem read may be in flight
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
-        const int tile_row = t * kRowsPerTile;
-        for (int l = 0; l <= nh; ++l) {
-          const uint32_t buf = l & 1u;
-          const uint32_t ub = buf ? use_buf1 : use_buf0;
-          for (int c = 0; c < C::KB; ++c) {
-            mbar_wait(&chunk_done[buf * C::KB + c], ub & 1u);
-            tma_store_2d(&tmAct, smem + C::OFF_A + buf * C::A_BUF + c * kChunkBytes, c * 64,
-                         int(l * args.npix_pad) + tile_row);
-            tma_store_commit();
-            // keep two stores in flight; the one issued two chunks ago has been read out of smem
-            tma_store_wait_read<2>();
-            if (pend_buf[0] >= 0) mbar_arrive(&region_free[pend_buf[0] * C::KB + pend_c[0]]);
-            pend_buf[0] = pend_buf[1];
-            pend_c[0] = pend_c[1];
-            pend_buf[1] = int(buf);
-            pend_c[1] = c;
-          }
-          if (buf) ++use_buf1; else ++use_buf0;
-        }
-      }
-      tma_store_wait_all<0>();
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;
-    const int c = (warp - 4) >> 2;  // this warp's 64-column chunk
-    const int r_in_tile = q * 32 + lane;
-    uint32_t use_acc0 = 0, use_acc1 = 0, use_buf0 = 0, use_buf1 = 0;
-    // Bias folding: every accumulator is pre-loaded with the bias of the layer that will use it next
-    // (each warp fills the lanes x columns it later drains), so the MMAs always accumulate and the
-    // epilogue needs no per-column constant.  Initial fill: acc 1 <- bias of layer 1, acc 0 <- layer 2.
-    auto fill_bias = [&](uint32_t acc_idx, int layer, int col0) {
-      uint32_t bv[32];
-      const float4* src = reinterpret_cast<const float4*>(args.bias_raw + (layer - 1) * W + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 f = __ldg(src + j);
-        bv[4 * j] = __float_as_uint(f.x);
-        bv[4 * j + 1] = __float_as_uint(f.y);
-        bv[4 * j + 2] = __float_as_uint(f.z);
-        bv[4 * j + 3] = __float_as_uint(f.w);
-      }
-      tmem_st_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc_idx * W + col0, bv);
-    };
-    for (int hb = 0; hb < 2; ++hb) {
-      fill_bias(1, 1, c * 64 + hb * 32);
-      if (nh >= 2) fill_bias(0, 2, c * 64 + hb * 32);
-    }
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {  // both accumulators are ready for their first use
-      mbar_arrive(&acc_empty[1]);
-      mbar_arrive(&acc_empty[0]);
-    }
-    const int role = (lane == 0 && q == 0 && (c == 0 || c == 3)) ? (c == 0 ? 1 : 2) : -1;
-    int ti = -1;
-    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
-      ++ti;
-      const int tile_row = t * kRowsPerTile;
-      float xh, xw;
-      {
-        int64_t p = int64_t(tile_row) + r_in_tile;
-        if (p >= args.npix) p = args.npix - 1;
-        float gh, gw;
-        if (args.coords) {
-          const float2 v = reinterpret_cast<const float2*>(args.coords)[p];
-          gh = v.x;
-          gw = v.y;
-        } else {
-          const unsigned pu = unsigned(p);
-          const int r = int(pu / unsigned(args.width));
-          const int col = int(pu - unsigned(r) * unsigned(args.width));
-          gh = __ldg(args.lin_h + args.row_begin + r);
-          gw = __ldg(args.lin_w + col);
-        }
-        xh = (gh - 0.5f) * 2.0f;
-        xw = (gw - 0.5f) * 2.0f;
-      }
-      for (int l = 0; l <= nh; ++l) {
-        const uint32_t buf = l & 1u, acc = l & 1u;
-        const uint32_t ub = buf ? use_buf1 : use_buf0;
-        if (role > 0) SB_DBG(role, ti, l, 0);
-        if (l > 0) {
-          mbar_wait(&acc_full[acc], (acc ? use_acc1 : use_acc0) & 1u);
-          tc_fence_after();
-        }
-        if (role > 0) SB_DBG(role, ti, l, 1);
-        // the previous occupant of this region (two layers back) must have been stored
-        mbar_wait(&region_free[buf * C::KB + c], (ub & 1u) ^ 1u);
-        if (role > 0) SB_DBG(role, ti, l, 2);
-        const uint32_t row_addr =
-            smem_u32(smem + C::OFF_A + buf * C::A_BUF) + c * kChunkBytes + r_in_tile * 128;
-        const int nxt = (l + 2 <= nh) ? l + 2 : ((l & 1) ? 1 : 2);  // next layer accumulating here
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          uint32_t o[16];
-          const int col0 = c * 64 + hb * 32;
-          if (l == 0) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float4 ta = __ldg(args.tab0 + col0 + 2 * j);
-              const float4 tb = __ldg(args.tab0 + col0 + 2 * j + 1);
-              const float t0 = fmaf(xh, ta.x, fmaf(xw, ta.y, ta.z));
-              const float t1 = fmaf(xh, tb.x, fmaf(xw, tb.y, tb.z));
-              o[j] = sine_signed_half2(t0, t1);
-            }
-          } else {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * W + col0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float t0 = __uint_as_float(v[2 * j]) * args.omega;
-              const float t1 = __uint_as_float(v[2 * j + 1]) * args.omega;
-              o[j] = sine_signed_half2(t0, t1);
-            }
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
-            st_shared_v4(row_addr + (chunk << 4), o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2],
-                         o[4 * c4 + 3]);
-          }
-          // refill the drained columns with the bias of the next layer that accumulates here
-          if (l > 0 && nxt <= nh) fill_bias(acc, nxt, col0);
-        }
-        if (role > 0) SB_DBG(role, ti, l, 3);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&chunk_done[buf * C::KB + c]);
-        if (role > 0) SB_DBG(role, ti, l, 4);
-        if (l > 0) {
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[acc]);
-          if (acc) ++use_acc1; else ++use_acc0;
-        }
-        if (buf) ++use_buf1; else ++use_buf0;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// fused backward step of one hidden layer l (hidden = 256):
-//     dz[l-1] = (dz[l] . omega W_l) (*) +-sqrt(1 - act[l-1]^2)          (the dX GEMM + cos epilogue)
-//     dW_l   += dz[l]^T . act[l-1],   db_l += sum_p dz[l]                (the pixel reduction)
-// from ONE pass over dz[l] and act[l-1]: the separate split-K pass (which re-reads both tensors,
-// 402 MB per layer at config 2) disappears.
-//
-// Work is split by FEATURE HALF, not only by pixels: CTA b handles half h = b & 1 of the features for the
-// 128-pixel tiles t = b/2, b/2 + grid/2, ...: it computes the 128 output columns [128h, 128h+128) of
-// dz[l-1] (UMMA M=128 px, N=128, K=256) and the 128 rows [128h, ..) of dW_l (UMMA M=128, N=256, K=128 px),
-// whose accumulator (256 TMEM columns) stays resident for the whole kernel.  CTAs 2j and 2j+1 load the
-// same two tiles at the same time, so the second read is served by L2.
-//   smem : omega W_l^T half (64 KiB, resident) | dz tile (4 chunks) | act tile (4 chunks) | 2 output chunks
-//   TMEM : dX accumulator 128 cols | dW accumulator 256 cols | db accumulator 16 cols
-// ------------------------------------------------------------------------------------------
-struct BwdArgs {
-  int num_tiles;       // 128-pixel tiles
-  int dz_row0;         // first row of dz[l] inside the dz tensor map
-  int act_row0;        // first row of act[l-1] inside the activation tensor map
-  int out_row0;        // first row of dz[l-1] inside the dz tensor map
-  int valid_rows;      // pixel rows >= valid_rows are written as zero
-  float* dw_partial;   // [pairs][prob_total][256][256] fp32 (slab = pair * prob_total + prob)
-  float* db_partial;   // [pairs][prob_total][256]
-  int prob;            // index of this layer inside the partial slabs
-  int prob_total;
-};
-
-struct BwdCfg {
-  static constexpr int W = 256;
-  static constexpr uint32_t OFF_B = 0;                       // 4 k-blocks of [128 x 64] = 64 KiB
-  static constexpr uint32_t OFF_D = 65536;                   // dz tile: 4 chunks
-  static constexpr uint32_t OFF_E = OFF_D + 4 * kChunkBytes; // act tile: 4 chunks
-  static constexpr uint32_t OFF_O = OFF_E + 4 * kChunkBytes; // output staging: 2 chunks
-  static constexpr uint32_t OFF_ONES = OFF_O + 2 * kChunkBytes;
-  static constexpr uint32_t OFF_BAR = OFF_ONES + 512;
-  static constexpr int NUM_BARS = 8;
-  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
-  static constexpr uint32_t TMEM_COLS = 512;
-  static constexpr uint32_t TM_DX = 0, TM_DW = 128, TM_DB = 384;
-  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
-};
-
-__global__ void __launch_bounds__(256, 1)
-bwd_layer_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmAct,
-                 const __grid_constant__ CUtensorMap tmWt, const BwdArgs args, const uint32_t idesc_dx,
-                 const uint32_t idesc_dw, const uint32_t idesc_ones) {
-  using C = BwdCfg;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* b_full = bars + 0;    // resident weights landed
-  uint64_t* in_full = bars + 1;   // dz + act tiles landed (128 KiB)
-  uint64_t* in_empty = bars + 2;  // 2 arrivals: all MMAs of the item retired + epilogue done with act
-  uint64_t* dx_full = bars + 3;   // dX accumulator complete
-  uint64_t* dx_empty = bars + 4;  // dX accumulator drained (4 epilogue warps)
-  uint64_t* dw_done = bars + 5;   // final: dW/db accumulators complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int h = blockIdx.x & 1;          // feature half of this CTA
-  const int pair = blockIdx.x >> 1;
-  const int npairs = gridDim.x >> 1;
-
-  if (threadIdx.x == 0) {
-    mbar_init(b_full, 1);
-    mbar_init(in_full, 1);
-    mbar_init(in_empty, 2);
-    mbar_init(dx_full, 1);
-    mbar_init(dx_empty, 4);
-    mbar_init(dw_done, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&tmDz);
-    tma_prefetch_desc(&tmAct);
-    tma_prefetch_desc(&tmWt);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  if (warp >= 4) {
-    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + C::OFF_ONES);
-    for (int i = threadIdx.x - 128; i < 128; i += 128) ones[i] = 0x3C003C00u;
-    fence_proxy_async_smem();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(b_full, 4 * kChunkBytes);
-      for (int kb = 0; kb < 4; ++kb)  // rows [128h, 128h+128) of omega W_l^T, k-block kb
-        tma_load_2d(smem + C::OFF_B + kb * kChunkBytes, &tmWt, b_full, kb * 64, h * 128);
-      uint32_t it = 0;
-      for (int t = pair; t < args.num_tiles; t += npairs, ++it) {
-        mbar_wait(in_empty, (it & 1u) ^ 1u);
-        mbar_expect_tx(in_full, 8 * kChunkBytes);
-        const int prow = t * kRowsPerTile;
-        for (int c = 0; c < 4; ++c)
-          tma_load_2d(smem + C::OFF_D + c * kChunkBytes, &tmDz, in_full, c * 64, args.dz_row0 + prow);
-        for (int c = 0; c < 4; ++c)
-          tma_load_2d(smem + C::OFF_E + c * kChunkBytes, &tmAct, in_full, c * 64,
-                      args.act_row0 + prow);
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      mbar_wait(b_full, 0);
-      const uint32_t b_addr = smem_u32(smem + C::OFF_B);
-      const uint32_t d_addr = smem_u32(smem + C::OFF_D);
-      const uint32_t e_addr = smem_u32(smem + C::OFF_E);
-      const uint64_t d_ones = umma_smem_desc(smem_u32(smem + C::OFF_ONES), 128, 256, 0);
-      uint32_t it = 0;
-      for (int t = pair; t < args.num_tiles; t += npairs, ++it) {
-        mbar_wait(in_full, it & 1u);
-        mbar_wait(dx_empty, (it & 1u) ^ 1u);
-        tc_fence_after();
-        // dX half: [128 px x 128] = dz tile (K-major, 4 k-blocks) x W^T half
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc(d_addr + kb * kChunkBytes + k * 32, 0, 1024, 2);
-            const uint64_t db = umma_smem_desc(b_addr + kb * kChunkBytes + k * 32, 0, 1024, 2);
-            umma_f16(tmem_base + C::TM_DX, da, db, idesc_dx, (kb | k) != 0 ? 1u : 0u);
-          }
-        umma_commit(dx_full);
-        // dW half / db half: A = dz columns [128h, 128h+128) read MN-major (chunks 2h, 2h+1),
-        // B = act tile read MN-major (4 chunks); K = the tile's 128 pixels in 8 steps of 16
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t dx =
-              umma_smem_desc(d_addr + 2 * h * kChunkBytes + k * 2048, kChunkBytes, 1024, 2);
-          const uint64_t dy = umma_smem_desc(e_addr + k * 2048, kChunkBytes, 1024, 2);
-          const uint32_t accum = (it | uint32_t(k)) != 0 ? 1u : 0u;
-          umma_f16(tmem_base + C::TM_DW, dx, dy, idesc_dw, accum);
-          umma_f16(tmem_base + C::TM_DB, dx, d_ones, idesc_ones, accum);
-        }
-        umma_commit(in_empty);  // every MMA that reads the tile buffers has retired
-      }
-      umma_commit(dw_done);
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;
-    const int r_in_tile = q * 32 + lane;
-    const bool issuer = (threadIdx.x == 128);
-    uint32_t it = 0;
-    for (int t = pair; t < args.num_tiles; t += npairs, ++it) {
-      mbar_wait(in_full, it & 1u);  // the act chunks read below were written by TMA
-      mbar_wait(dx_full, it & 1u);
-      tc_fence_after();
-      const bool row_valid = (t * kRowsPerTile + r_in_tile) < args.valid_rows;
-      // the previous item's two output chunks must have been read by their TMA stores
-      if (issuer) tma_store_wait_read<0>();
-      named_bar_sync(1, 128);
-#pragma unroll
-      for (int nb = 0; nb < 2; ++nb) {
-        const uint32_t e_row =
-            smem_u32(smem + C::OFF_E + (2 * h + nb) * kChunkBytes) + r_in_tile * 128;
-        const uint32_t o_row = smem_u32(smem + C::OFF_O + nb * kChunkBytes) + r_in_tile * 128;
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DX + nb * 64 + hb * 32, v);
-          uint32_t e[16];
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
-            const uint4 ld = ld_shared_v4(e_row + (chunk << 4));
-            e[4 * c4 + 0] = ld.x;
-            e[4 * c4 + 1] = ld.y;
-            e[4 * c4 + 2] = ld.z;
-            e[4 * c4 + 3] = ld.w;
-          }
-          tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float g0 = __uint_as_float(v[2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
-            float g1 = __uint_as_float(v[2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
-            if (!row_valid) g0 = g1 = 0.0f;
-            o[j] = pack_f16x2(g0, g1);
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
-            st_shared_v4(o_row + (chunk << 4), o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
-          }
-        }
-      }
-      // accumulator drained and act chunks read: release both
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dx_empty);
-      named_bar_sync(1, 128);
-      if (issuer) {
-        mbar_arrive(in_empty);
-        for (int nb = 0; nb < 2; ++nb)
-          tma_store_2d(&tmDz, smem + C::OFF_O + nb * kChunkBytes, h * 128 + nb * 64,
-                       args.out_row0 + t * kRowsPerTile);
-        tma_store_commit();
-      }
-    }
-    if (issuer) tma_store_wait_all<0>();
-    // ---- final: this CTA's half of dW_l and db_l -> partial slab of its pair ----
-    const int m = h * 128 + r_in_tile;  // dW row (output feature of layer l)
-    const size_t slab = size_t(pair) * args.prob_total + args.prob;
-    float* dw = args.dw_partial + (slab * 256 + m) * size_t(256);
-    float* dbp = args.db_partial + slab * 256 + m;
-    if (pair < args.num_tiles) {
-      mbar_wait(dw_done, 0);
-      tc_fence_after();
-      for (int cb = 0; cb < 8; ++cb) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DW + cb * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<uint4*>(dw + cb * 32)[j] =
-              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      uint32_t b8[8];
-      tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + C::TM_DB, b8);
-      tmem_ld_wait();
-      *dbp = __uint_as_float(b8[0]);
-    } else {
-      for (int j = 0; j < 64; ++j) reinterpret_cast<uint4*>(dw)[j] = make_uint4(0, 0, 0, 0);
-      *dbp = 0.0f;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // last layer on tensor cores (hidden <= 256, out <= 4): per 128-pixel tile, from ONE read of act[D-2]:
 //   y  = act . W_last^T (+ b)            UMMA M=128 px, N=16, K=W       -> pred, squared error, seed g
 //   dA = g . (omega W_last)              UMMA M=128 px, N=W,  K=16      -> dz[D-2] = dA (*) +-sqrt(1-a^2)
@@ -2207,286 +1636,6 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
         for (int c = 0; c < args.C; ++c) out[c * W + mb * 128 + r_in_tile] = __uint_as_float(dv[c]);
       }
     }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// forward pair kernel (hidden 128 / 256): TWO consecutive hidden layers per 128-pixel tile,
-//   T   = sin(w (A . W_a^T + b_a))   -> signed-half tile in shared memory, TMA-stored to the stash
-//   out = sin(w (T . W_b^T + b_b))   -> TMA-stored to the stash
-// so the intermediate activation is written once and never read back by the forward pass.  Operands are
-// streamed as in the tail kernel ({A k-block, W_a k-block} then {W_b k-block} stages from L2); the
-// second GEMM reads its A operand straight from T.  16 epilogue warps, next chunk's tcgen05.ld in flight.
-// (reference: SineLayer.forward x 2, implicit_image/models/siren.py:56-68)
-// ------------------------------------------------------------------------------------------
-struct FwdPairArgs {
-  int num_tiles;
-  int a_row0;          // rows of the input activation inside the activation tensor map
-  int t_row0;          // rows of the first layer's output (stash)
-  int o_row0;          // rows of the second layer's output (stash)
-  float omega_a, omega_b;
-  const float* bias_a;
-  const float* bias_b;
-  long long* dbg;      // optional timeline (block 0): dbg[tile * 16 + k], first 12 tiles
-};
-
-template <int W>
-struct FwdPairCfg {
-  static_assert(W == 128 || W == 256, "forward pair kernel: hidden 128 or 256");
-  static constexpr int NCH = W / 64;
-  static constexpr int CPH = NCH / 2;
-  static constexpr int S = 3;  // ring depth: the second GEMM sits on the epilogues' critical path, so the L2
-                               // latency of its weight k-blocks must be covered by stages in flight
-  static constexpr uint32_t B_KB_BYTES = W * 128;
-  static constexpr uint32_t STAGE_BYTES = kChunkBytes + B_KB_BYTES;
-  static constexpr uint32_t OFF_T = 0;
-  static constexpr uint32_t OFF_ST = NCH * kChunkBytes;
-  static constexpr uint32_t OFF_CONST = OFF_ST + S * STAGE_BYTES;  // omega*bias of both layers
-  static constexpr uint32_t OFF_BAR = OFF_CONST + 2 * W * 4;
-  static constexpr int NUM_BARS = 2 * S + 6;
-  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
-  static constexpr uint32_t TM_ACC1 = 0, TM_ACC2 = W;
-  static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * W);
-  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
-};
-
-template <int W>
-__global__ void __launch_bounds__(640, 1)
-fwd_pair_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmWa,
-                const __grid_constant__ CUtensorMap tmWb, const FwdPairArgs args) {
-  using C = FwdPairCfg<W>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* st_full = bars;
-  uint64_t* st_empty = st_full + C::S;
-  uint64_t* acc1_full = st_empty + C::S;
-  uint64_t* acc1_free = acc1_full + 1;  // epilogue 1 drained accumulator 1 (16 warps)
-  uint64_t* t_ready = acc1_free + 1;    // [2] half of T written and fenced (16 warps each)
-  uint64_t* acc2_full = t_ready + 2;    // second GEMM retired (it has also finished reading T)
-  uint64_t* acc2_free = acc2_full + 1;  // epilogue 2 drained accumulator 2 (16 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < C::S; ++i) {
-      mbar_init(&st_full[i], 1);
-      mbar_init(&st_empty[i], 1);
-    }
-    mbar_init(acc1_full, 1);
-    mbar_init(acc1_free, 16);
-    mbar_init(&t_ready[0], 16);
-    mbar_init(&t_ready[1], 16);
-    mbar_init(acc2_full, 1);
-    mbar_init(acc2_free, 16);
-    fence_barrier_init();
-    tma_prefetch_desc(&tmAct);
-    tma_prefetch_desc(&tmWa);
-    tma_prefetch_desc(&tmWb);
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
-  }
-  if (warp >= 4) {
-    float* cst = reinterpret_cast<float*>(smem + C::OFF_CONST);
-    for (int i = threadIdx.x - 128; i < W; i += 512) {
-      cst[i] = args.omega_a * args.bias_a[i];
-      cst[W + i] = args.omega_b * args.bias_b[i];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp == 0) {
-    // ===================== producer: per tile {A, W_a} x NCH then {W_b} x NCH =====================
-    if (lane == 0) {
-      uint32_t ia = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
-        for (int kb = 0; kb < 2 * C::NCH; ++kb, ++ia) {
-          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
-          mbar_wait(&st_empty[s], ph ^ 1u);
-          uint8_t* stage = smem + C::OFF_ST + s * C::STAGE_BYTES;
-          if (kb < C::NCH) {
-            mbar_expect_tx(&st_full[s], C::STAGE_BYTES);
-            tma_load_2d(stage, &tmAct, &st_full[s], kb * 64, args.a_row0 + t * kRowsPerTile);
-            tma_load_2d(stage + kChunkBytes, &tmWa, &st_full[s], kb * 64, 0);
-          } else {
-            mbar_expect_tx(&st_full[s], C::B_KB_BYTES);
-            tma_load_2d(stage + kChunkBytes, &tmWb, &st_full[s], (kb - C::NCH) * 64, 0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, W, 0, 0, 0, 0);
-      const uint32_t t_addr = smem_u32(smem + C::OFF_T);
-      uint32_t ia = 0, it = 0;
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
-        // GEMM 1 (accumulator 1 was drained by epilogue 1 of the previous tile)
-        mbar_wait(acc1_free, (it & 1u) ^ 1u);
-        tc_fence_after();
-        for (int kb = 0; kb < C::NCH; ++kb, ++ia) {
-          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
-          mbar_wait(&st_full[s], ph);
-          if (kb == 0) SB_DBG_T(it, 5);
-          if (kb == 2) SB_DBG_T(it, 9);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + C::OFF_ST + s * C::STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + C::TM_ACC1, umma_smem_desc(a_addr + k * 32, 0, 1024, 2),
-                     umma_smem_desc(a_addr + kChunkBytes + k * 32, 0, 1024, 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&st_empty[s]);
-        }
-        umma_commit(acc1_full);
-        SB_DBG_T(it, 6);
-        // GEMM 2: A = T, half by half as epilogue 1 hands it over
-        mbar_wait(acc2_free, (it & 1u) ^ 1u);
-        for (int kb = 0; kb < C::NCH; ++kb, ++ia) {
-          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
-          if (kb % C::CPH == 0) mbar_wait(&t_ready[kb / C::CPH], it & 1u);
-          mbar_wait(&st_full[s], ph);
-          if (kb == 0) SB_DBG_T(it, 7);
-          if (kb == 2) SB_DBG_T(it, 10);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(smem + C::OFF_ST + s * C::STAGE_BYTES) + kChunkBytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + C::TM_ACC2, umma_smem_desc(t_addr + kb * kChunkBytes + k * 32, 0, 1024, 2),
-                     umma_smem_desc(b_addr + k * 32, 0, 1024, 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&st_empty[s]);
-        }
-        umma_commit(acc2_full);
-        SB_DBG_T(it, 8);
-      }
-    }
-  } else if (warp >= 4) {
-    // ===================== epilogues (16 warps) =====================
-    const int q = warp & 3;
-    const int hb = (warp - 4) >> 2;  // 0..3: 16 of the 64 columns of a chunk
-    const int r_in_tile = q * 32 + lane;
-    const bool issuer = (threadIdx.x == 128);
-    const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
-    const uint32_t t_addr = smem_u32(smem + C::OFF_T);
-    const uint32_t lane_tm = uint32_t(q * 32) << 16;
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
-      // ---- epilogue 1: accumulator 1 -> sin -> T (+ stash store, half by half) ----
-      if (issuer) SB_DBG_T(it, 0);
-      mbar_wait(acc1_full, it & 1u);
-      if (issuer) SB_DBG_T(it, 1);
-      tc_fence_after();
-      {
-        uint32_t v[2][16];
-        tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC1 + hb * 16, v[0]);
-#pragma unroll
-        for (int nb = 0; nb < C::NCH; ++nb) {
-          if (it > 0 && nb % C::CPH == 0) {
-            // a half of T may be overwritten once the previous tile's output stores out of it (epilogue 2
-            // writes in place, one bulk group per chunk) have been read; the second GEMM that read T has
-            // retired (this warp waited for acc2_full in the previous epilogue 2)
-            if (issuer) {
-              if (nb == 0) tma_store_wait_read<C::CPH>(); else tma_store_wait_read<0>();
-            }
-            named_bar_sync(1, 512);
-          }
-          tmem_ld_wait();
-          if (nb + 1 < C::NCH)
-            tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC1 + (nb + 1) * 64 + hb * 16, v[(nb + 1) & 1]);
-          uint32_t o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = nb * 64 + hb * 16 + 2 * j;
-            const float t0 = fmaf(__uint_as_float(v[nb & 1][2 * j]), args.omega_a, cst[col]);
-            const float t1 = fmaf(__uint_as_float(v[nb & 1][2 * j + 1]), args.omega_a, cst[col + 1]);
-            o[j] = sine_signed_half2(t0, t1);
-          }
-          const uint32_t row_addr = t_addr + nb * kChunkBytes + r_in_tile * 128;
-#pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            const uint32_t chunk = uint32_t(hb * 2 + c2) ^ uint32_t(r_in_tile & 7);
-            st_shared_v4(row_addr + (chunk << 4), o[4 * c2], o[4 * c2 + 1], o[4 * c2 + 2], o[4 * c2 + 3]);
-          }
-          if (nb % C::CPH == C::CPH - 1) {
-            const int half = nb / C::CPH;
-            fence_proxy_async_smem();
-            if (nb == C::NCH - 1) tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (nb == C::NCH - 1) mbar_arrive(acc1_free);
-              mbar_arrive(&t_ready[half]);
-            }
-            named_bar_sync(1, 512);  // the whole half is in T: stash it
-            if (issuer) {
-              for (int c = half * C::CPH; c < (half + 1) * C::CPH; ++c)
-                tma_store_2d(&tmAct, smem + C::OFF_T + c * kChunkBytes, c * 64, args.t_row0 + t * kRowsPerTile);
-              tma_store_commit();
-            }
-          }
-        }
-      }
-      // ---- epilogue 2: accumulator 2 -> sin -> T in place (the second GEMM has finished reading it) ->
-      // stash store, chunk by chunk ----
-      if (issuer) SB_DBG_T(it, 2);
-      mbar_wait(acc2_full, it & 1u);
-      if (issuer) SB_DBG_T(it, 3);
-      tc_fence_after();
-      if (issuer) tma_store_wait_read<0>();  // the stash stores of T issued in epilogue 1 have read it
-      named_bar_sync(1, 512);
-      {
-        uint32_t v[2][16];
-        tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC2 + hb * 16, v[0]);
-#pragma unroll
-        for (int nb = 0; nb < C::NCH; ++nb) {
-          tmem_ld_wait();
-          if (nb + 1 < C::NCH)
-            tmem_ld_32x16(tmem_base + lane_tm + C::TM_ACC2 + (nb + 1) * 64 + hb * 16, v[(nb + 1) & 1]);
-          if (nb == C::NCH - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc2_free);
-          }
-          uint32_t o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = nb * 64 + hb * 16 + 2 * j;
-            const float t0 = fmaf(__uint_as_float(v[nb & 1][2 * j]), args.omega_b, cst[W + col]);
-            const float t1 = fmaf(__uint_as_float(v[nb & 1][2 * j + 1]), args.omega_b, cst[W + col + 1]);
-            o[j] = sine_signed_half2(t0, t1);
-          }
-          const uint32_t row_addr = t_addr + nb * kChunkBytes + r_in_tile * 128;
-#pragma unroll
-          for (int c2 = 0; c2 < 2; ++c2) {
-            const uint32_t chunk = uint32_t(hb * 2 + c2) ^ uint32_t(r_in_tile & 7);
-            st_shared_v4(row_addr + (chunk << 4), o[4 * c2], o[4 * c2 + 1], o[4 * c2 + 2], o[4 * c2 + 3]);
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 512);
-          if (issuer) {
-            tma_store_2d(&tmAct, smem + C::OFF_T + nb * kChunkBytes, nb * 64, args.o_row0 + t * kRowsPerTile);
-            tma_store_commit();
-            if (nb == C::NCH - 1) SB_DBG_T(it, 4);
-          }
-        }
-      }
-    }
-    if (issuer) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
