@@ -55,8 +55,11 @@ def main(cfg, fast=True):
             out.update(loss=loss, PSNR=psnr, PSNR_8bit=psnr8)
             logging.info(f"Train | Step: {done} | loss: {loss:.6f} | PSNR: {psnr:.4f} | PSNR_8bit: {psnr8:.4f}")
     else:
+        # the reference's loop verbatim (compress.py:131-143), GradScaler included: fp32 arithmetic, the scaler
+        # only adds its skip-on-overflow behaviour (autocast is never entered)
+        scaler = torch.amp.GradScaler("cuda") if (cfg.train.get("mixed_precision") and device.type == "cuda") else None
         for i in range(num_steps):
-            train_epoch(model, optim, grid, img, lr_scheduler=lr_scheduler, mask=mask)
+            train_epoch(model, optim, grid, img, lr_scheduler=lr_scheduler, mask=mask, scaler=scaler)
             if mask and i <= masking_cfg["end_when"] and i % masking_cfg["interval"] == 0:
                 mask.update_connections()
             if (i + 1) % cfg.train.log_steps == 0:
@@ -69,14 +72,33 @@ def main(cfg, fast=True):
         quantized_model = deepcopy(model)
         optim_q, sched_q = get_optimizer_lr_scheduler(quantized_model, cfg.optim, quantize_mode=True)
         quantized_model.train()
+        # Reference quirk App. A.2 (compress.py:186-188 + train_helper.py:166-168): with a mask present the
+        # reference passes the ORIGINAL model's Masking into the quant loop, so `mask.step()` steps the old
+        # optimizer on the original model with its stale gradients and the quantised copy only changes through
+        # re-clustering.  quant.replicate_reference_mask_bug=true reproduces exactly that (for a "Quant PSNR"
+        # comparable with the reference); the default fine-tunes the quantised copy with the final masks
+        # FROZEN on it, so pruned weights stay exactly zero and k-means keeps excluding them.
+        replicate = bool(mask) and bool(dict(cfg.quant).get("replicate_reference_mask_bug", False))
+        if mask and not replicate:
+            q_params = dict(quantized_model.named_parameters())
+            optim_q.fused_masks = {q_params[n]: mask.mask_dict[n].clone() for n, _ in mask._masked_parameters()}
         with quant_context.Quantize(quantized_model, optim_q, cfg.quant) as q:
             for i in range(cfg.quant.num_steps):
-                # the reference passes the ORIGINAL model's mask here (App. A.2), which steps the old
-                # optimizer; the fixed behaviour (fine-tune the quantised copy) is what runs here.
-                train_epoch(quantized_model, optim_q, grid, img, lr_scheduler=sched_q)
+                if replicate:
+                    train_epoch(quantized_model, optim_q, grid, img, lr_scheduler=sched_q, mask=mask)
+                else:
+                    train_epoch(quantized_model, optim_q, grid, img, lr_scheduler=sched_q)
         quantized_model = q.convert()
         _, loss, psnr, psnr8 = eval_epoch(quantized_model, grid, img)
         out.update({"Quant loss": loss, "Quant PSNR": psnr, "Quant PSNR 8bit": psnr8})
+        if mask:
+            nz = tot = 0
+            q_params = dict(quantized_model.named_parameters())
+            for n, _ in mask._masked_parameters():
+                nz += int((q_params[n] != 0).sum())
+                tot += q_params[n].numel()
+            out["Quant Density"] = nz / max(tot, 1)  # measured on the quantised weights, not the mask
+            out["quant_replicates_reference_mask_bug"] = replicate
     return out
 
 

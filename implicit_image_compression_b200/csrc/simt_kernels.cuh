@@ -1194,7 +1194,7 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
 }
 __global__ void __launch_bounds__(kCommThreads) p2p_allreduce_kernel(const CommPeers cp, uint32_t* epoch_b, float* io,
                                                             int64_t n, int64_t max_floats, int rank,
-                                                            int world) {
+                                                            int world, uint64_t timeout_ns) {
   const int b = blockIdx.x;
   const uint32_t epoch = epoch_b[b] + 1u;
   const uint32_t par = epoch & 1u;
@@ -1212,12 +1212,23 @@ __global__ void __launch_bounds__(kCommThreads) p2p_allreduce_kernel(const CommP
     __threadfence_system();
     st_release_sys(cp.sig[r] + slot + rank, epoch);
     const uint32_t* flag = cp.sig[rank] + slot + r;
-    uint32_t spins = 0;
+    // Wait with exponential back-off; the bound is wall-clock (globaltimer) and generous — a rank may be late
+    // by seconds for legitimate reasons (rank-0-only evaluation or logging, first-use graph capture) — and
+    // SIRENB200_EXCHANGE_TIMEOUT_S=0 disables it.
+    uint32_t ns = 32;
+    uint64_t t_start = 0;
     while (ld_acquire_sys(flag) != epoch) {
-      if (++spins > (1u << 26)) {  // seconds: a peer died or never launched; fail loudly instead of hanging
-        printf("sirenb200: gradient exchange timeout: rank %d block %d waiting for rank %d epoch %u\n", rank, b, r,
-               epoch);
-        __trap();
+      __nanosleep(ns);
+      if (ns < 4096) ns <<= 1;
+      if (timeout_ns != 0) {
+        uint64_t now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t_start == 0) t_start = now;
+        if (now - t_start > timeout_ns) {
+          printf("sirenb200: gradient exchange timeout: rank %d block %d waiting for rank %d epoch %u\n", rank, b, r,
+                 epoch);
+          __trap();
+        }
       }
     }
   }

@@ -1305,6 +1305,17 @@ int sirenb200_kmeans_quantize(const float* w, int64_t n, int32_t bits, int32_t i
 // ---------------------------------------------------------------------------------------
 }  // extern "C" (the comm struct is C++)
 
+// Wall-clock bound of a rank's wait for its peers inside the exchange kernel: SIRENB200_EXCHANGE_TIMEOUT_S
+// (default 120 s; 0 = wait forever).
+static uint64_t exchange_timeout_ns() {
+  static const uint64_t v = [] {
+    const char* env = getenv("SIRENB200_EXCHANGE_TIMEOUT_S");
+    const double s = env ? atof(env) : 120.0;
+    return s <= 0.0 ? uint64_t(0) : uint64_t(s * 1e9);
+  }();
+  return v;
+}
+
 struct sirenb200_comm {
   int rank = 0, world = 1, device = 0;
   int64_t max_floats = 0;
@@ -1386,7 +1397,7 @@ int sirenb200_comm_allreduce(sirenb200_comm_t c, float* data, int64_t n, sirenb2
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   p2p_allreduce_kernel<<<kCommBlocks, kCommThreads, 0, st>>>(c->peers, c->epoch_b, data, n, c->max_floats, c->rank,
-                                                    c->world);
+                                                    c->world, exchange_timeout_ns());
   LAUNCH_CHECK();
   return 0;
 }

@@ -139,7 +139,7 @@ class Fitter:
         self._g = {
             "state": shared["state"], "ring": shared["ring"], "host_loss": shared["host_loss"],
             "n": n, "p": _lib.ptr_array([p.data for p in params]),
-            "g": _lib.ptr_array([p.grad for p in params]),
+            "g": _lib.ptr_array(self._grad_views(params)),
             "m": _lib.ptr_array([opt.state[p]["exp_avg"] for p in params]),
             "v": _lib.ptr_array([opt.state[p]["exp_avg_sq"] for p in params]),
             "mask": masks, "mask_bufs": mask_bufs,
@@ -150,6 +150,17 @@ class Fitter:
         # one eager run of the body (a real step) initialises everything lazily created, then capture
         self._graph = None
         self._graph_key = key
+
+    def _grad_views(self, params):
+        """The gradient tensors the captured step WRITES (this Fitter's flat views), in `params` order — not
+        `p.grad`, which another Fitter on the same model may have rebound since."""
+        by_param = {id(p): v for p, v in zip(self.flat.params, self.flat.views)}
+        return [by_param[id(p)] for p in params]
+
+    def _attach(self):
+        flat = self.flat
+        if any(p.grad is not v for p, v in zip(flat.params, flat.views)):
+            flat.attach()
 
     def _sync_sched_state(self):
         group = self.optim.param_groups[0]
@@ -237,6 +248,7 @@ class Fitter:
             return None
         if not self.model.training:
             self.model.train()
+        self._attach()
         value = self._graph_steps(1, None, 0)
         self.step_index += 1
         return value
@@ -249,6 +261,7 @@ class Fitter:
             raise _lib.SirenB200Error("native_steps needs a graph-eligible (dense / dense-gradient) fit")
         if not self.model.training:
             self.model.train()
+        self._attach()
         self._prepare_graph()
         g = self._g
         if self.mask is not None:
@@ -288,6 +301,7 @@ class Fitter:
         """Run k fit steps; returns a device tensor [k] with each step's (pre-update) loss."""
         if not self.model.training:
             self.model.train()
+        self._attach()
         losses = torch.empty(k, dtype=torch.float32, device=self.img.device)
         done = 0
         while done < k:

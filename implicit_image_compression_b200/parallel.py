@@ -65,14 +65,8 @@ class FlatGrads:
         world = dist.get_world_size(group)
         if world < 2 or world > 8 or os.environ.get("SIRENB200_PEER_EXCHANGE", "1") == "0":
             return False
-        comm, ok = None, 1
-        try:
-            comm = PeerExchange(self.flat.numel(), group)
-        except _lib.SirenB200Error:
-            ok = 0
-        flag = torch.tensor([ok], device=self.flat.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        if int(flag.item()) == 1:
+        comm = PeerExchange.create(self.flat.numel(), group, self.flat.device)
+        if comm is not None:
             self.comm = comm
             return True
         return False
@@ -83,27 +77,52 @@ class PeerExchange:
     through torch.distributed (any transport would do), and from then on one kernel per step sums the flat
     gradient buffer over NVLink (include/siren_b200.h)."""
 
-    def __init__(self, max_floats, group=None):
+    def __init__(self, lib, handle, rank, world):
+        self.lib, self.handle, self.rank, self.world = lib, handle, rank, world
+
+    @classmethod
+    def create(cls, max_floats, group=None, device=None):
+        """Collective constructor: EVERY rank runs the same sequence of collectives whatever fails locally
+        (create -> MIN(ok) -> all_gather(handles) -> connect -> MIN(ok)); on any rank's failure all ranks
+        destroy what they built and return None (the caller keeps torch.distributed)."""
         dist = torch.distributed
-        self.lib = _lib.load()
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.handle = ctypes.c_void_p()
-        _lib.check(self.lib.sirenb200_comm_create(self.rank, self.world, int(max_floats),
-                                                  ctypes.byref(self.handle)))
+        lib = _lib.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+
+        def all_ok(ok):
+            flag = torch.tensor([1 if ok else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag.item()) == 1
+
+        handle = ctypes.c_void_p()
         mine = ctypes.create_string_buffer(64)
-        _lib.check(self.lib.sirenb200_comm_handle(self.handle, mine))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(mine.raw), group=group)
-        blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
-        _lib.check(self.lib.sirenb200_comm_connect(self.handle, blob))
-        dist.barrier(group=group)
+        ok = lib.sirenb200_comm_create(rank, world, int(max_floats), ctypes.byref(handle)) == 0
+        ok = ok and lib.sirenb200_comm_handle(handle, mine) == 0
+        everyone = all_ok(ok)
+        if everyone:
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            blob = ctypes.create_string_buffer(b"".join(handles), 64 * world)
+            everyone = all_ok(lib.sirenb200_comm_connect(handle, blob) == 0)
+        if not everyone:
+            if handle:
+                lib.sirenb200_comm_destroy(handle)
+            return None
+        return cls(lib, handle, rank, world)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def all_reduce(self, flat):
         _lib.check(self.lib.sirenb200_comm_allreduce(self.handle, flat.data_ptr(), flat.numel(),
                                                      torch.cuda.current_stream().cuda_stream))
 
     def close(self):
-        if self.handle:
+        if getattr(self, "handle", None):
             self.lib.sirenb200_comm_destroy(self.handle)
             self.handle = ctypes.c_void_p()
 

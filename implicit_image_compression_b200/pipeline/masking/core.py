@@ -185,10 +185,14 @@ class Masking:
         return []
 
     # ------------------------------------------------------------------ optimizer step
-    def step(self, scaler=None):
-        """core.py:671-702: optimizer step, then masks, then the prune-rate schedule."""
+    def step(self, scaler=None, skip_optimizer=False):
+        """core.py:671-702: optimizer step, then masks, then the prune-rate schedule.  GradScaler handling
+        (scale, unscale, found-inf, update) is done by train_epoch around this call; `skip_optimizer` is its
+        verdict for this step (scaler.step() skips optimizer.step() on a non-finite gradient, :679-682)."""
         opt = self.optimizer
-        if hasattr(opt, "fused_masks"):
+        if skip_optimizer:
+            self.apply_mask()
+        elif hasattr(opt, "fused_masks"):
             opt.fused_masks = {w: self.mask_dict[n] for n, w in self._masked_parameters()}
             opt.step()  # Adam + mask multiply in one kernel
         else:

@@ -40,6 +40,7 @@ class FusedAdam(torch.optim.Adam):
         super().__init__(params, lr=lr, betas=betas, eps=eps)
         self.fused_masks = {}      # param -> mask tensor, applied inside the Adam kernel (set by Masking)
         self.skip_flag = None      # device float: non-zero -> skip the update (GradScaler semantics)
+        self.inv_scale = 1.0       # gradients are multiplied by this inside the kernel (GradScaler.unscale_)
         self._step_count_fused = 0
 
     def _ensure_state(self, p):
@@ -73,7 +74,7 @@ class FusedAdam(torch.optim.Adam):
                                   [s["exp_avg"] for s in states[sl]],
                                   [s["exp_avg_sq"] for s in states[sl]],
                                   masks[sl] if masks is not None else None, group["lr"], beta1, beta2,
-                                  group["eps"], step, 1.0, self.skip_flag, False)
+                                  group["eps"], step, float(self.inv_scale), self.skip_flag, False)
         return loss
 
     def sync_state(self):
@@ -86,6 +87,20 @@ class FusedAdam(torch.optim.Adam):
     def state_dict(self):
         self.sync_state()
         return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """A stock torch.optim.Adam checkpoint (or any state_dict without `_fused_step`) carries the step count
+        only in the per-parameter `step` entries: seed the fused counter from them, otherwise bias correction
+        would restart at t = 1 on warm moments.  The device-side schedule mirror is invalidated either way."""
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:
+            if "_fused_step" not in group:
+                steps = [int(float(self.state[p]["step"])) for p in group["params"]
+                         if p in self.state and "step" in self.state[p]]
+                group["_fused_step"] = max(steps) if steps else 0
+        shared = self.__dict__.get("_sirenb200_sched")
+        if shared is not None:
+            shared["dev_state"] = None
 
 
 def get_optimizer_lr_scheduler(model, optim_cfg, quantize_mode=False):
@@ -126,15 +141,16 @@ def setup_mask(model, optim, masking_cfg=None):
     return None
 
 
-def _fused_loss_and_grads(model, grid, img):
-    """forward + F.mse_loss + backward in one library call; gradients land in param.grad."""
+def _fused_loss_and_grads(model, grid, img, loss_scale=1.0):
+    """forward + F.mse_loss + backward in one library call; gradients (of loss * loss_scale) land in param.grad."""
     model.run_weight_transforms()
     params = model.hot_parameters()
     for p in params:
         if p.grad is None or p.grad.shape != p.shape:
             p.grad = torch.empty_like(p)
     eng = model.engine_for(grid)
-    stats = eng.forward_backward(model.kernel_parameters(), img.contiguous(), [p.grad for p in params])
+    stats = eng.forward_backward(model.kernel_parameters(), img.contiguous(), [p.grad for p in params],
+                                 loss_scale=loss_scale)
     for fn in model._post_backward:
         fn(model)
     return stats
@@ -155,29 +171,39 @@ def _graph_step(model, optim, grid, img, lr_scheduler, mask):
             cache.clear()
         fitter = Fitter(model, optim, grid, img, lr_scheduler, mask, None)
         cache[key] = fitter
-    flat = fitter.flat
-    if flat.params[0].grad is not flat.views[0] or flat.params[-1].grad is not flat.views[-1]:
-        flat.attach()  # param.grad must be the views the captured step writes
-    return fitter.step_loss()
+    return fitter.step_loss()  # (re-)attaches param.grad to the views the captured step writes
+
+
+def _scaler_update(scaler, found_inf, device):
+    """GradScaler.update() with the library's non-finite flag as found_inf: the same device-side rule torch
+    applies (torch._amp_update_scale_: x backoff on inf, x growth after growth_interval clean steps)."""
+    if getattr(scaler, "_scale", None) is None:
+        scaler._lazy_init_scale_growth_tracker(device)
+    torch._amp_update_scale_(scaler._scale, scaler._growth_tracker, found_inf.reshape(1).to(torch.float32),
+                             scaler._growth_factor, scaler._backoff_factor, scaler._growth_interval)
 
 
 def train_epoch(model, optim, grid, img, **kwargs):
     """One fit step; returns this step's loss as a Python float (train_helper.py:132-185).
 
     kwargs: mask, pbar, lr_scheduler, scaler, criterion, context, preconditioner — as in the reference.
-    The reference never enters autocast (it looks the context up under the wrong key)
-    and GradScaler's power-of-two scaling is exact in fp32, so `scaler` only contributes its skip-on-inf
-    behaviour, which the fused Adam implements through the library's non-finite flag."""
+    The reference never enters autocast (it looks the context up under the wrong key), so a
+    `scaler` means fp32 arithmetic with GradScaler around it (train_helper.py:156-175, core.py:679-685): the
+    backward runs on loss * scale, the optimizer step is skipped when a scaled gradient is not finite, the
+    gradients left in param.grad are unscaled, and the scale follows GradScaler.update()."""
     mask = kwargs.get("mask")
     pbar = kwargs.get("pbar")
     lr_scheduler = kwargs.get("lr_scheduler")
     criterion = kwargs.get("criterion", F.mse_loss)
+    scaler = kwargs.get("scaler")
+    use_scaler = scaler is not None and scaler.is_enabled()
     if kwargs.get("preconditioner"):
         raise _lib.SirenB200Error("preconditioners (EKFAC) are dead code in the reference and unsupported")
 
     if not model.training:
         model.train()
-    if criterion is F.mse_loss and hasattr(model, "hot_parameters") and isinstance(optim, FusedAdam):
+    fused = criterion is F.mse_loss and hasattr(model, "hot_parameters")
+    if fused and isinstance(optim, FusedAdam) and not use_scaler:
         # one replay of the captured step graph (fit.Fitter) when nothing on the step needs the host;
         # the contract is unchanged: this step's loss as a float, param.grad populated, optimizer /
         # scheduler / mask bookkeeping advanced by one
@@ -186,7 +212,27 @@ def train_epoch(model, optim, grid, img, **kwargs):
             if pbar:
                 pbar.update(1)
             return loss
-    if criterion is F.mse_loss and hasattr(model, "hot_parameters"):
+    if fused and use_scaler:
+        if not isinstance(optim, FusedAdam):
+            raise _lib.SirenB200Error("GradScaler on the fused path needs the FusedAdam optimizer")
+        scale = float(scaler.get_scale())
+        stats = _fused_loss_and_grads(model, grid, img, loss_scale=scale)
+        host = stats.tolist()  # the step's one device->host read: [sum sq err, loss, non-finite flag, -]
+        found_inf = host[2] != 0.0
+        grads = [p.grad for p in model.hot_parameters()]
+        torch._foreach_mul_(grads, 1.0 / scale)  # scaler.unscale_: what the reference leaves in param.grad
+        optim.skip_flag, optim.inv_scale = None, 1.0
+        if mask:
+            mask.step(scaler, skip_optimizer=found_inf)
+        elif not found_inf:
+            optim.step()  # GradScaler.step() does not call optimizer.step() on a non-finite gradient
+        _scaler_update(scaler, stats[2], stats.device)
+        if pbar:
+            pbar.update(1)
+        if lr_scheduler:
+            lr_scheduler.step()
+        return host[1]
+    if fused:
         stats = _fused_loss_and_grads(model, grid, img)
         loss_t = stats[1]
         if isinstance(optim, FusedAdam):
@@ -200,7 +246,7 @@ def train_epoch(model, optim, grid, img, **kwargs):
             optim.skip_flag = None
 
     if mask:
-        mask.step(kwargs.get("scaler"))
+        mask.step()
     else:
         optim.step()
     if pbar:

@@ -17,7 +17,7 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 n = 264707 + 4 + 1  # c2 parameter count + stats, padded
 n = (n + 3) // 4 * 4
-comm = PeerExchange(n)
+comm = PeerExchange.create(n)
 g = torch.Generator(device=dev).manual_seed(100 + rank)
 ok = True
 for it in range(40):
