@@ -558,11 +558,14 @@ struct PrepArgs {
   float4* tab0;                   // [W] (omega0*w_h, omega0*w_w, omega0*b0, 0)
   float* bias_w;                  // [nlayers][W] omega_h * bias
   float* bias_raw;                // [nlayers][W] bias
+  unsigned int* pace;             // [2 * kMaxLayers] pace counters of the merged backward launches (zeroed here)
 };
 __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const PrepArgs a) {
   __shared__ float tile[32][33];
   if (a.stats && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x < 4)
     a.stats[threadIdx.x] = 0.f;
+  if (a.pace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x < 2 * kMaxLayers)
+    a.pace[threadIdx.x] = 0u;
   const int l = blockIdx.z;
   const float* w = a.w[l];
   const int W = a.W;
@@ -607,6 +610,8 @@ struct ReduceDesc {
   int nsplit;
   int64_t split_stride;
   int vec;           // 1: few splits of a large tensor -> a thread owns 4 consecutive elements (n % 4 == 0)
+  int cols;          // > 0: the partial slab is a [rows, cols_pad] matrix of which [rows, cols] are gradient elements
+  int cols_pad;
 };
 struct ReduceArgs {
   ReduceDesc d[kMaxTensors];
@@ -616,6 +621,11 @@ struct ReduceArgs {
   const float* gscale;       // device seed scale G (grads are divided by it) or null
   float* stats;              // stats[2] <- 1 if any non-finite
 };
+__device__ __forceinline__ int64_t reduce_src_index(const ReduceDesc& d, int e) {
+  // gradient element e of a [rows, cols] tensor lives at (e / cols) * cols_pad + e % cols of the (width-padded)
+  // partial slab; cols == 0: same layout
+  return d.cols ? int64_t(e / d.cols) * d.cols_pad + (e % d.cols) : int64_t(e);
+}
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a) {
   // block = 32 consecutive elements x 8 split lanes (one warp per lane: 128-byte coalesced rows)
   int t = 0;
@@ -629,7 +639,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
     bool bad4 = false;
     if (e4 < d.n) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float* src = d.src + e4;
+      const float* src = d.src + reduce_src_index(d, e4);
 #pragma unroll 8
       for (int sp = 0; sp < d.nsplit; ++sp) {
         const float4 v = *reinterpret_cast<const float4*>(src + int64_t(sp) * d.split_stride);
@@ -652,15 +662,16 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceArgs a
   const int lane = threadIdx.x >> 5;
   float s = 0.f;
   if (e < d.n) {
+    const float* src = d.src + reduce_src_index(d, e);
     int sp = lane;
     for (; sp + 24 < d.nsplit; sp += 32) {  // 4 independent loads in flight
-      const float v0 = d.src[int64_t(sp) * d.split_stride + e];
-      const float v1 = d.src[int64_t(sp + 8) * d.split_stride + e];
-      const float v2 = d.src[int64_t(sp + 16) * d.split_stride + e];
-      const float v3 = d.src[int64_t(sp + 24) * d.split_stride + e];
+      const float v0 = src[int64_t(sp) * d.split_stride];
+      const float v1 = src[int64_t(sp + 8) * d.split_stride];
+      const float v2 = src[int64_t(sp + 16) * d.split_stride];
+      const float v3 = src[int64_t(sp + 24) * d.split_stride];
       s += (v0 + v1) + (v2 + v3);
     }
-    for (; sp < d.nsplit; sp += 8) s += d.src[int64_t(sp) * d.split_stride + e];
+    for (; sp < d.nsplit; sp += 8) s += src[int64_t(sp) * d.split_stride];
   }
   __shared__ float red[8][32];
   red[lane][threadIdx.x & 31] = s;
@@ -1159,15 +1170,19 @@ __global__ void kmeans_linspace_kernel(const float* mm, int k, float* cent) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Gradient exchange of a pixel-sharded fit over NVLink peer memory (SURVEY.md §8e): in-place sum of a flat
-// fp32 buffer over the ranks of ONE node.  Every rank owns a peer-mapped region {signals, two data
-// buffers}.  Block b of every rank: (1) copies its slice of `io` into the local data buffer of this epoch's
-// parity, (2) tells block b of every peer that the slice is there and waits for theirs (one system-scope
-// flag per (parity, block, source rank)), (3) sums the slice over the ranks' buffers IN RANK ORDER — the
-// same order on every rank, so the replicated weights stay bit-identical — and writes it back to `io`.
-// No trailing barrier: the next exchange uses the other parity, and a rank can only be one exchange ahead
-// of a peer because step (2) needs that peer's flag for the new epoch.  Epochs live in device memory
-// (per block), so the launch is identical every step and can be captured in a CUDA graph.
+// step_end_kernel: everything of a fit step that follows the last GEMM, in ONE launch.
+//   phase 1  every block reduces ITS chunks of the split-K / per-CTA gradient partials (x scale / G);
+//            block 0 also sums the squared-error partials (F.mse_loss, train_helper.py:151-154)
+//   exchange (pixel-sharded fits, world > 1) the block's reduced chunks go to this rank's
+//            peer-visible buffer, block b of every rank signals block b of every peer (system-scope flags), then
+//            loads the same chunks from EVERY rank's buffer over NVLink and sums them in rank order — bit-identical
+//            results on all ranks, so the replicated weights never drift.  No grid-wide step is needed for it.
+//   barrier  one grid-wide arrive/wait (all blocks are co-resident: grid <= #SMs): publishes the non-finite flag
+//            (GradScaler's found_inf) and the loss
+//   phase 2  StepLR + Adam bias corrections from the device-side step counter (same double arithmetic as
+//            sched_step_kernel), then torch.optim.Adam.step + Masking.apply_mask (train_helper.py:72-84,177;
+//            core.py:272-279,687) on the block's own chunks — the gradients it just wrote.
+// It replaces reduce_partials + finalize_loss + p2p_allreduce + sched_step + adam_multi (5 launches).
 // ------------------------------------------------------------------------------------------
 constexpr int kCommMaxRanks = 8;
 constexpr int kCommBlocks = 144;   // one CTA per SM (<= 148): a 1 MB buffer moves in a single pass of float4s
@@ -1192,6 +1207,312 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float* p) {
                : "memory");
   return v;
 }
+__device__ __forceinline__ float ld_volatile_f1(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+// Wait until *flag == epoch (written by a peer GPU) with exponential back-off; the bound is wall-clock
+// (globaltimer): a rank may legitimately be seconds late (rank-0-only evaluation, first-use graph capture).
+__device__ __forceinline__ void wait_peer_flag(const uint32_t* flag, uint32_t epoch, uint64_t timeout_ns, int rank,
+                                               int b, int r) {
+  uint32_t ns = 32;
+  uint64_t t_start = 0;
+  while (ld_acquire_sys(flag) != epoch) {
+    __nanosleep(ns);
+    if (ns < 4096) ns <<= 1;
+    if (timeout_ns != 0) {
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_start == 0) t_start = now;
+      if (now - t_start > timeout_ns) {
+        printf("sirenb200: gradient exchange timeout: rank %d block %d waiting for rank %d epoch %u\n", rank, b, r,
+               epoch);
+        __trap();
+      }
+    }
+  }
+}
+
+struct StepEndArgs {
+  ReduceArgs red;                     // partials -> gradient tensors (dst = the caller's h_grads[t])
+  float* p[kMaxTensors];              // Adam tensors, aligned with red.d[]
+  float* m[kMaxTensors];
+  float* v[kMaxTensors];
+  const float* mask[kMaxTensors];
+  int64_t flat_off[kMaxTensors];      // exchange: offset (floats) of tensor t's gradient inside the flat buffer
+  float beta2, eps, omb1, omb2;
+  const float* loss_partial;          // squared-error partials
+  int loss_nparts;
+  int64_t loss_stride;
+  float inv_count;                    // 1 / (H*W*C) of the FULL image
+  float* gstate;                      // [0] seed scale G, [1] cap (tensor-core path) or null
+  double* sched;                      // 8 doubles, see sched_step_kernel
+  float* loss_ring;
+  int ring_len;
+  float* loss_host;
+  unsigned long long* bar;            // grid barrier counter (monotonic)
+  CommPeers cp;                       // exchange (world > 1)
+  uint32_t* epoch_b;
+  int rank, world;
+  int64_t max_floats;
+  int64_t stats_off;                  // offset of the 4 stats floats inside the flat buffer
+  unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
+  __shared__ float red_s[8][32];
+  __shared__ float sh_scal[2];
+  const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+  const ReduceArgs& r = a.red;
+  const int nchunks = r.chunk_begin[r.ndesc];
+  const float scale = r.gscale ? r.scale / *r.gscale : r.scale;  // the OLD seed scale: read before the barrier
+  const int step = int(a.sched[0]);                              // 0-based index of this optimiser step
+  const bool comm = a.world > 1;
+  uint32_t epoch = 0, par = 0;
+  float* mine = nullptr;
+  if (comm) {
+    epoch = a.epoch_b[b] + 1u;
+    par = epoch & 1u;
+    mine = a.cp.data[a.rank] + int64_t(par) * a.max_floats;
+  }
+  bool bad = false;
+
+  // ---- squared error (block 0) ----
+  float sse = 0.f;
+  if (b == 0) {
+    float s = 0.f;
+    for (int i = tid; i < a.loss_nparts; i += 256) s += a.loss_partial[i * a.loss_stride];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) red_s[0][tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 0; k < 8; ++k) sse += red_s[0][k];
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 1: reduce this block's chunks over the splits ----
+  int t = 0;
+  for (int c = b; c < nchunks; c += G) {
+    while (t + 1 < r.ndesc && c >= r.chunk_begin[t + 1]) ++t;
+    const ReduceDesc d = r.d[t];
+    float* out = comm ? mine + a.flat_off[t] : d.dst;
+    if (d.vec) {
+      const int e4 = (c - r.chunk_begin[t]) * 1024 + tid * 4;
+      if (e4 < d.n) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* src = d.src + reduce_src_index(d, e4);
+#pragma unroll 8
+        for (int sp = 0; sp < d.nsplit; ++sp) {
+          const float4 v = *reinterpret_cast<const float4*>(src + int64_t(sp) * d.split_stride);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+        acc.x *= scale;
+        acc.y *= scale;
+        acc.z *= scale;
+        acc.w *= scale;
+        *reinterpret_cast<float4*>(out + e4) = acc;
+        if (!comm) bad |= !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+      }
+    } else {
+      const int e = (c - r.chunk_begin[t]) * 32 + (tid & 31);
+      const int lane = tid >> 5;
+      float s = 0.f;
+      if (e < d.n) {
+        const float* src = d.src + reduce_src_index(d, e);
+        int sp = lane;
+        for (; sp + 24 < d.nsplit; sp += 32) {  // 4 independent loads in flight
+          const float v0 = src[int64_t(sp) * d.split_stride];
+          const float v1 = src[int64_t(sp + 8) * d.split_stride];
+          const float v2 = src[int64_t(sp + 16) * d.split_stride];
+          const float v3 = src[int64_t(sp + 24) * d.split_stride];
+          s += (v0 + v1) + (v2 + v3);
+        }
+        for (; sp < d.nsplit; sp += 8) s += src[int64_t(sp) * d.split_stride];
+      }
+      red_s[lane][tid & 31] = s;
+      __syncthreads();
+      if (lane == 0 && e < d.n) {
+        float x = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x += red_s[k][tid];
+        x *= scale;
+        out[e] = x;
+        if (!comm) bad |= !isfinite(x);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- exchange over NVLink peer memory ----
+  if (comm) {
+    if (b == 0 && tid == 0)
+      *reinterpret_cast<float4*>(mine + a.stats_off) = make_float4(sse, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (tid < a.world) {
+      const int q = tid;
+      const int64_t slot = (int64_t(par) * kCommBlocks + b) * kCommMaxRanks;
+      __threadfence_system();
+      st_release_sys(a.cp.sig[q] + slot + a.rank, epoch);
+      wait_peer_flag(a.cp.sig[a.rank] + slot + q, epoch, a.timeout_ns, a.rank, b, q);
+    }
+    __syncthreads();
+    const int64_t poff = int64_t(par) * a.max_floats;
+    t = 0;
+    for (int c = b; c < nchunks; c += G) {
+      while (t + 1 < r.ndesc && c >= r.chunk_begin[t + 1]) ++t;
+      const ReduceDesc d = r.d[t];
+      if (d.vec) {
+        const int e4 = (c - r.chunk_begin[t]) * 1024 + tid * 4;
+        if (e4 < d.n) {
+          float4 v[kCommMaxRanks];
+#pragma unroll
+          for (int q = 0; q < kCommMaxRanks; ++q)
+            if (q < a.world) v[q] = ld_volatile_f4(a.cp.data[q] + poff + a.flat_off[t] + e4);
+          float4 acc = v[0];
+#pragma unroll
+          for (int q = 1; q < kCommMaxRanks; ++q)
+            if (q < a.world) {
+              acc.x += v[q].x;
+              acc.y += v[q].y;
+              acc.z += v[q].z;
+              acc.w += v[q].w;
+            }
+          *reinterpret_cast<float4*>(d.dst + e4) = acc;
+          bad |= !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+        }
+      } else {
+        const int e = (c - r.chunk_begin[t]) * 32 + tid;
+        if (tid < 32 && e < d.n) {
+          float v[kCommMaxRanks];
+#pragma unroll
+          for (int q = 0; q < kCommMaxRanks; ++q)
+            if (q < a.world) v[q] = ld_volatile_f1(a.cp.data[q] + poff + a.flat_off[t] + e);
+          float acc = v[0];
+#pragma unroll
+          for (int q = 1; q < kCommMaxRanks; ++q)
+            if (q < a.world) acc += v[q];
+          d.dst[e] = acc;
+          bad |= !isfinite(acc);
+        }
+      }
+    }
+    if (b == 0 && tid == 0) {
+      sse = 0.f;
+      for (int q = 0; q < a.world; ++q) sse += ld_volatile_f1(a.cp.data[q] + poff + a.stats_off);
+    }
+  }
+  if (b == 0 && tid == 0) {
+    r.stats[0] = sse;
+    r.stats[1] = sse * a.inv_count;
+  }
+  if (__syncthreads_or(bad) && tid == 0) r.stats[2] = 1.0f;
+
+  // ---- grid barrier ----
+  if (tid == 0) {
+    __threadfence();
+    const unsigned long long old = atomicAdd(a.bar, 1ull);
+    const unsigned long long target = (old / G + 1ull) * G;
+    uint32_t ns = 16;
+    while (true) {
+      unsigned long long cur;
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(a.bar) : "memory");
+      if (cur >= target) break;
+      __nanosleep(ns);
+      if (ns < 256) ns <<= 1;
+    }
+    // schedule of the step about to be applied (sched_step_kernel's arithmetic, bit for bit)
+    const double lr = double(float(a.sched[1] * pow(a.sched[2], double(step / int(a.sched[3])))));
+    const double bc1 = 1.0 - pow(double(float(a.sched[4])), double(step + 1));
+    const double bc2 = 1.0 - pow(double(float(a.sched[5])), double(step + 1));
+    const double step_size = lr / bc1, bc2_sqrt = sqrt(bc2);
+    sh_scal[0] = float(step_size);
+    sh_scal[1] = float(bc2_sqrt);
+    if (b == 0) {
+      const float loss = ld_volatile_f1(r.stats + 1);
+      const float flag = ld_volatile_f1(r.stats + 2);
+      if (a.gstate) {
+        float cap = a.gstate[1];
+        if (flag != 0.f) cap = fmaxf(1.f, a.gstate[0] * (1.f / 16.f));
+        // next seed scale: power of two near 0.125 / rmse, clamped to [1, cap]
+        float g = 1.f;
+        if (loss > 0.f && isfinite(loss)) g = exp2f(floorf(log2f(0.125f * rsqrtf(loss))));
+        g = fminf(fmaxf(g, 1.f), cap);
+        a.gstate[0] = g;
+        a.gstate[1] = cap;
+      }
+      a.sched[6] = step_size;
+      a.sched[7] = bc2_sqrt;
+      if (a.loss_ring) a.loss_ring[step % a.ring_len] = loss;
+      if (a.loss_host) {
+        a.loss_host[0] = loss;
+        __threadfence_system();
+        a.loss_host[1] = float(step + 1);
+      }
+      a.sched[0] = double(step + 1);
+    }
+  }
+  __syncthreads();
+  const bool skip = ld_volatile_f1(r.stats + 2) != 0.f;
+  const float step_size = sh_scal[0], bc2_sqrt = sh_scal[1];
+
+  // ---- phase 2: Adam (+ mask) on the block's own chunks ----
+  auto adam1 = [&](float* P, float* M, float* V, const float* K, int i, float g) {
+    float pv = P[i];
+    if (!skip) {
+      float mv = M[i], vv = V[i];
+      mv = mv + (g - mv) * a.omb1;                  // exp_avg.lerp_(grad, 1-beta1)
+      vv = vv * a.beta2 + (a.omb2 * g) * g;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+      const float denom = sqrtf(vv) / bc2_sqrt + a.eps;
+      pv = pv + (-step_size * mv) / denom;          // addcdiv_(m, denom, -step_size)
+      M[i] = mv;
+      V[i] = vv;
+    }
+    if (K) pv = pv * K[i];                          // Masking.apply_mask
+    P[i] = pv;
+  };
+  t = 0;
+  for (int c = b; c < nchunks; c += G) {
+    while (t + 1 < r.ndesc && c >= r.chunk_begin[t + 1]) ++t;
+    const ReduceDesc d = r.d[t];
+    if (a.p[t] == nullptr) continue;
+    if (d.vec) {
+      const int e4 = (c - r.chunk_begin[t]) * 1024 + tid * 4;
+      if (e4 < d.n) {
+        const float4 g = *reinterpret_cast<const float4*>(d.dst + e4);
+        adam1(a.p[t], a.m[t], a.v[t], a.mask[t], e4 + 0, g.x);
+        adam1(a.p[t], a.m[t], a.v[t], a.mask[t], e4 + 1, g.y);
+        adam1(a.p[t], a.m[t], a.v[t], a.mask[t], e4 + 2, g.z);
+        adam1(a.p[t], a.m[t], a.v[t], a.mask[t], e4 + 3, g.w);
+      }
+    } else {
+      const int e = (c - r.chunk_begin[t]) * 32 + tid;
+      if (tid < 32 && e < d.n) adam1(a.p[t], a.m[t], a.v[t], a.mask[t], e, d.dst[e]);
+    }
+  }
+  if (comm) {
+    __syncthreads();
+    if (tid == 0) a.epoch_b[b] = epoch;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Gradient exchange of a pixel-sharded fit over NVLink peer memory (SURVEY.md §8e): in-place sum of a flat
+// fp32 buffer over the ranks of ONE node.  Every rank owns a peer-mapped region {signals, two data
+// buffers}.  Block b of every rank: (1) copies its slice of `io` into the local data buffer of this epoch's
+// parity, (2) tells block b of every peer that the slice is there and waits for theirs (one system-scope
+// flag per (parity, block, source rank)), (3) sums the slice over the ranks' buffers IN RANK ORDER — the
+// same order on every rank, so the replicated weights stay bit-identical — and writes it back to `io`.
+// No trailing barrier: the next exchange uses the other parity, and a rank can only be one exchange ahead
+// of a peer because step (2) needs that peer's flag for the new epoch.  Epochs live in device memory
+// (per block), so the launch is identical every step and can be captured in a CUDA graph.
+// ------------------------------------------------------------------------------------------
+// (constants, peer tables and the system-scope flag helpers are declared with step_end_kernel above)
 __global__ void __launch_bounds__(kCommThreads) p2p_allreduce_kernel(const CommPeers cp, uint32_t* epoch_b, float* io,
                                                             int64_t n, int64_t max_floats, int rank,
                                                             int world, uint64_t timeout_ns) {
@@ -1212,25 +1533,7 @@ __global__ void __launch_bounds__(kCommThreads) p2p_allreduce_kernel(const CommP
     __threadfence_system();
     st_release_sys(cp.sig[r] + slot + rank, epoch);
     const uint32_t* flag = cp.sig[rank] + slot + r;
-    // Wait with exponential back-off; the bound is wall-clock (globaltimer) and generous — a rank may be late
-    // by seconds for legitimate reasons (rank-0-only evaluation or logging, first-use graph capture) — and
-    // SIRENB200_EXCHANGE_TIMEOUT_S=0 disables it.
-    uint32_t ns = 32;
-    uint64_t t_start = 0;
-    while (ld_acquire_sys(flag) != epoch) {
-      __nanosleep(ns);
-      if (ns < 4096) ns <<= 1;
-      if (timeout_ns != 0) {
-        uint64_t now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t_start == 0) t_start = now;
-        if (now - t_start > timeout_ns) {
-          printf("sirenb200: gradient exchange timeout: rank %d block %d waiting for rank %d epoch %u\n", rank, b, r,
-                 epoch);
-          __trap();
-        }
-      }
-    }
+    wait_peer_flag(flag, epoch, timeout_ns, rank, b, r);
   }
   __syncthreads();
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {

@@ -113,6 +113,13 @@ struct sirenb200_plan {
   int chunk_tiles = 0;         // 128-row tiles per L2-resident chunk (0 = whole shard)
   int nchunks = 1;
   int active_splits = 1;       // split slabs the dW GEMM actually writes (<= col_splits)
+  unsigned int* pace = nullptr;  // [2 * kMaxLayers] pace counters (merged dX + dW launches)
+  bool bwd_merged = true;      // dX GEMM and weight-gradient reduction of a layer in ONE launch (SIRENB200_BWD_MERGED=0: separate)
+  int dw_ctas = 0;             // CTAs of that launch that run the reduction
+  int merged_splits = 0;       // pixel splits of the reduction role
+  int pace_window = 192;       // tiles the two roles may drift apart
+  bool defer_reduce = false;   // transient: tc_run leaves the partial reduction to the fused step-end kernel
+  unsigned long long* bar = nullptr;  // grid-barrier counter of step_end_kernel
 
   // ---- optional per-kernel timing (cudaEvent pairs recorded around tagged launches) ----
   bool prof_on = false;
@@ -301,6 +308,7 @@ int tc_prep(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* 
     pa.wl16 = p->last_tc ? p->wl16 : nullptr;
     pa.wlt16 = p->wlt16;
     pa.bias_raw = p->bias_raw;
+    pa.pace = p->pace;
     {
       ProfScope ps(p, PK_PREP, st);
       tc_prep_weights_kernel<<<dim3(W / 32, W / 32, nh), 256, 0, st>>>(pa);
@@ -475,6 +483,34 @@ int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const fl
   return 0;
 }
 
+// one backward layer: dX GEMM of layer l (CTAs [0, dx)) + its weight-gradient reduction (the rest), one launch
+template <int W, bool RED>
+int launch_bwd_merged(sirenb200_plan* p, const RowGemmArgs& ra, const ColGemmJobs& jobs, int l, cudaStream_t st) {
+  constexpr int NT = W < 256 ? W : 256;
+  constexpr int NPARTS = W / NT;
+  using RCfg = RowGemmCfg<W, NT, MODE_DX, NPARTS>;
+  using CCfg = ColGemmCfg<NT>;
+  constexpr uint32_t SMEM = RCfg::SMEM_BYTES > CCfg::SMEM_BYTES ? RCfg::SMEM_BYTES : CCfg::SMEM_BYTES;
+  auto kfn = bwd_merged_kernel<W, RED>;
+  static bool attr_set[64] = {};
+  if (!attr_set[p->device & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)));
+    attr_set[p->device & 63] = true;
+  }
+  const int dw = jobs.num_problems * jobs.mblocks * jobs.nparts * jobs.splits;
+  int dx = p->nsm - dw;
+  if (dx > ra.num_tiles * NPARTS) dx = ra.num_tiles * NPARTS;
+  {
+    ProfScope ps(p, PK_DX_GEMM, st);
+    launch_ex(kfn, dim3(dx + dw), dim3(RED ? 640 : 384), SMEM, st, p->pdl && !p->prof_on, p->tm_dz, p->tm_wt[l - 1],
+              p->tm_act, ra, umma_idesc(128, NT, 0, 0, 0, 0), jobs, umma_idesc(128, NT, 0, 0, 1, 1),
+              umma_idesc(128, 16, 0, 0, 1, 1), dx, p->pace + 2 * l, p->pace_window);
+  }
+  LAUNCH_CHECK();
+  p->last_rowgemm_grid = dx;
+  return 0;
+}
+
 template <int W>
 int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch, cudaStream_t st) {
   const int nh = p->D - 2;
@@ -501,6 +537,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     jobs.interleave = interleave;
   };
   const bool fuse_l0 = p->fuse_l0 && nh >= 1 && p->nchunks == 1;
+  const bool merged = p->bwd_merged && p->dw_ctas > 0 && p->nchunks == 1;
   // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
   for (int l = nh; l >= 1; --l) {
     RowGemmArgs ra{};
@@ -512,6 +549,21 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     ra.b_early = 1;  // omega W^T was staged at the start of the step, at least two kernels ago
     int rc;
     bool done = false;
+    if (merged) {
+      ColGemmJobs jobs{};
+      fill_jobs(jobs, l, 1, p->active_splits, 1);
+      if (l == 1 && fuse_l0) {
+        ra.gen_coord = p->coord;
+        ra.gen_coord.p_offset = ch.p0;
+        ra.red_part = p->l0_part;
+        rc = launch_bwd_merged<W, true>(p, ra, jobs, l, st);
+        p->l0_used = 2 * p->last_rowgemm_grid;
+      } else {
+        rc = launch_bwd_merged<W, false>(p, ra, jobs, l, st);
+      }
+      if (rc) return rc;
+      continue;
+    }
     {
       if (l == 1 && fuse_l0) {
         ra.gen_coord = p->coord;
@@ -526,7 +578,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     if (rc) return rc;
   }
   // hidden-layer weight / bias gradients: one split-K launch over all layers
-  if (nh > 0) {
+  if (nh > 0 && !merged) {
     ColGemmJobs jobs{};
     fill_jobs(jobs, 1, nh, p->col_splits, 0);
     int rc = launch_colgemm<W>(p, jobs, st);
@@ -552,12 +604,10 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
   return 0;
 }
 
-// reduce every partial buffer into the caller's gradient tensors
-template <int W>
-int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats, int nchunks,
-              cudaStream_t st) {
-  const int D = p->D, C = p->C, nh = D - 2;
-  ReduceArgs ra{};
+// descriptors of every partial buffer -> the caller's gradient tensors (order = model.parameters())
+void tc_build_reduce(const sirenb200_plan* p, float* const* grads, float scale, float* stats, int nchunks,
+                     ReduceArgs& ra) {
+  const int D = p->D, C = p->C, W = p->W, nh = D - 2;
   int nd = 0;
   auto add = [&](float* dst, const float* src, int n, int nsplit, int64_t stride) {
     ra.d[nd].dst = dst;
@@ -569,6 +619,8 @@ int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats,
     ra.d[nd].vec = (n >= 4096 && n % 4 == 0 && stride % 4 == 0 && nsplit <= 64 &&
                     (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0)
                        ? 1 : 0;
+    ra.d[nd].cols = 0;
+    ra.d[nd].cols_pad = 0;
     ++nd;
   };
   add(grads[0], p->l0_part, 2 * W, p->l0_used, 3 * W);
@@ -591,9 +643,16 @@ int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats,
   ra.scale = scale;
   ra.gscale = p->gstate;
   ra.stats = stats;
+}
+
+// reduce every partial buffer into the caller's gradient tensors
+int tc_reduce(sirenb200_plan* p, float* const* grads, float scale, float* stats, int nchunks,
+              cudaStream_t st) {
+  ReduceArgs ra{};
+  tc_build_reduce(p, grads, scale, stats, nchunks, ra);
   {
     ProfScope ps(p, PK_REDUCE, st);
-    reduce_partials_kernel<<<chunks, 256, 0, st>>>(ra);
+    reduce_partials_kernel<<<ra.chunk_begin[ra.ndesc], 256, 0, st>>>(ra);
   }
   LAUNCH_CHECK();
   return 0;
@@ -616,7 +675,7 @@ int tc_run(sirenb200_plan* p, const float* const* prm, int mode, const float* im
                        : tc_last_chunk<W>(p, prm, mode, img_or_dpred, pred, ch, st);
     if (!rc && mode != 0) rc = tc_backward_chunk<W>(p, prm, ch, st);
   }
-  if (!rc && mode != 0) rc = tc_reduce<W>(p, grads, scale, stats, int(chunks.size()), st);
+  if (!rc && mode != 0 && !p->defer_reduce) rc = tc_reduce(p, grads, scale, stats, int(chunks.size()), st);
   return rc;
 }
 
@@ -851,6 +910,13 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
   }
   ALLOC(p->gstate, 4);
   ALLOC(p->eval_acc, 2);
+  ALLOC(p->bar, 1);
+  ALLOC(p->pace, 2 * kMaxLayers);
+  cudaMemset(p->pace, 0, 2 * kMaxLayers * sizeof(unsigned int));
+  if (cudaMemset(p->bar, 0, sizeof(*p->bar)) != cudaSuccess) {
+    sirenb200_destroy(p);
+    return fail(SIRENB200_ERR_CUDA, "cudaMemset failed");
+  }
   {
     const float init[4] = {1.f, 4096.f, 0.f, 0.f};
     cudaError_t e = cudaMemcpy(p->gstate, init, sizeof(init), cudaMemcpyHostToDevice);
@@ -906,13 +972,31 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     if (splits < 1) splits = 1;
     if (splits > p->ntiles) splits = p->ntiles;
     p->col_splits = splits;  // (re-clamped to the chunk size below)
-    const int slabs = splits;
+    {
+      // merged dX + dW launches: the reduction role gets ~30 % of the SMs (its MMA time per tile is ~2/5 of the
+      // dX role's epilogue-bound time, and its loads come from L2), as (W/128 row blocks) x (column parts) x splits
+      const char* env = getenv("SIRENB200_BWD_MERGED");
+      p->bwd_merged = nh > 0 && !(env && atoi(env) == 0);
+      const int per_split = (W / 128) * (W / (W < 256 ? W : 256));
+      int want = (p->nsm * 30) / 100;
+      env = getenv("SIRENB200_DW_CTAS");
+      if (env && atoi(env) > 0) want = atoi(env);
+      int ms = want / per_split;
+      if (ms < 1) ms = 1;
+      if (ms > p->ntiles) ms = p->ntiles;
+      p->dw_ctas = ms * per_split;
+      if (p->dw_ctas >= p->nsm) p->bwd_merged = false;
+      env = getenv("SIRENB200_PACE_WINDOW");
+      if (env && atoi(env) > 0) p->pace_window = atoi(env);
+      if (p->bwd_merged) p->merged_splits = ms;
+    }
+    const int slabs = (p->bwd_merged && p->merged_splits > splits) ? p->merged_splits : splits;
     ALLOC(p->dw_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W * W);
     ALLOC(p->db_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W);
     p->chunk_tiles = p->ntiles;  // the whole shard is one chunk (row chunking lost to launch overheads)
     p->nchunks = 1;
     if (p->col_splits > p->chunk_tiles) p->col_splits = p->chunk_tiles;
-    p->active_splits = p->col_splits;
+    p->active_splits = p->bwd_merged ? p->merged_splits : p->col_splits;
     const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
     {
       const char* env = getenv("SIRENB200_LAST_TC");
@@ -974,7 +1058,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
 
 int sirenb200_destroy(sirenb200_handle_t p) {
   if (!p) return 0;
-  void* ptrs[] = {p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
+  void* ptrs[] = {p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
                   p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
                   p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
                   p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline,
@@ -1402,14 +1486,18 @@ int sirenb200_comm_allreduce(sirenb200_comm_t c, float* data, int64_t n, sirenb2
   return 0;
 }
 
-int sirenb200_fit_steps(sirenb200_handle_t h, int32_t k, const float* img, const sirenb200_fit_t* f,
-                        sirenb200_stream_t stream) {
-  if (!h || !img || !f || k < 0) return fail(SIRENB200_ERR_INVALID, "fit_steps: bad argument");
+// One whole fit step.  Tensor-core handles: forward + MSE + backward leave their partials in the workspace and
+// ONE kernel (step_end_kernel) reduces them, exchanges them over NVLink when fit->comm is set, finalises the loss,
+// advances the schedule and applies Adam.  fp32 handles: the same sequence as separate launches.
+int sirenb200_fit_step(sirenb200_handle_t h, const float* img, const sirenb200_fit_t* f, sirenb200_stream_t stream) {
+  if (!h || !img || !f) return fail(SIRENB200_ERR_INVALID, "fit_step: bad argument");
   if (!f->h_params || !f->h_grads || !f->h_exp_avg || !f->h_exp_avg_sq || !f->h_numel || !f->sched_state ||
       !f->stats)
-    return fail(SIRENB200_ERR_INVALID, "fit_steps: null field");
-  if (f->comm && (!f->flat || f->flat_n < 1)) return fail(SIRENB200_ERR_INVALID, "fit_steps: comm without flat");
-  for (int i = 0; i < k; ++i) {
+    return fail(SIRENB200_ERR_INVALID, "fit_step: null field");
+  if (f->comm && (!f->flat || f->flat_n < 1)) return fail(SIRENB200_ERR_INVALID, "fit_step: comm without flat");
+  const bool fused = h->cfg.precision == SIRENB200_PREC_F16TC && f->n_tensors == 2 * h->D &&
+                     !(getenv("SIRENB200_STEP_END") && atoi(getenv("SIRENB200_STEP_END")) == 0);
+  if (!fused) {
     int rc = sirenb200_forward_backward(h, f->h_params, img, 1.0f, f->h_grads, f->stats, stream);
     if (!rc && f->comm) rc = sirenb200_comm_allreduce(f->comm, f->flat, f->flat_n, stream);
     if (!rc)
@@ -1419,6 +1507,79 @@ int sirenb200_fit_steps(sirenb200_handle_t h, int32_t k, const float* img, const
       rc = sirenb200_adam_step_dev(f->n_tensors, f->h_params, f->h_grads, f->h_exp_avg, f->h_exp_avg_sq, f->h_mask,
                                    f->h_numel, f->beta1, f->beta2, f->eps, f->sched_state, 1.0f, f->stats + 2, 0,
                                    stream);
+    return rc;
+  }
+  int rc = check_ready(h);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  sirenb200_comm_t c = f->comm;
+  const bool comm = c && c->world > 1;
+  if (comm) {
+    if (!c->connected || c->peers.data[c->rank] == nullptr) return fail(SIRENB200_ERR_STATE, "fit_step: comm not connected");
+    if (f->flat_n > c->max_floats) return fail(SIRENB200_ERR_INVALID, "fit_step: flat buffer exceeds the comm region");
+    if (reinterpret_cast<uintptr_t>(f->flat) & 15u) return fail(SIRENB200_ERR_INVALID, "fit_step: flat must be 16-byte aligned");
+    if (f->stats < f->flat || f->stats + 4 > f->flat + f->flat_n || ((f->stats - f->flat) & 3))
+      return fail(SIRENB200_ERR_INVALID, "fit_step: stats must be 4 aligned floats inside the flat buffer");
+  }
+  h->defer_reduce = true;
+  rc = tc_dispatch(h, f->h_params, 1, img, nullptr, f->h_grads, h->inv_count, f->stats, st);
+  h->defer_reduce = false;
+  h->have_fwd = (rc == 0);
+  if (rc) return rc;
+  StepEndArgs a{};
+  tc_build_reduce(h, f->h_grads, h->inv_count, f->stats, h->nchunks, a.red);
+  for (int i = 0; i < f->n_tensors; ++i) {
+    if (f->h_numel[i] != a.red.d[i].n) return fail(SIRENB200_ERR_INVALID, "fit_step: tensor %d has %lld elements, the model has %d", i, (long long)f->h_numel[i], a.red.d[i].n);
+    a.p[i] = f->h_params[i];
+    a.m[i] = f->h_exp_avg[i];
+    a.v[i] = f->h_exp_avg_sq[i];
+    a.mask[i] = f->h_mask ? f->h_mask[i] : nullptr;
+    if (comm) {
+      const int64_t off = f->h_grads[i] - f->flat;
+      if (off < 0 || off + a.red.d[i].n > f->flat_n || (a.red.d[i].vec && (off & 3)))
+        return fail(SIRENB200_ERR_INVALID, "fit_step: gradient %d is not an (aligned) view of the flat buffer", i);
+      a.flat_off[i] = off;
+    }
+  }
+  a.beta2 = f->beta2;
+  a.eps = f->eps;
+  a.omb1 = float(1.0 - double(f->beta1));
+  a.omb2 = float(1.0 - double(f->beta2));
+  a.loss_partial = h->last_part + h->C * h->W + h->C;
+  a.loss_nparts = h->last_grid * h->nchunks;
+  a.loss_stride = int64_t(h->C) * h->W + h->C + 1;
+  a.inv_count = h->inv_count;
+  a.gstate = h->gstate;
+  a.sched = f->sched_state;
+  a.loss_ring = f->loss_ring;
+  a.ring_len = f->ring_len > 0 ? f->ring_len : 1;
+  a.loss_host = f->loss_host;
+  a.bar = h->bar;
+  a.world = 1;
+  int grid = h->nsm < a.red.chunk_begin[a.red.ndesc] ? h->nsm : a.red.chunk_begin[a.red.ndesc];
+  if (comm) {
+    a.cp = c->peers;
+    a.epoch_b = c->epoch_b;
+    a.rank = c->rank;
+    a.world = c->world;
+    a.max_floats = c->max_floats;
+    a.stats_off = f->stats - f->flat;
+    a.timeout_ns = exchange_timeout_ns();
+    grid = kCommBlocks;  // every rank runs the same blocks: block b pairs with block b of each peer
+  }
+  {
+    ProfScope ps(h, PK_REDUCE, st);
+    step_end_kernel<<<grid, 256, 0, st>>>(a);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int sirenb200_fit_steps(sirenb200_handle_t h, int32_t k, const float* img, const sirenb200_fit_t* f,
+                        sirenb200_stream_t stream) {
+  if (k < 0) return fail(SIRENB200_ERR_INVALID, "fit_steps: bad argument");
+  for (int i = 0; i < k; ++i) {
+    int rc = sirenb200_fit_step(h, img, f, stream);
     if (rc) return rc;
   }
   return 0;

@@ -97,6 +97,33 @@ __device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh,
   xw = (gw - 0.5f) * 2.0f;
 }
 
+// Pace hint between two roles of ONE launch that sweep the same tensors (the dX GEMM and the weight-gradient
+// reduction of a layer both read dz[l] and act[l-1]): each role counts the tiles whose loads it has issued and
+// holds its own loads back while it is more than `window` tiles ahead of the other, so that whichever role
+// touches a tile second finds it in the 126 MB L2 instead of HBM.  It is a hint, not a dependency: the wait is
+// bounded and a role that has finished releases the other for good.
+struct PaceCtx {
+  unsigned int* mine;         // tiles (x my_per_tile) this role has issued; null = no pacing
+  const unsigned int* other;  // the other role's counter
+  int window;                 // tiles
+  int my_per_tile, other_per_tile;
+};
+__device__ __forceinline__ void pace_wait(const PaceCtx& pc, int tile) {
+  if (!pc.mine) return;
+  for (int spins = 0; spins < 4096; ++spins) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pc.other) : "memory");
+    if (tile <= int(v / unsigned(pc.other_per_tile)) + pc.window) return;
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void pace_post(const PaceCtx& pc, unsigned int n = 1u) {
+  if (pc.mine) atomicAdd(pc.mine, n);
+}
+__device__ __forceinline__ void pace_finish(const PaceCtx& pc) {
+  if (pc.mine) atomicAdd(pc.mine, 1u << 28);
+}
+
 // ------------------------------------------------------------------------------------------
 // rowgemm
 // ------------------------------------------------------------------------------------------
@@ -162,7 +189,7 @@ struct RowGemmArgs {
 // roles 0..3 = generator warps, 4 = MMA issuer, 5 = epilogue
 #define SB_DBG_G(role, tile_i, k)                                                   \
   do {                                                                              \
-    if (GEN && args.gen_tl && blockIdx.x == 0 && (tile_i) < 8)                      \
+    if (GEN && args.gen_tl && cta == 0 && (tile_i) < 8)                      \
       args.gen_tl[((role) * 8 + (tile_i)) * 8 + (k)] = clock64();                   \
   } while (0)
 
@@ -171,10 +198,11 @@ template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN 
 // (two warps per TMEM lane quadrant; each takes 32 of the 64 columns of every output chunk);
 // GEN: warps 0, 2, 3 and 12..16 = A-operand generators (network layer 0), two per 64-wide k-block; the
 // weight load moves to warp 1.
-__global__ void __launch_bounds__(GEN ? 544 : (RED ? 640 : 384), 1)
-rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
-               const RowGemmArgs args, const uint32_t idesc) {
+// `cta` / `ncta`: index of this CTA among the CTAs of the role and their number (== cta / ncta when the
+// whole grid runs this body).
+__device__ __forceinline__ void
+rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmE, const CUtensorMap& tmO,
+             const RowGemmArgs& args, const uint32_t idesc, const int cta, const int ncta, const PaceCtx pace) {
   using C = RowGemmCfg<KDIM, NDIM, MODE, NPARTS>;
   const int num_items = args.num_tiles * NPARTS;  // item = (tile, output part)
   extern __shared__ uint8_t smem_raw[];
@@ -267,7 +295,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         bb[j] = __ldg(args.gen_b0 + col) * args.gen_omega;
       }
       uint32_t ig = uint32_t(kb);
-      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ig += C::KB) {
+      for (int t = cta; t < args.num_tiles; t += ncta, ig += C::KB) {
         const uint32_t s = ig % C::SA, ph = (ig / C::SA) & 1u;
         const uint32_t stage = smem_u32(smem + C::OFF_A + s * C::A_STAGE);
         const int r_first = rg + 64 * half;
@@ -340,9 +368,11 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer: B once, then A k-blocks =====================
     if (lane == 0) {
       uint32_t ia = 0;
-      for (int it = blockIdx.x; !GEN && it < num_items; it += gridDim.x) {
+      for (int it = cta; !GEN && it < num_items; it += ncta) {
         const int t = it / NPARTS, part = it % NPARTS;
         const int row = args.a_row0 + t * kRowsPerTile;
+        pace_wait(pace, t);
+        pace_post(pace);
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
           mbar_wait(&a_empty[s], ph ^ 1u);
@@ -353,6 +383,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         part * NDIM);
         }
       }
+      pace_finish(pace);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -360,7 +391,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!C::STREAM_B) mbar_wait(b_full, 0);
       tc_fence_after();
       uint32_t ia = 0, it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      for (int item = cta; item < num_items; item += ncta, ++it) {
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
         SB_DBG_G(4, it, 0);
         mbar_wait(&tm_empty[acc], aph ^ 1u);
@@ -391,7 +422,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue-input producer (MODE_DX only) =====================
     if (MODE == MODE_DX && lane == 0) {
       uint32_t ic = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = cta; item < num_items; item += ncta) {
         const int t = item / NPARTS, part = item % NPARTS;
         const int row = args.e_row0 + t * kRowsPerTile;
         for (int nb = 0; nb < C::NB; ++nb, ++ic) {
@@ -421,7 +452,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // red_full[nb] belongs to this chunk index alone and is waited on once per work item, so its parity
       // cannot alias (a barrier shared between the chunk indices could be probed more than one phase ahead)
       uint32_t ic = uint32_t(nb), il = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ic += C::NB, ++il) {
+      for (int item = cta; item < num_items; item += ncta, ic += C::NB, ++il) {
         const int t = item / NPARTS, part = item % NPARTS;
         // coordinates of rows lane + 32 q (zero for the padding rows: their dz is zero anyway)
         float xh[2], xw[2];
@@ -468,7 +499,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
       }
       constexpr int WFULL = NDIM * NPARTS;
-      float* part_out = args.red_part + (size_t(blockIdx.x) * 2 + half) * 3 * WFULL;
+      float* part_out = args.red_part + (size_t(cta) * 2 + half) * 3 * WFULL;
 #pragma unroll
       for (int pp = 0; pp < NPARTS; ++pp) {
         const int c0 = pp * NDIM + nb * 64 + 2 * lane;
@@ -480,7 +511,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         part_out[2 * WFULL + c0 + 1] = acc[pp][5];
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue: TMEM -> f() -> smem -> TMA store =====================
     const int q = warp & 3;
     const int hb = (warp - 4) >> 2;  // which 32 of the 64 columns of a chunk this warp handles
@@ -488,7 +519,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool issuer = (threadIdx.x == 128);
     const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
     uint32_t it = 0, ic = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    for (int item = cta; item < num_items; item += ncta, ++it) {
       const int t = item / NPARTS, part = item % NPARTS;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       if (issuer) SB_DBG_G(5, it, 0);
@@ -573,6 +604,15 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
+__global__ void __launch_bounds__(GEN ? 544 : (RED ? 640 : 384), 1)
+rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
+               const RowGemmArgs args, const uint32_t idesc) {
+  rowgemm_body<KDIM, NDIM, MODE, OUT_BF16, NPARTS, GEN, RED>(tmA, tmB, tmE, tmO, args, idesc, int(blockIdx.x),
+                                                             int(gridDim.x), PaceCtx{});
+}
+
 // ------------------------------------------------------------------------------------------
 // colgemm: weight-gradient reduction over the pixel dimension (split-K over pixel tiles)
 // ------------------------------------------------------------------------------------------
@@ -617,9 +657,9 @@ struct ColGemmJobs {
 };
 
 template <int NY>
-__global__ void __launch_bounds__(256, 1)
-colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-               const ColGemmJobs jobs, const uint32_t idesc_main, const uint32_t idesc_ones) {
+__device__ __forceinline__ void
+colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& jobs, const uint32_t idesc_main,
+             const uint32_t idesc_ones, const int job, const PaceCtx pace) {
   using C = ColGemmCfg<NY>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -633,7 +673,6 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
 
   // job decode
-  const int job = blockIdx.x;
   const int split = job % jobs.splits;
   const int part = (job / jobs.splits) % jobs.nparts;
   const int mb = (job / (jobs.splits * jobs.nparts)) % jobs.mblocks;
@@ -683,6 +722,8 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int i = 0; i < ntiles; ++i) {
         const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
         const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile;
+        pace_wait(pace, tile_begin + i * tile_step);
+        pace_post(pace);
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], C::STAGE_BYTES);
         uint8_t* st = smem + s * C::STAGE_BYTES;
@@ -693,6 +734,7 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           tma_load_2d(st + (C::XC + c) * kChunkBytes, &tmY, &full[s], part * NY + c * 64,
                       jobs.y_row0[prob] + prow);
       }
+      pace_finish(pace);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -716,7 +758,7 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       umma_commit(done);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
     const int m = mb * 128 + q * 32 + lane;  // output row of this thread
     const size_t slab = size_t(split) * jobs.prob_total + jobs.prob0 + prob;
@@ -764,6 +806,38 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
+
+template <int NY>
+__global__ void __launch_bounds__(256, 1)
+colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+               const ColGemmJobs jobs, const uint32_t idesc_main, const uint32_t idesc_ones) {
+  colgemm_body<NY>(tmX, tmY, jobs, idesc_main, idesc_ones, int(blockIdx.x), PaceCtx{});
+}
+
+// ------------------------------------------------------------------------------------------
+// One backward layer in ONE launch: CTAs [0, dx_ctas) run the dX GEMM of layer l (rowgemm, MODE_DX), the others
+// its weight-gradient reduction (colgemm).  Both roles read dz[l] and act[l-1]; a pace hint (PaceCtx) keeps their
+// sweeps within a window of each other, so every tile comes from HBM once and from L2 the second time — the
+// reduction's 2 x 201 MB per layer never reach HBM (autograd of nn.Linear: grad_input and grad_weight from ONE
+// pass over grad_output, siren.py:62).  pace_counters: two zeroed uint32 (dX, dW) owned by this launch.
+// ------------------------------------------------------------------------------------------
+template <int W, bool RED>
+__global__ void __launch_bounds__(RED ? 640 : 384, 1)
+bwd_merged_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmWt,
+                  const __grid_constant__ CUtensorMap tmAct, const RowGemmArgs rargs, const uint32_t idesc_row,
+                  const ColGemmJobs jobs, const uint32_t idesc_main, const uint32_t idesc_ones, const int dx_ctas,
+                  unsigned int* pace_counters, const int window) {
+  constexpr int NT = W < 256 ? W : 256;
+  constexpr int NPARTS = W / NT;
+  if (int(blockIdx.x) < dx_ctas) {
+    const PaceCtx pc{pace_counters, pace_counters + 1, window, NPARTS, jobs.mblocks * jobs.nparts};
+    rowgemm_body<W, NT, MODE_DX, false, NPARTS, false, RED>(tmDz, tmWt, tmAct, tmDz, rargs, idesc_row,
+                                                            int(blockIdx.x), dx_ctas, pc);
+  } else {
+    const PaceCtx pc{pace_counters + 1, pace_counters, window, jobs.mblocks * jobs.nparts, NPARTS};
+    colgemm_body<NT>(tmDz, tmAct, jobs, idesc_main, idesc_ones, int(blockIdx.x) - dx_ctas, pc);
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // last layer on tensor cores (hidden <= 256, out <= 4): per 128-pixel tile, from ONE read of act[D-2]:

@@ -90,14 +90,36 @@ class Fitter:
                 return False
         return True
 
+    def _fit_args(self):
+        """sirenb200_fit_t over the tables of _prepare_graph (kept alive in self._g)."""
+        g, flat = self._g, self.flat
+        if "fa" not in g:
+            cast = lambda arr: ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))  # noqa: E731
+            sharded = self.world > 1
+            g["fa"] = _lib.FitArgs(
+                n_tensors=g["n"], h_params=cast(g["p"]), h_grads=cast(g["g"]), h_exp_avg=cast(g["m"]),
+                h_exp_avg_sq=cast(g["v"]), h_mask=cast(g["mask"]) if g["mask"] is not None else None,
+                h_numel=g["numel"], beta1=g["beta1"], beta2=g["beta2"], eps=g["eps"],
+                sched_state=g["state"].data_ptr(), stats=flat.stats.data_ptr(), loss_ring=g["ring"].data_ptr(),
+                ring_len=_RING, loss_host=g["host_loss"].data_ptr(),
+                comm=flat.comm.handle if (sharded and flat.comm is not None) else None,
+                flat=flat.flat.data_ptr(), flat_n=flat.flat.numel(),
+                inv_count=self.inv_count if sharded else 0.0)
+        return g["fa"]
+
     def _graph_body(self):
         lib, flat, g = self.engine.lib, self.flat, self._g
-        self.engine.forward_backward(self.model.kernel_parameters(), self.img, flat.views, flat.stats)
-        if self.world > 1:
-            flat.all_reduce(self.group)
         stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.sirenb200_sched_step(g["state"].data_ptr(), flat.stats.data_ptr(),
-                                            self.inv_count if self.world > 1 else 0.0,
+        if self.world == 1 or flat.comm is not None:
+            # one C call: GEMM chain, then ONE kernel for partial reduction + peer exchange + loss + schedule + Adam
+            _lib.check(lib.sirenb200_fit_step(self.engine.handle, self.img.data_ptr(),
+                                              ctypes.byref(self._fit_args()), stream))
+            self.engine.generation += 1
+            return
+        # torch.distributed exchange (a rank could not map a peer's memory): separate launches around NCCL
+        self.engine.forward_backward(self.model.kernel_parameters(), self.img, flat.views, flat.stats)
+        flat.all_reduce(self.group)
+        _lib.check(lib.sirenb200_sched_step(g["state"].data_ptr(), flat.stats.data_ptr(), self.inv_count,
                                             g["ring"].data_ptr(), _RING, g["host_loss"].data_ptr(), stream))
         _lib.check(lib.sirenb200_adam_step_dev(
             g["n"], g["p"], g["g"], g["m"], g["v"], g["mask"], g["numel"], g["beta1"], g["beta2"],
@@ -269,17 +291,8 @@ class Fitter:
                 g["mask_bufs"][w].copy_(self.mask.mask_dict[n])
         self._sync_sched_state()
         step0 = self.optim.param_groups[0].get("_fused_step", 0)
-        cast = lambda arr: ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))  # noqa: E731
         flat = self.flat
-        fa = _lib.FitArgs(
-            n_tensors=g["n"], h_params=cast(g["p"]), h_grads=cast(g["g"]), h_exp_avg=cast(g["m"]),
-            h_exp_avg_sq=cast(g["v"]), h_mask=cast(g["mask"]) if g["mask"] is not None else None,
-            h_numel=g["numel"], beta1=g["beta1"], beta2=g["beta2"], eps=g["eps"],
-            sched_state=g["state"].data_ptr(), stats=flat.stats.data_ptr(), loss_ring=g["ring"].data_ptr(),
-            ring_len=_RING, loss_host=g["host_loss"].data_ptr(),
-            comm=flat.comm.handle if (self.world > 1 and flat.comm is not None) else None,
-            flat=flat.flat.data_ptr(), flat_n=flat.flat.numel(),
-            inv_count=self.inv_count if self.world > 1 else 0.0)
+        fa = self._fit_args()
         if self.world > 1 and flat.comm is None:
             raise _lib.SirenB200Error("native_steps on a sharded fit needs the peer-memory exchange")
         k = min(int(k), _RING)

@@ -188,6 +188,15 @@ typedef struct {
 } sirenb200_fit_t;
 int sirenb200_fit_steps(sirenb200_handle_t h, int32_t k, const float* img, const sirenb200_fit_t* fit,
                         sirenb200_stream_t stream);
+/* One step of the above (what a CUDA-graph capture of a step records).  On a tensor-core handle everything after
+ * the last GEMM is ONE kernel: it reduces the split-K / per-CTA gradient partials into h_grads, sums them over the
+ * ranks through NVLink peer memory when fit->comm is set (block b of every rank exchanges its slice with block b of
+ * every peer; results are bit-identical on all ranks), finalises the loss (stats[0] = sum of squared errors over the
+ * whole image, stats[1] = loss, stats[2] = non-finite flag), advances the device-side schedule and applies Adam
+ * (+ masks) — train_helper.py:151-184 from `loss.backward()` onwards.  SIRENB200_STEP_END=0 (environment) keeps
+ * the separate kernels. */
+int sirenb200_fit_step(sirenb200_handle_t h, const float* img, const sirenb200_fit_t* fit,
+                       sirenb200_stream_t stream);
 
 /* ---- gradient exchange for pixel-sharded fits (SURVEY.md §8e "allreduce_grads") ---------------------------
  * One process per GPU of ONE node.  The reference has no distributed code; this is the exchange step of the

@@ -1,0 +1,184 @@
+"""GPU tests (-m gpu) of the round-2 kernels against the kernels they replace and against the CPU oracle:
+  * bwd_merged_kernel (dX GEMM + weight-gradient reduction of a layer in one launch) vs rowgemm + colgemm
+  * step_end_kernel (partial reduction + loss + schedule + Adam in one launch) vs the five separate kernels
+  * full-image config-2 step and a 60-step config-2 trajectory vs the oracle
+  * depth-8 / hidden-512 (config 3's network) vs the oracle
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import siren_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _pkg():
+    from implicit_image_compression_b200.data import get_grid, synth_image
+    from implicit_image_compression_b200.fit import Fitter
+    from implicit_image_compression_b200.models import Siren
+    from implicit_image_compression_b200.utils import train_helper
+    return get_grid, synth_image, Fitter, Siren, train_helper
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _grads(Siren, get_grid, synth_image, hidden, depth, H, W):
+    torch.manual_seed(0)
+    model = Siren(depth=depth, hidden_size=hidden, first_omega_0=50, hidden_omega_0=30, precision="f16tc").cuda()
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    grads = [torch.empty_like(p) for p in model.hot_parameters()]
+    stats = model.engine_for(grid).forward_backward(model.kernel_parameters(), img, grads)
+    torch.cuda.synchronize()
+    return stats.tolist(), grads
+
+
+@pytest.mark.parametrize("hidden,depth,H,W", [(256, 6, 96, 160), (128, 4, 37, 53), (512, 4, 64, 96), (256, 5, 512, 768)])
+def test_merged_backward_matches_separate_kernels(monkeypatch, hidden, depth, H, W):
+    """Same operands, same MMAs; only the number of pixel splits of the weight gradient (fp32 summation order)
+    differs between the two launch plans."""
+    get_grid, synth_image, _, Siren, _ = _pkg()
+    monkeypatch.setenv("SIRENB200_BWD_MERGED", "1")
+    s1, g1 = _grads(Siren, get_grid, synth_image, hidden, depth, H, W)
+    monkeypatch.setenv("SIRENB200_BWD_MERGED", "0")
+    s0, g0 = _grads(Siren, get_grid, synth_image, hidden, depth, H, W)
+    assert s1[0] == s0[0] and s1[2] == 0.0
+    for i, (a, b) in enumerate(zip(g1, g0)):
+        assert _rel(a, b) <= 2e-6, f"tensor {i}"
+    # dz is bit-identical, so layer 0 (reduced inside the dX role) must be bit-identical when its CTA count is
+    assert _rel(g1[0], g0[0]) <= 2e-6
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_step_end_kernel_matches_separate_kernels(monkeypatch, with_mask):
+    get_grid, synth_image, Fitter, Siren, th = _pkg()
+    H, W = 64, 96
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    cfg = dict(name="RigL", density=0.5, sparse_init="erdos-renyi-kernel", dense_gradients=True,
+               growth_mode="absolute-gradient", prune_mode="magnitude", redistribution_mode="none",
+               dense=False, prune_rate=0.1, decay_schedule="cosine", end_when=100, interval=1000)
+    out = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SIRENB200_STEP_END", fused)
+        torch.manual_seed(0)
+        model = Siren(depth=5, hidden_size=256, first_omega_0=50, hidden_omega_0=30).cuda()
+        optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
+        mask = None
+        if with_mask:
+            torch.manual_seed(7)
+            mask = th.setup_mask(model, optim, cfg)
+        f = Fitter(model, optim, grid, img, sched, mask)
+        losses = f.steps(20).tolist()
+        out.append((losses, [p.detach().clone() for p in model.hot_parameters()],
+                    [p.grad.detach().clone() for p in model.hot_parameters()],
+                    [optim.state[p]["exp_avg_sq"].clone() for p in model.hot_parameters()]))
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=2e-6)
+    for a, b in zip(out[0][1], out[1][1]):
+        assert (a - b).abs().max().item() <= 1e-6
+    for a, b in zip(out[0][2], out[1][2]):
+        assert _rel(a, b) <= 1e-5
+    for a, b in zip(out[0][3], out[1][3]):
+        assert _rel(a, b) <= 1e-5
+    if with_mask:
+        for n, w in mask._masked_parameters():
+            assert torch.equal(w.detach() * mask.mask_dict[n], w.detach())
+
+
+def test_step_end_skips_on_nonfinite_gradient():
+    """A real overflow inside the captured step: the fused kernel raises stats[2] and leaves weights and moments
+    untouched (GradScaler semantics without a scaler object)."""
+    get_grid, synth_image, Fitter, Siren, th = _pkg()
+    H, W = 48, 64
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    torch.manual_seed(0)
+    model = Siren(depth=4, hidden_size=128, first_omega_0=50, hidden_omega_0=30).cuda()
+    optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
+    f = Fitter(model, optim, grid, img, sched)
+    f.steps(3)
+    with torch.no_grad():
+        model.layers[-1].linear.bias.fill_(3.0e38)
+    before = [p.detach().clone() for p in model.hot_parameters()]
+    m_before = [optim.state[p]["exp_avg"].clone() for p in model.hot_parameters()]
+    loss = f.steps(1).tolist()[0]
+    assert not math.isfinite(loss)
+    assert f.flat.stats[2].item() == 1.0
+    assert all(torch.equal(a, b.detach()) for a, b in zip(before, model.hot_parameters()))
+    assert all(torch.equal(a, optim.state[p]["exp_avg"]) for a, p in zip(m_before, model.hot_parameters()))
+
+
+def test_c2_full_image_step_vs_oracle():
+    """ONE full 512x768 step of config 2 against the CPU oracle: loss and every gradient tensor."""
+    get_grid, synth_image, _, Siren, _ = _pkg()
+    H, W = 512, 768
+    torch.manual_seed(0)
+    model = Siren(depth=6, hidden_size=256, first_omega_0=50, hidden_omega_0=30, precision="f16tc")
+    ref = [p.detach().clone() for p in model.parameters()]
+    model = model.cuda()
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    grads = [torch.empty_like(p) for p in model.hot_parameters()]
+    stats = model.engine_for(grid).forward_backward(model.kernel_parameters(), img, grads).tolist()
+    loss_ref, grads_ref = O.siren_loss_and_grads(ref, grid.cpu(), img.cpu(), 50.0, 30.0)
+    assert abs(stats[1] - loss_ref.item()) <= 1e-4 * loss_ref.item()
+    for i, (a, b) in enumerate(zip(grads, grads_ref)):
+        assert _rel(a, b) <= 1e-2, f"gradient {i}: {_rel(a, b):.3e}"
+
+
+def test_c2_sixty_steps_track_the_oracle():
+    """60 fit steps of config 2 (full image) against the CPU oracle's fp32 trajectory (explicit backward + Adam
+    restating train_helper.py:132-185): per-step loss within 3 % for the first 25 steps and within 12 % up to step
+    60 (the trajectories are chaotic; the fp32 reference run twice with different summation
+    order drifts apart at the same rate), PSNR of the fitted weights within 0.3 dB at step 60."""
+    get_grid, synth_image, Fitter, Siren, th = _pkg()
+    H, W, steps = 512, 768, 60
+    torch.manual_seed(0)
+    model = Siren(depth=6, hidden_size=256, first_omega_0=50, hidden_omega_0=30, precision="f16tc")
+    params = [p.detach().clone() for p in model.parameters()]
+    model = model.cuda()
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
+    got = Fitter(model, optim, grid, img, sched).steps(steps).tolist()
+    gc, ic = grid.cpu(), img.cpu()
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    want = []
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    for s in range(1, steps + 1):
+        loss, grads = O.siren_loss_and_grads(params, gc, ic, 50.0, 30.0)
+        want.append(loss.item())
+        for i in range(len(params)):
+            params[i], m[i], v[i] = O.adam_step(params[i], grads[i], m[i], v[i], s, 3e-4)
+    rel = [abs(a - b) / b for a, b in zip(got, want)]
+    print("max rel loss error, steps 1-25:", max(rel[:25]), " steps 26-60:", max(rel[25:]))
+    assert max(rel[:25]) <= 3e-2
+    assert max(rel[25:]) <= 1.2e-1
+    pred_ref = O.siren_forward(params, gc, 50.0, 30.0)
+    psnr_ref = 10 * math.log10(1 / torch.mean((pred_ref - ic) ** 2).item())
+    psnr = th.eval_epoch(model, grid, img)[2]
+    print("PSNR at step 60: f16tc", psnr, "oracle", psnr_ref)
+    assert abs(psnr - psnr_ref) <= 0.3
+
+
+def test_depth8_hidden512_vs_oracle():
+    """Config 3's network (depth 8, hidden 512) on a small image: forward, loss, gradients vs the oracle."""
+    get_grid, synth_image, _, Siren, th = _pkg()
+    H, W = 56, 72
+    torch.manual_seed(0)
+    model = Siren(depth=8, hidden_size=512, first_omega_0=50, hidden_omega_0=30, precision="f16tc")
+    ref = [p.detach().clone() for p in model.parameters()]
+    model = model.cuda()
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    with torch.no_grad():
+        pred = model(grid)
+    want = O.siren_forward(ref, grid.cpu(), 50.0, 30.0)
+    assert (pred.cpu() - want).abs().max().item() <= 1e-3
+    grads = [torch.empty_like(p) for p in model.hot_parameters()]
+    stats = model.engine_for(grid).forward_backward(model.kernel_parameters(), img, grads).tolist()
+    loss_ref, grads_ref = O.siren_loss_and_grads(ref, grid.cpu(), img.cpu(), 50.0, 30.0)
+    assert abs(stats[1] - loss_ref.item()) <= 2e-4 * loss_ref.item()
+    for i, (a, b) in enumerate(zip(grads, grads_ref)):
+        assert _rel(a, b) <= 1.5e-2, f"gradient {i}: {_rel(a, b):.3e}"

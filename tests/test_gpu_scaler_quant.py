@@ -44,7 +44,7 @@ def test_gradscaler_real_overflow_matches_torch(precision, hidden):
     ref_scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 16, growth_interval=3)
     optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
     scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 16, growth_interval=3)
-    tol = 1e-5 if precision == "fp32" else 2e-2
+    tol = 1e-5 if precision == "fp32" else 3e-2
 
     def ref_step():
         ref_opt.zero_grad()
