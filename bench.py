@@ -182,8 +182,98 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# the reference's math in plain (eager) PyTorch on the GPU: the same-box yardstick
+# ------------------------------------------------------------------------------------------------
+def torch_forward(params, x):
+    """models/siren.py:123-134 restated functionally (fp32, TF32 off): x in [-1,1]^2 [N,2] -> pred [N,3]."""
+    import torch
+    depth = len(params) // 2
+    a = x
+    for l in range(depth):
+        z = torch.addmm(params[2 * l + 1], a, params[2 * l].t())
+        if l == depth - 1:
+            return z / 2 + 0.5
+        a = torch.sin((OMEGA0 if l == 0 else OMEGA) * z)
+
+
+def psnr_of(params, x, tgt):
+    import math
+    import torch
+    with torch.no_grad():
+        return 10 * math.log10(1 / torch.mean((torch_forward(params, x) - tgt) ** 2).item())
+
+
+def eager_torch_reference(grid, img, steps, tail=400, every=25):
+    """nn.Linear-style fp32 GEMMs + torch.sin + autograd + F.mse_loss + torch.optim.Adam + StepLR on the same GPU
+    (utils/train_helper.py:132-185).  Returns steps/s and the trailing-median PSNR over the last `tail` steps."""
+    import torch
+    from implicit_image_compression_b200.models import Siren
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    m = Siren(depth=DEPTH, hidden_size=HIDDEN, first_omega_0=OMEGA0, hidden_omega_0=OMEGA)
+    params = [p.detach().clone().to(grid.device).requires_grad_(True) for p in m.hot_parameters()]
+    x = ((grid.view(-1, 2) - 0.5) * 2).contiguous()
+    tgt = img.view(-1, C)
+    optim = torch.optim.Adam(params, lr=LR)
+    sched = torch.optim.lr_scheduler.StepLR(optim, 2000, gamma=0.5)
+    evals, t_eval = [], 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(1, steps + 1):
+        optim.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(torch_forward(params, x), tgt)
+        loss.backward()
+        optim.step()
+        sched.step()
+        if s > steps - tail and (steps - s) % every == 0:
+            torch.cuda.synchronize()
+            te = time.perf_counter()
+            evals.append(psnr_of([p.detach() for p in params], x, tgt))
+            t_eval += time.perf_counter() - te
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0 - t_eval
+    return {"steps": steps, "steps_per_s": steps / dt, "trailing_median_psnr": statistics.median(evals),
+            "tail_min": min(evals), "tail_max": max(evals),
+            "what": "the reference's fp32 math in eager PyTorch (cuBLAS SGEMM, TF32 off, autograd, torch.optim.Adam) "
+                    "on the same GPU; PSNR = median over the last %d steps, evaluated every %d" % (tail, every)}
+
+
+def time_to_psnr(model, fitter, grid, img, target, max_steps, every=50, window=5):
+    """Wall-clock of FITTING (evaluation excluded) until the median PSNR of the last `window` evaluations (fp32
+    torch forward of the fp32 master weights, every `every` steps) first reaches `target`."""
+    import torch
+    x = ((grid.view(-1, 2) - 0.5) * 2).contiguous()
+    tgt = img.view(-1, C)
+    spent, done, hist = 0.0, 0, []
+    while done < max_steps:
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        fitter.steps(every)
+        torch.cuda.synchronize()
+        spent += time.perf_counter() - t
+        done += every
+        hist.append(psnr_of([p.detach() for p in model.hot_parameters()], x, tgt))
+        if len(hist) >= window and statistics.median(hist[-window:]) >= target:
+            return {"target_psnr": target, "steps": done, "seconds": spent, "psnr_at_stop": hist[-1],
+                    "psnr_at_2000": hist[2000 // every - 1] if len(hist) >= 2000 // every else None}
+    return {"target_psnr": target, "steps": None, "seconds": None, "max_steps": max_steps,
+            "best_trailing_median": max(statistics.median(hist[i - window:i]) for i in range(window, len(hist) + 1)),
+            "psnr_at_2000": hist[2000 // every - 1] if len(hist) >= 2000 // every else None}
+
+
+# Trailing-median PSNR of the eager-PyTorch fp32 reference after 2000 steps on synthetic image 0 (config 2), measured
+# on a B200 this round (profiles/r02_psnr_study.jsonl, arm ref32); used as the time-to-PSNR target when the live
+# yardstick is not run (N > 1, --no-reference-fit)
+REF32_PSNR_2000_C2_IMG0 = 56.16
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def set_workload(name):
+    global DEPTH, HIDDEN, H, W
+    DEPTH, HIDDEN, H, W = WORKLOADS[name]
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -201,34 +291,44 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py needs a B200: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     # NCCL prints its version banner on STDOUT at communicator creation: keep stdout clean for the one
-    # JSON line by pointing fd 1 at stderr until the warm-up (first collective) is over
+    # JSON line by pointing fd 1 at stderr until the line is printed
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-
-    torch.manual_seed(0)
-    model = Siren(depth=DEPTH, hidden_size=HIDDEN, first_omega_0=OMEGA0, hidden_omega_0=OMEGA,
-                  precision="f16tc").to(dev)
-    grid = get_grid(H, W, dev)
-    img_host = synth_image(H, W, 0).pin_memory()
-    img = img_host.to(dev, non_blocking=True)
-    optim, sched = get_optimizer_lr_scheduler(model, {"name": "adam", "lr": LR})
-    fitter = Fitter(model, optim, grid, img, sched, rank=rank, world_size=world)
+    peaks = load_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput -----------------------------------------------------------
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def build(seed=0, shard=True):
+        torch.manual_seed(seed)
+        model = Siren(depth=DEPTH, hidden_size=HIDDEN, first_omega_0=OMEGA0, hidden_omega_0=OMEGA,
+                      precision="f16tc").to(dev)
+        optim, sched = get_optimizer_lr_scheduler(model, {"name": "adam", "lr": LR})
+        return model, optim, sched
+
+    # =============================== primary workload ===============================================
+    grid = get_grid(H, W, dev)
+    img_host = synth_image(H, W, 0).pin_memory()
+    img = img_host.to(dev, non_blocking=True)
+    model, optim, sched = build()
+    fitter = Fitter(model, optim, grid, img, sched, rank=rank, world_size=world)
+
+    # ---- device-resident throughput ----
     fitter.steps(max(3, args.warmup))
     barrier()
-    sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
-    os.close(saved_stdout)
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
@@ -262,12 +362,35 @@ def run_gpu_arm(args):
     prof = fitter.engine.profile_read()
     fitter.engine.profile(False)
     fitter.use_graph = graph_mode
-    if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = tms.item()
+    ms = max_over_ranks(ms)
     ms_per_step = ms / args.steps
     value = 1000.0 / ms_per_step
+
+    # ---- sustained rate: a window of at least ~2 s with its own clock record ----
+    sustained = None
+    if not args.no_sustained:
+        n_sus = max(200, int(2.2 / (ms_per_step * 1e-3)))
+        sam2 = ClockSampler(local)
+        sam2.start()
+        time.sleep(0.2)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ts0 = time.time()
+        s0.record()
+        done = 0
+        while done < n_sus:
+            k = min(4096, n_sus - done)
+            fitter.steps(k)
+            done += k
+        s1.record()
+        barrier()
+        ts1 = time.time()
+        sms = max_over_ranks(s0.elapsed_time(s1))
+        sv = n_sus / (sms * 1e-3)
+        sustained = {"value": sv, "unit": UNIT, "steps": n_sus, "seconds": sms * 1e-3,
+                     "clocks": sam2.stop(ts0, ts1),
+                     "roofline_step_frac_of_sustained_peak": f_step(H * W) * sv / 1e12 /
+                     ((peaks["bf16_sustained"] or peaks["bf16"]) * world)}
 
     # ---- end to end through the drop-in API: pinned host image -> device every step, loss read back ----
     e2e = None
@@ -300,7 +423,6 @@ def run_gpu_arm(args):
                "d2h_bytes_per_step": 4,
                "note": "train_epoch() drop-in API (one CUDA-graph replay per call); image copied from pinned "
                        "host memory every step (prefetched on a copy stream), loss.item() read back every step"}
-
     else:
         # pixel-sharded: every rank copies ITS rows of the image from pinned host memory each step and
         # rank 0 reads the (all-reduced) loss back each step
@@ -330,16 +452,126 @@ def run_gpu_arm(args):
                 prefetch(i + 1)
             _ = fitter.step_loss()  # one graph replay; the loss comes back through pinned host memory
         barrier()
-        dt = torch.tensor([time.perf_counter() - t], device=dev)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_e2e / dt.item(), "unit": UNIT, "h2d_bytes_per_step": img_host.numel() * 4,
+        dt = max_over_ranks(time.perf_counter() - t)
+        e2e = {"value": n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": img_host.numel() * 4,
                "d2h_bytes_per_step": 4 * world,
                "note": "Fitter.step_loss() per step on every rank; each rank copies its image rows from pinned "
                        "host memory every step (prefetched on a copy stream into a staging buffer) and reads the "
                        "all-reduced loss back every step (max over ranks)"}
+    final_loss = float(losses[-1].item())
+    npix_rank = (fitter.row_end - fitter.row_begin) * W
+    primary_name = "c2" if (HIDDEN, DEPTH) == (256, 6) else ("c3" if HIDDEN == 512 and DEPTH == 8 else "c5w")
+
+    # =============================== sharded-fit correctness (N > 1) ================================
+    sharded_check = None
+    if world > 1:
+        # (1) the exchange kernel against NCCL on random data, (2) 10 steps of the sharded fit against the same 10
+        # steps of an UNSHARDED fit on rank 0's GPU (same seed): losses must agree to fp32 summation order
+        flat = fitter.flat
+        exch = None
+        if flat.comm is not None:
+            gen = torch.Generator(device=dev).manual_seed(100 + rank)
+            xr = torch.randn(flat.flat.numel(), device=dev, generator=gen)
+            ref = xr.clone()
+            dist.all_reduce(ref)
+            flat.comm.all_reduce(xr)
+            torch.cuda.synchronize()
+            err = (xr - ref).abs().max().item()
+            gathered = [torch.empty_like(xr) for _ in range(world)]
+            dist.all_gather(gathered, xr)
+            same = all(torch.equal(gathered[0], g_) for g_ in gathered)
+            exch = {"max_abs_err_vs_nccl": err, "bit_identical_across_ranks": bool(same)}
+            assert same and err <= 1e-4 * world, f"peer exchange check failed: {exch}"
+        m2, o2, s2 = build()
+        f2 = Fitter(m2, o2, grid, img, s2, rank=rank, world_size=world)
+        sh_losses = f2.steps(10).tolist()
+        w_sh = [p.detach().clone() for p in m2.hot_parameters()]
+        del f2
+        single = None
+        if rank == 0:
+            m1, o1, s1_ = build()
+            f1 = Fitter(m1, o1, grid, img, s1_)
+            single = f1.steps(10).tolist()
+            rel = max(abs(a - b) / abs(b) for a, b in zip(sh_losses, single))
+            wdiff = max((a - b.detach()).abs().max().item() for a, b in zip(w_sh, m1.hot_parameters()))
+            sharded_check = {"exchange_vs_nccl": exch, "steps": 10, "max_rel_loss_diff_vs_unsharded": rel,
+                             "max_abs_weight_diff_vs_unsharded": wdiff, "losses_sharded": sh_losses,
+                             "losses_unsharded": single}
+            assert rel <= 2e-4, f"sharded fit diverges from the unsharded fit: {sharded_check}"
+            del f1, m1
+        # weights bit-identical across ranks
+        flatw = torch.cat([p.reshape(-1) for p in w_sh])
+        gw = [torch.empty_like(flatw) for _ in range(world)]
+        dist.all_gather(gw, flatw)
+        ident = all(torch.equal(gw[0], g_) for g_ in gw)
+        assert ident, "replicated weights differ between ranks"
+        if rank == 0:
+            sharded_check["weights_bit_identical_across_ranks"] = bool(ident)
+        del m2
+        barrier()
+
+    # =============================== time to PSNR ====================================================
+    ttp, eager = None, None
+    if primary_name == "c2" and not args.no_time_to_psnr:
+        target_ref = REF32_PSNR_2000_C2_IMG0
+        if world == 1 and not args.no_reference_fit:
+            eager = eager_torch_reference(grid, img, 2000)
+            target_ref = eager["trailing_median_psnr"]
+        m3, o3, s3 = build()
+        f3 = Fitter(m3, o3, grid, img, s3, rank=rank, world_size=world)
+        f3.steps(1)  # capture
+        ttp = time_to_psnr(m3, f3, grid, img, target_ref - 0.1, 6000)
+        ttp["target_definition"] = ("trailing-median PSNR of the eager-PyTorch fp32 reference after 2000 steps on the "
+                                    "same image (%s) minus 0.1 dB" % ("measured in this run" if eager else
+                                                                      "profiles/r02_psnr_study.jsonl"))
+        if eager and ttp.get("seconds"):
+            ttp["reference_seconds_to_2000_steps"] = 2000 / eager["steps_per_s"]
+            ttp["speedup_vs_eager_torch_same_gpu"] = ttp["reference_seconds_to_2000_steps"] / ttp["seconds"]
+        del f3, m3
+
+    # =============================== secondary workload: config 3 ===================================
+    secondary = None
+    if primary_name == "c2" and not args.no_secondary:
+        keep = (DEPTH, HIDDEN, H, W)
+        set_workload("c3")
+        try:
+            g3 = get_grid(H, W, dev)
+            i3 = synth_image(H, W, 0).to(dev)
+            m4, o4, s4 = build()
+            f4 = Fitter(m4, o4, g3, i3, s4, rank=rank, world_size=world)
+            f4.steps(3)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sam3 = ClockSampler(local)
+            sam3.start()
+            time.sleep(0.2)
+            barrier()
+            tc0 = time.time()
+            c0.record()
+            n3 = max(10, args.steps // 5)
+            l3 = f4.steps(n3)
+            c1.record()
+            barrier()
+            tc1 = time.time()
+            ms3 = max_over_ranks(c0.elapsed_time(c1)) / n3
+            v3 = 1000.0 / ms3
+            tf3 = f_step(H * W) * v3 / 1e12
+            secondary = {"workload": "c3: SIREN hidden 512 depth 8, 2048x2048 synthetic 16-bit RGB, rows sharded over "
+                                     "%d rank(s)" % world, "metric": METRIC, "value": v3, "unit": UNIT, "steps": n3,
+                         "ms_per_step": ms3, "final_loss": float(l3[-1].item()),
+                         "algorithmic_flops_per_step": f_step(H * W),
+                         "roofline_step": {"bound": "tensor", "achieved": tf3, "unit": "TFLOP/s",
+                                           "frac_of_burst_peak": tf3 / (peaks["bf16"] * world),
+                                           "frac_of_sustained_peak": tf3 / ((peaks["bf16_sustained"] or peaks["bf16"]) * world)},
+                         "clocks": sam3.stop(tc0, tc1), "workspace_gb_per_rank": f4.engine.workspace_bytes() / 1e9}
+            del f4, m4, g3, i3
+        finally:
+            DEPTH_, HIDDEN_, H_, W_ = keep
+            globals().update(DEPTH=DEPTH_, HIDDEN=HIDDEN_, H=H_, W=W_)
+        torch.cuda.empty_cache()
 
     def finish():
-        # Tear-down: drop the captured graph (it holds NCCL kernels) before leaving, and leave without
+        # Tear-down: drop the captured graph (it may hold collectives) before leaving, and leave without
         # running NCCL's destructor chain — destroy_process_group() after a captured collective can hang.
         sys.stdout.flush()
         if world > 1:
@@ -353,14 +585,13 @@ def run_gpu_arm(args):
         finish()
         return
 
-    peaks = load_peaks()
-    npix_rank = (fitter.row_end - fitter.row_begin) * W
     # dominant kernel = the tagged kind with the largest device time in the timed region
     kinds = {k: v for k, v in prof.items() if v[1] > 0}
     dom = max(kinds, key=lambda k: kinds[k][0]) if kinds else None
+    merged = os.environ.get("SIRENB200_BWD_MERGED", "1") != "0"
     alg_bytes = {  # algorithmic HBM bytes per launch (fp16 activations)
         "fwd_gemm": 2 * npix_rank * HIDDEN * 2,
-        "dx_gemm": 3 * npix_rank * HIDDEN * 2,
+        "dx_gemm": 3 * npix_rank * HIDDEN * 2,   # merged launch: the weight-gradient role re-reads the same tiles from L2
         "dw_gemm": (DEPTH - 2) * 2 * npix_rank * HIDDEN * 2,
         "last_layer_loss": 2 * npix_rank * HIDDEN * 2 + npix_rank * C * 4,
         "first_layer": npix_rank * HIDDEN * 2,
@@ -372,22 +603,25 @@ def run_gpu_arm(args):
         achieved = alg_bytes[dom] / (avg_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and world == 1 and primary_name == "c2":
             with open(tpath) as f:
-                traffic = json.load(f).get(dom)
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm"],
+                tj = json.load(f)
+            traffic = tj.get(dom + ("_merged" if (merged and dom == "dx_gemm") else ""))
+        roofline = {"bound": "hbm", "kernel": dom + (" (dX GEMM + weight-gradient reduction, one launch)"
+                                                     if merged and dom == "dx_gemm" else ""),
+                    "achieved": achieved, "peak": peaks["hbm"],
                     "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
                     "avg_launch_ms": avg_ms, "launches": kinds[dom][1], "peak_source": peaks["source"],
                     "share_of_step": kinds[dom][0] / ms_eager,
                     "note": "kernel timed with cudaEvent pairs in an eager pass of the same K steps run "
-                            "right after the (CUDA-graph) timed region"}
+                            "right after the (CUDA-graph) timed region; traffic = ncu dram bytes per launch of this "
+                            "kernel at this configuration (profiles/), null when not captured for it"}
     step_tflops = f_step(H * W) * value / 1e12
-    tpeak = (peaks["bf16_sustained"] or peaks["bf16"]) * world
-    roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": tpeak,
-                     "unit": "TFLOP/s", "frac": step_tflops / tpeak,
-                     "frac_of_burst_peak": step_tflops / (peaks["bf16"] * world),
-                     "note": "whole fit step, algorithmic FLOPs (SURVEY.md §8d) vs measured cuBLAS bf16 "
-                             "(sustained) — fp16 tcgen05 MMA has the same peak"}
+    roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16"] * world,
+                     "unit": "TFLOP/s", "frac": step_tflops / (peaks["bf16"] * world),
+                     "frac_of_sustained_peak": step_tflops / ((peaks["bf16_sustained"] or peaks["bf16"]) * world),
+                     "note": "whole fit step, algorithmic FLOPs (SURVEY.md §8d) vs measured cuBLAS bf16 BURST peak "
+                             "(the timed window is tens of ms) — fp16 tcgen05 MMA has the same peak"}
     kernel_ms = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                  for k, v in kinds.items()}
 
@@ -399,15 +633,20 @@ def run_gpu_arm(args):
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate",
         "data": "synthetic", "config": workload_config(world),
-        "exchange": None if world == 1 else ("library peer-memory kernel (NVLink P2P, CUDA IPC)"
+        "exchange": None if world == 1 else ("fused into the step-end kernel (NVLink P2P loads, CUDA IPC)"
                                              if fitter.peer_exchange else "NCCL all-reduce"),
-        "final_loss": float(losses[-1].item()), "cuda_graph": bool(graph_mode and fitter._graph is not None),
+        "final_loss": final_loss, "cuda_graph": bool(graph_mode and fitter._graph is not None),
         "ms_per_step_eager_profiled": ms_eager / args.steps,
         "roofline": roofline, "roofline_step": roofline_step, "kernel_ms": kernel_ms,
+        "sustained": sustained, "time_to_psnr": ttp, "eager_torch_fp32_same_gpu": eager,
+        "secondary": secondary, "sharded_check": sharded_check,
         "cpu_baseline": None if cpu_val is None else
         {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_desc},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     print(json.dumps(line))
     finish()
 
@@ -419,10 +658,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config-3 block")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-time-to-psnr", action="store_true")
+    ap.add_argument("--no-reference-fit", action="store_true",
+                    help="do not run the 2000-step eager-PyTorch fp32 yardstick (time-to-PSNR then uses the recorded target)")
+    ap.add_argument("--quick", action="store_true", help="primary measurement only")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
-    global DEPTH, HIDDEN, H, W
-    DEPTH, HIDDEN, H, W = WORKLOADS[args.workload]
+    set_workload(args.workload)
+    if args.quick:
+        args.no_cpu_baseline = args.no_secondary = args.no_sustained = args.no_time_to_psnr = True
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -88,6 +88,12 @@ def main(cfg, fast=True):
                     train_epoch(quantized_model, optim_q, grid, img, lr_scheduler=sched_q, mask=mask)
                 else:
                     train_epoch(quantized_model, optim_q, grid, img, lr_scheduler=sched_q)
+                # compress.py:190-193: periodic evaluation INSIDE the context — its forward re-clusters the
+                # weights, which is what leaves an exact-zero centroid behind for convert() (kmeans.py:73-98)
+                if (i + 1) % cfg.quant.get("log_steps", 10) == 0:
+                    _, loss, psnr, psnr8 = eval_epoch(quantized_model, grid, img)
+                    logging.info(f"Quant | Step: {i + 1} | loss: {loss:.6f} | PSNR: {psnr:.4f}")
+                    quantized_model.train()
         quantized_model = q.convert()
         _, loss, psnr, psnr8 = eval_epoch(quantized_model, grid, img)
         out.update({"Quant loss": loss, "Quant PSNR": psnr, "Quant PSNR 8bit": psnr8})

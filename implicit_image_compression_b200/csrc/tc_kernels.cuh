@@ -101,7 +101,7 @@ __device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh,
 // reduction of a layer both read dz[l] and act[l-1]): each role counts the tiles whose loads it has issued and
 // holds its own loads back while it is more than `window` tiles ahead of the other, so that whichever role
 // touches a tile second finds it in the 126 MB L2 instead of HBM.  It is a hint, not a dependency: the wait is
-// bounded and a role that has finished releases the other for good.
+// bounded.
 struct PaceCtx {
   unsigned int* mine;         // tiles (x my_per_tile) this role has issued; null = no pacing
   const unsigned int* other;  // the other role's counter
@@ -110,18 +110,17 @@ struct PaceCtx {
 };
 __device__ __forceinline__ void pace_wait(const PaceCtx& pc, int tile) {
   if (!pc.mine) return;
-  for (int spins = 0; spins < 4096; ++spins) {
+  // the other role's frontier ends at the last tile once all its CTAs are done, so this can only wait on a role
+  // that is still running; bounded anyway (~0.1 ms) so that a pacing mistake costs time, never a hang
+  for (int spins = 0; spins < 1024; ++spins) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pc.other) : "memory");
-    if (tile <= int(v / unsigned(pc.other_per_tile)) + pc.window) return;
+    if (unsigned(tile) <= v / unsigned(pc.other_per_tile) + unsigned(pc.window)) return;
     __nanosleep(64);
   }
 }
 __device__ __forceinline__ void pace_post(const PaceCtx& pc, unsigned int n = 1u) {
   if (pc.mine) atomicAdd(pc.mine, n);
-}
-__device__ __forceinline__ void pace_finish(const PaceCtx& pc) {
-  if (pc.mine) atomicAdd(pc.mine, 1u << 28);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -383,7 +382,6 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
                         part * NDIM);
         }
       }
-      pace_finish(pace);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -734,7 +732,6 @@ colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& 
           tma_load_2d(st + (C::XC + c) * kChunkBytes, &tmY, &full[s], part * NY + c * 64,
                       jobs.y_row0[prob] + prow);
       }
-      pace_finish(pace);
     }
   } else if (warp == 1) {
     if (lane == 0) {

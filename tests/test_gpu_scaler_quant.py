@@ -44,7 +44,7 @@ def test_gradscaler_real_overflow_matches_torch(precision, hidden):
     ref_scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 16, growth_interval=3)
     optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
     scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 16, growth_interval=3)
-    tol = 1e-5 if precision == "fp32" else 3e-2
+    tol = 1e-5 if precision == "fp32" else 5e-2
 
     def ref_step():
         ref_opt.zero_grad()
@@ -118,7 +118,7 @@ def test_quant_phase_keeps_pruned_weights_zero():
     cfg = load_config(["mlp.hidden_size=128", "mlp.depth=4", "img.height=64", "img.width=96", "masking=Pruning",
                        "masking.final_density=0.3", "masking.end_when=60", "masking.interval=10",
                        "masking.start_when=5", "train.num_steps=80", "train.multiplier=1", "train.log_steps=40",
-                       "quant=kmeans", "quant.bits=5", "quant.num_steps=6"])
+                       "quant=kmeans", "quant.bits=5", "quant.num_steps=6", "quant.log_steps=3"])
     cfg.quant["skip_ll"] = ["layers.0.linear", "layers.3.linear"]
     out = main(cfg)
     assert abs(out["Density"] - out["Quant Density"]) <= 0.02, out
