@@ -118,16 +118,6 @@ struct sirenb200_plan {
   int dw_ctas = 0;             // CTAs of that launch that run the reduction
   int merged_splits = 0;       // pixel splits of the reduction role
   int pace_window = 192;       // tiles the two roles may drift apart
-  // chained backward (one launch for all hidden layers, tile flags through L2)
-  bool bwd_chain = false;
-  ChainTable* chain_tab = nullptr;      // device
-  ChainTable* chain_host = nullptr;     // host copy (rebuilt when the grid binding changes)
-  unsigned int* chain_flags = nullptr;  // [nh][flag_stride]
-  unsigned int* chain_state = nullptr;  // [0] launches completed, [1] CTAs done
-  int chain_dx = 0, chain_dw = 0;       // CTAs per layer of the two roles
-  int chain_splits = 0;
-  int chain_l0_rows = 0;
-  bool chain_dirty = true;
   bool defer_reduce = false;   // transient: tc_run leaves the partial reduction to the fused step-end kernel
   unsigned long long* bar = nullptr;  // grid-barrier counter of step_end_kernel
 
@@ -493,111 +483,6 @@ int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const fl
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------
-// chained backward: role table (static per handle; rebuilt when the grid binding changes)
-// ---------------------------------------------------------------------------------------
-int chain_build(sirenb200_plan* p) {
-  if (!p->bwd_chain) return 0;
-  static_assert(kChainMaxLayers == kMaxLayers, "layer limits");
-  const int W = p->W, nh = p->D - 2;
-  const int NT = W < 256 ? W : 256, NPARTS = W / NT;
-  ChainTable& t = *p->chain_host;
-  memset(&t, 0, sizeof(t));
-  t.tm_dz = p->tm_dz;
-  t.tm_act = p->tm_act;
-  for (int l = 0; l < nh; ++l) t.tm_wt[l] = p->tm_wt[l];
-  t.flag_stride = p->ntiles;
-  int nr = 0, cta0 = 0;
-  const int splits = p->chain_dw / ((W / 128) * NPARTS);
-  for (int l = nh; l >= 1; --l) {
-    ChainRole& dx = t.role[nr++];
-    dx.kind = (l == 1) ? 1 : 0;
-    dx.layer = l;
-    dx.cta0 = cta0;
-    dx.ncta = p->chain_dx;
-    cta0 += dx.ncta;
-    dx.wait_idx = l < nh ? l : -1;
-    dx.post_idx = l >= 2 ? l - 1 : -1;
-    dx.parts = NPARTS;
-    RowGemmArgs& ra = dx.row;
-    ra.num_tiles = p->ntiles;
-    ra.a_row0 = int(l * p->npix_pad);
-    ra.e_row0 = int((l - 1) * p->npix_pad);
-    ra.o_row0 = int((l - 1) * p->npix_pad);
-    ra.valid_rows = int(p->npix);
-    ra.b_early = 1;
-    if (l == 1) {
-      ra.gen_coord = p->coord;
-      ra.gen_coord.p_offset = 0;
-      ra.red_part = p->l0_part;
-    }
-    ChainRole& dw = t.role[nr++];
-    dw.kind = 2;
-    dw.layer = l;
-    dw.cta0 = cta0;
-    dw.ncta = p->chain_dw;
-    cta0 += dw.ncta;
-    dw.wait_idx = l < nh ? l : -1;
-    dw.post_idx = -1;
-    dw.parts = NPARTS;
-    ColGemmJobs& jobs = dw.col;
-    jobs.num_problems = 1;
-    jobs.mblocks = W / 128;
-    jobs.nparts = NPARTS;
-    jobs.splits = splits;
-    jobs.tile0 = 0;
-    jobs.tiles_total = p->ntiles;
-    jobs.tiles_per_split = cdiv(p->ntiles, splits);
-    jobs.accumulate = 0;
-    jobs.x_row0[0] = int(l * p->npix_pad);
-    jobs.y_row0[0] = int((l - 1) * p->npix_pad);
-    jobs.dw_partial = p->dw_part;
-    jobs.db_partial = p->db_part;
-    jobs.nx = W;
-    jobs.ny_total = W;
-    jobs.prob0 = l - 1;
-    jobs.prob_total = nh;
-    jobs.interleave = 1;
-    // the dX role's pace hint needs the reduction role's jobs-per-tile: same for every layer
-    dx.col.mblocks = jobs.mblocks;
-    dx.col.nparts = jobs.nparts;
-  }
-  t.nroles = nr;
-  CUDA_TRY(cudaDeviceSynchronize());
-  CUDA_TRY(cudaMemcpy(p->chain_tab, &t, sizeof(t), cudaMemcpyHostToDevice));
-  p->chain_dirty = false;
-  return 0;
-}
-
-template <int W>
-int launch_bwd_chain(sirenb200_plan* p, cudaStream_t st) {
-  constexpr int NT = W < 256 ? W : 256;
-  constexpr int NPARTS = W / NT;
-  using RCfg = RowGemmCfg<W, NT, MODE_DX, NPARTS>;
-  using CCfg = ColGemmCfg<NT>;
-  constexpr uint32_t SMEM = RCfg::SMEM_BYTES > CCfg::SMEM_BYTES ? RCfg::SMEM_BYTES : CCfg::SMEM_BYTES;
-  auto kfn = bwd_chain_kernel<W>;
-  static bool attr_set[64] = {};
-  if (!attr_set[p->device & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)));
-    attr_set[p->device & 63] = true;
-  }
-  if (p->chain_dirty) {
-    int rc = chain_build(p);
-    if (rc) return rc;
-  }
-  const int nh = p->D - 2;
-  const int grid = nh * (p->chain_dx + p->chain_dw);
-  {
-    ProfScope ps(p, PK_DX_GEMM, st);
-    launch_ex(kfn, dim3(grid), dim3(640), SMEM, st, p->pdl && !p->prof_on, static_cast<const ChainTable*>(p->chain_tab),
-              p->chain_flags, p->chain_state, p->pace, p->pace_window);
-  }
-  LAUNCH_CHECK();
-  p->l0_used = 2 * p->chain_dx;
-  return 0;
-}
-
 // one backward layer: dX GEMM of layer l (CTAs [0, dx)) + its weight-gradient reduction (the rest), one launch
 template <int W, bool RED>
 int launch_bwd_merged(sirenb200_plan* p, const RowGemmArgs& ra, const ColGemmJobs& jobs, int l, cudaStream_t st) {
@@ -653,10 +538,6 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
   };
   const bool fuse_l0 = p->fuse_l0 && nh >= 1 && p->nchunks == 1;
   const bool merged = p->bwd_merged && p->dw_ctas > 0 && p->nchunks == 1;
-  if (p->bwd_chain && p->nchunks == 1) {
-    (void)prm;
-    return launch_bwd_chain<W>(p, st);
-  }
   // dZ chain: dz[l-1] = (dz[l] * omega_{l-1} W_l) .* cos(...)
   for (int l = nh; l >= 1; --l) {
     RowGemmArgs ra{};
@@ -1092,12 +973,12 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     if (splits > p->ntiles) splits = p->ntiles;
     p->col_splits = splits;  // (re-clamped to the chunk size below)
     {
-      // merged dX + dW launches: the reduction role gets ~35 % of the SMs (measured best at config 2: 52 of 148) (its MMA time per tile is ~2/5 of the
+      // merged dX + dW launches: the reduction role gets ~30 % of the SMs (its MMA time per tile is ~2/5 of the
       // dX role's epilogue-bound time, and its loads come from L2), as (W/128 row blocks) x (column parts) x splits
       const char* env = getenv("SIRENB200_BWD_MERGED");
       p->bwd_merged = nh > 0 && !(env && atoi(env) == 0);
       const int per_split = (W / 128) * (W / (W < 256 ? W : 256));
-      int want = (p->nsm * 35) / 100;
+      int want = (p->nsm * 30) / 100;
       env = getenv("SIRENB200_DW_CTAS");
       if (env && atoi(env) > 0) want = atoi(env);
       int ms = want / per_split;
@@ -1109,31 +990,13 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       if (env && atoi(env) > 0) p->pace_window = atoi(env);
       if (p->bwd_merged) p->merged_splits = ms;
     }
-    {
-      // chained backward: ONE launch for all hidden layers; per layer nsm/nh CTAs, ~38 % of them for the
-      // weight-gradient role (SIRENB200_BWD_CHAIN=0: per-layer launches)
-      const char* env = getenv("SIRENB200_BWD_CHAIN");
-      const int per_split = (W / 128) * (W / (W < 256 ? W : 256));
-      const int budget = nh > 0 ? p->nsm / nh : 0;
-      int frac = 38;
-      const char* ef = getenv("SIRENB200_CHAIN_DW_PCT");
-      if (ef && atoi(ef) > 0 && atoi(ef) < 90) frac = atoi(ef);
-      int cs = (budget * frac + 50 * per_split) / (100 * per_split);
-      if (cs < 1) cs = 1;
-      if (cs > p->ntiles) cs = p->ntiles;
-      p->chain_dw = cs * per_split;
-      p->chain_dx = budget - p->chain_dw;
-      p->bwd_chain = p->bwd_merged && nh >= 2 && nh <= kChainMaxLayers && p->chain_dx >= 1 && !(env && atoi(env) == 0);
-      if (p->bwd_chain) p->chain_splits = cs;
-    }
-    int slabs = (p->bwd_merged && p->merged_splits > splits) ? p->merged_splits : splits;
-    if (p->bwd_chain && p->chain_splits > slabs) slabs = p->chain_splits;
+    const int slabs = (p->bwd_merged && p->merged_splits > splits) ? p->merged_splits : splits;
     ALLOC(p->dw_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W * W);
     ALLOC(p->db_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W);
     p->chunk_tiles = p->ntiles;  // the whole shard is one chunk (row chunking lost to launch overheads)
     p->nchunks = 1;
     if (p->col_splits > p->chunk_tiles) p->col_splits = p->chunk_tiles;
-    p->active_splits = p->bwd_chain ? p->chain_splits : (p->bwd_merged ? p->merged_splits : p->col_splits);
+    p->active_splits = p->bwd_merged ? p->merged_splits : p->col_splits;
     const int64_t chunk_pad = int64_t(p->chunk_tiles) * kRowsPerTile;
     {
       const char* env = getenv("SIRENB200_LAST_TC");
@@ -1183,18 +1046,6 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       sirenb200_destroy(p);
       return fail(SIRENB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", trc);
     }
-    if (p->bwd_chain) {
-      ALLOC(p->chain_tab, 1);
-      ALLOC(p->chain_flags, int64_t(nh + 1) * p->ntiles);
-      ALLOC(p->chain_state, 2);
-      p->chain_host = new (std::nothrow) ChainTable();
-      if (!p->chain_host || cudaMemset(p->chain_flags, 0, size_t(nh + 1) * p->ntiles * sizeof(unsigned int)) != cudaSuccess ||
-          cudaMemset(p->chain_state, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
-        sirenb200_destroy(p);
-        return fail(SIRENB200_ERR_CUDA, "chained-backward setup failed");
-      }
-      p->chain_dirty = true;
-    }
     if (getenv("SIRENB200_TIMELINE")) {
       ALLOC(p->dbg_timeline, 3 * 4 * 8 * 16 + 12 * 16);
       cudaMemset(p->dbg_timeline, 0, (3 * 4 * 8 * 16 + 12 * 16) * sizeof(long long));
@@ -1207,9 +1058,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
 
 int sirenb200_destroy(sirenb200_handle_t p) {
   if (!p) return 0;
-  delete p->chain_host;
-  p->chain_host = nullptr;
-  void* ptrs[] = {p->chain_tab, p->chain_flags, p->chain_state, p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
+  void* ptrs[] = {p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
                   p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
                   p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
                   p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline,
@@ -1262,15 +1111,13 @@ int sirenb200_set_grid_lut(sirenb200_handle_t h, const float* lin_h, const float
   h->coord.lin_h = lin_h;
   h->coord.lin_w = lin_w;
   h->coord.coords = nullptr;
-  h->chain_dirty = true;
-  return chain_build(h);  // (outside any stream capture: the table upload synchronises)
+  return 0;
 }
 
 int sirenb200_set_grid_coords(sirenb200_handle_t h, const float* coords) {
   if (!h || !coords) return fail(SIRENB200_ERR_INVALID, "null argument");
   h->coord.coords = coords;
-  h->chain_dirty = true;
-  return chain_build(h);
+  return 0;
 }
 
 int sirenb200_forward(sirenb200_handle_t h, const float* const* prm, float* pred,

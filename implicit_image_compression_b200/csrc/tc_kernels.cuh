@@ -123,38 +123,6 @@ __device__ __forceinline__ void pace_post(const PaceCtx& pc, unsigned int n = 1u
   if (pc.mine) atomicAdd(pc.mine, n);
 }
 
-// Tile-granular dependency between two roles of ONE launch (the chained backward pass): the role that produces a
-// tensor adds 1 to flags[tile] when that tile's stores have completed; a consumer waits until the count reaches
-// need = (launches so far + 1) * parts before it loads the tile.  Counts only grow (every launch produces every
-// tile exactly once), so nothing is ever reset.  All CTAs of the launch are co-resident (grid <= #SMs) and every
-// producer walks its tiles in increasing order, so the waits always end; the spin is bounded and traps.
-struct DepCtx {
-  const unsigned int* wait;  // flags of the tensor this role's A / X operand comes from, or null
-  unsigned int* post;        // flags of the tensor this role writes, or null
-  unsigned int need;         // count that means "complete in this launch"
-};
-__device__ __forceinline__ void dep_wait(const DepCtx& d, int tile) {
-  if (!d.wait) return;
-  const unsigned int* f = d.wait + tile;
-  for (uint32_t spins = 0;; ++spins) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    if (int(v - d.need) >= 0) break;
-    __nanosleep(40);
-    if (spins > (1u << 24)) {
-      printf("sirenb200: tile dependency timeout block %d tile %d have %u need %u\n", blockIdx.x, tile, v, d.need);
-      __trap();
-    }
-  }
-  asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA loads that follow read what the flag covers
-}
-__device__ __forceinline__ void dep_post(const DepCtx& d, int tile) {
-  // caller: the tile's bulk stores have COMPLETED (cp.async.bulk.wait_group, not .read)
-  asm volatile("fence.proxy.async.global;" ::: "memory");
-  __threadfence();
-  atomicAdd(d.post + tile, 1u);
-}
-
 // ------------------------------------------------------------------------------------------
 // rowgemm
 // ------------------------------------------------------------------------------------------
@@ -233,8 +201,7 @@ template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN 
 // whole grid runs this body).
 __device__ __forceinline__ void
 rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmE, const CUtensorMap& tmO,
-             const RowGemmArgs& args, const uint32_t idesc, const int cta, const int ncta, const PaceCtx pace,
-             const DepCtx dep = DepCtx{}) {
+             const RowGemmArgs& args, const uint32_t idesc, const int cta, const int ncta, const PaceCtx pace) {
   using C = RowGemmCfg<KDIM, NDIM, MODE, NPARTS>;
   const int num_items = args.num_tiles * NPARTS;  // item = (tile, output part)
   extern __shared__ uint8_t smem_raw[];
@@ -405,7 +372,6 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
         const int row = args.a_row0 + t * kRowsPerTile;
         pace_wait(pace, t);
         pace_post(pace);
-        dep_wait(dep, t);
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
           mbar_wait(&a_empty[s], ph ^ 1u);
@@ -551,7 +517,6 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     const bool issuer = (threadIdx.x == 128);
     const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
     uint32_t it = 0, ic = 0;
-    int post_t = -1;  // tile whose completion flag is still to be posted
     for (int item = cta; item < num_items; item += ncta, ++it) {
       const int t = item / NPARTS, part = item % NPARTS;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
@@ -625,19 +590,8 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tm_empty[acc]);
       if (issuer) SB_DBG_G(5, it, 2);
-      if (issuer && dep.post) {
-        // the PREVIOUS item's stores are complete once only this item's NB groups can still be pending
-        if (post_t >= 0) {
-          tma_store_wait_all<C::NB>();
-          dep_post(dep, post_t);
-        }
-        post_t = t;
-      }
     }
-    if (issuer) {
-      tma_store_wait_all<0>();
-      if (dep.post && post_t >= 0) dep_post(dep, post_t);
-    }
+    if (issuer) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -703,7 +657,7 @@ struct ColGemmJobs {
 template <int NY>
 __device__ __forceinline__ void
 colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& jobs, const uint32_t idesc_main,
-             const uint32_t idesc_ones, const int job, const PaceCtx pace, const DepCtx dep = DepCtx{}) {
+             const uint32_t idesc_ones, const int job, const PaceCtx pace) {
   using C = ColGemmCfg<NY>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -768,7 +722,6 @@ colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& 
         const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile;
         pace_wait(pace, tile_begin + i * tile_step);
         pace_post(pace);
-        dep_wait(dep, tile_begin + i * tile_step);
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], C::STAGE_BYTES);
         uint8_t* st = smem + s * C::STAGE_BYTES;
@@ -880,92 +833,6 @@ bwd_merged_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
   } else {
     const PaceCtx pc{pace_counters + 1, pace_counters, window, jobs.mblocks * jobs.nparts, NPARTS};
     colgemm_body<NT>(tmDz, tmAct, jobs, idesc_main, idesc_ones, int(blockIdx.x) - dx_ctas, pc);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// The WHOLE backward pass of the hidden layers in ONE launch (hidden <= 256 output columns per role item):
-// for every layer l = nh .. 1 a group of CTAs runs its dX GEMM and another its weight-gradient reduction, all
-// resident at once (grid <= #SMs).  dX(l) hands dz[l-1] to dX(l-1) and dW(l-1) tile by tile through completion
-// flags (DepCtx), so a dz tile is read back out of the 126 MB L2 a few microseconds after it was written instead
-// of from HBM a kernel later: per layer HBM carries one read of act[l-1] and one write of dz[l-1]
-// (autograd of the nn.Linear / sin chain, siren.py:62,66, walked as a wavefront over pixel tiles).
-// The role table lives in global memory (static per handle).
-// ------------------------------------------------------------------------------------------
-struct ChainRole {
-  int kind;      // 0 = dX GEMM, 1 = dX GEMM + layer-0 gradient reduction (RED), 2 = weight-gradient reduction
-  int layer;     // l
-  int cta0, ncta;
-  int wait_idx;  // index of the flag row this role's dz operand waits on (-1: produced by an earlier launch)
-  int post_idx;  // index of the flag row this role posts (-1: none)
-  int parts;     // arrivals that complete a tile of the awaited tensor
-  int pad_;
-  RowGemmArgs row;
-  ColGemmJobs col;
-};
-constexpr int kChainMaxLayers = 16;
-struct alignas(64) ChainTable {
-  CUtensorMap tm_dz, tm_act;
-  CUtensorMap tm_wt[kChainMaxLayers];
-  int nroles;
-  int flag_stride;  // flags per tensor (>= tiles)
-  int pad_[14];
-  ChainRole role[2 * kChainMaxLayers];
-};
-
-template <int W>
-__global__ void __launch_bounds__(640, 1)
-bwd_chain_kernel(const ChainTable* __restrict__ tab, unsigned int* flags, unsigned int* chain_state,
-                 unsigned int* pace_counters, const int window) {
-  constexpr int NT = W < 256 ? W : 256;
-  constexpr int NPARTS = W / NT;
-  __shared__ RowGemmArgs s_row;
-  __shared__ ColGemmJobs s_col;
-  __shared__ int s_role;
-  if (threadIdx.x == 0) {
-    int r = 0;
-    while (r + 1 < tab->nroles && int(blockIdx.x) >= tab->role[r + 1].cta0) ++r;
-    s_role = r;
-    s_row = tab->role[r].row;
-    s_col = tab->role[r].col;
-  }
-  __syncthreads();
-  const ChainRole& role = tab->role[s_role];
-  const int kind = role.kind, l = role.layer, cta = int(blockIdx.x) - role.cta0;
-  // chain_state[0] = launches completed so far (written by the last CTA of a launch), [1] = CTAs done
-  const unsigned int launches = chain_state[0];
-  DepCtx dep{};
-  dep.wait = role.wait_idx >= 0 ? flags + size_t(role.wait_idx) * tab->flag_stride : nullptr;
-  dep.post = role.post_idx >= 0 ? flags + size_t(role.post_idx) * tab->flag_stride : nullptr;
-  dep.need = (launches + 1u) * unsigned(role.parts);
-  unsigned int* pc = pace_counters + 2 * l;
-  const int dw_per_tile = s_col.mblocks * s_col.nparts;
-  if (kind == 2) {
-    // (mblocks / nparts of the layer's reduction role: the dX role needs them for its pace hint only)
-    const PaceCtx pace{pc + 1, pc, window, dw_per_tile, NPARTS};
-    colgemm_body<NT>(tab->tm_dz, tab->tm_act, s_col, umma_idesc(128, NT, 0, 0, 1, 1), umma_idesc(128, 16, 0, 0, 1, 1),
-                     cta, pace, dep);
-  } else {
-    const PaceCtx pace{pc, pc + 1, window, NPARTS, (W / 128) * NPARTS};
-    if (kind == 1)
-      rowgemm_body<W, NT, MODE_DX, false, NPARTS, false, true>(tab->tm_dz, tab->tm_wt[l - 1], tab->tm_act, tab->tm_dz,
-                                                               s_row, umma_idesc(128, NT, 0, 0, 0, 0), cta, role.ncta,
-                                                               pace, dep);
-    else
-      rowgemm_body<W, NT, MODE_DX, false, NPARTS, false, false>(tab->tm_dz, tab->tm_wt[l - 1], tab->tm_act, tab->tm_dz,
-                                                                s_row, umma_idesc(128, NT, 0, 0, 0, 0), cta, role.ncta,
-                                                                pace, dep);
-  }
-  // the last CTA to finish closes the launch: every CTA has read chain_state[0] long before
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int done = atomicAdd(chain_state + 1, 1u);
-    if (done == gridDim.x - 1) {
-      chain_state[1] = 0u;
-      __threadfence();
-      chain_state[0] = launches + 1u;
-    }
   }
 }
 

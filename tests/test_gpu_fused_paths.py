@@ -38,48 +38,18 @@ def _grads(Siren, get_grid, synth_image, hidden, depth, H, W):
     return stats.tolist(), grads
 
 
-@pytest.mark.parametrize("plan", ["chain", "merged"])
-@pytest.mark.parametrize("hidden,depth,H,W", [(256, 6, 96, 160), (128, 4, 37, 53), (512, 4, 64, 96), (256, 5, 512, 768),
-                                              (256, 3, 40, 40), (512, 8, 128, 160)])
-def test_backward_launch_plans_match_separate_kernels(monkeypatch, plan, hidden, depth, H, W):
-    """Three launch plans of the hidden layers' backward pass — per-layer dX and one split-K dW launch (separate),
-    dX + dW of a layer in one launch (merged), all layers in ONE launch with tile flags through L2 (chain) — run
-    the same MMAs on the same operands; only the number of pixel splits of the weight gradient (fp32 summation
-    order) differs."""
+@pytest.mark.parametrize("hidden,depth,H,W", [(256, 6, 96, 160), (128, 4, 37, 53), (512, 4, 64, 96), (256, 5, 512, 768)])
+def test_merged_backward_matches_separate_kernels(monkeypatch, hidden, depth, H, W):
+    """Same operands, same MMAs; only the number of pixel splits of the weight gradient (fp32 summation order)
+    differs between the two launch plans."""
     get_grid, synth_image, _, Siren, _ = _pkg()
     monkeypatch.setenv("SIRENB200_BWD_MERGED", "1")
-    monkeypatch.setenv("SIRENB200_BWD_CHAIN", "1" if plan == "chain" else "0")
     s1, g1 = _grads(Siren, get_grid, synth_image, hidden, depth, H, W)
-    s1b, g1b = _grads(Siren, get_grid, synth_image, hidden, depth, H, W)  # a second handle: flags start from zero again
     monkeypatch.setenv("SIRENB200_BWD_MERGED", "0")
     s0, g0 = _grads(Siren, get_grid, synth_image, hidden, depth, H, W)
     assert s1[0] == s0[0] and s1[2] == 0.0
     for i, (a, b) in enumerate(zip(g1, g0)):
         assert _rel(a, b) <= 2e-5, f"tensor {i}: {_rel(a, b):.3e}"
-    for a, b in zip(g1, g1b):
-        assert torch.equal(a, b)
-
-
-def test_chained_backward_is_stable_over_many_launches():
-    """The completion flags of the chained backward only ever count up: 300 consecutive steps through one handle
-    (graph replays) must reproduce the per-layer launch plan's losses."""
-    get_grid, synth_image, Fitter, Siren, th = _pkg()
-    H, W = 128, 192
-    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
-    import os
-    out = []
-    for chain in ("1", "0"):
-        os.environ["SIRENB200_BWD_CHAIN"] = chain
-        try:
-            torch.manual_seed(0)
-            model = Siren(depth=6, hidden_size=256, first_omega_0=50, hidden_omega_0=30).cuda()
-            optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4})
-            out.append(Fitter(model, optim, grid, img, sched).steps(300).tolist())
-        finally:
-            os.environ.pop("SIRENB200_BWD_CHAIN", None)
-    np.testing.assert_allclose(out[0][:40], out[1][:40], rtol=1e-4)
-    assert all(math.isfinite(v) for v in out[0])
-    assert abs(out[0][-1] - out[1][-1]) <= 0.5 * out[1][-1]  # chaotic by then; same order of magnitude
 
 
 @pytest.mark.parametrize("with_mask", [False, True])
