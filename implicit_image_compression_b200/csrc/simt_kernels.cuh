@@ -559,6 +559,10 @@ struct PrepArgs {
   float* bias_w;                  // [nlayers][W] omega_h * bias
   float* bias_raw;                // [nlayers][W] bias
   unsigned int* pace;             // [2 * kMaxLayers] pace counters of the merged backward launches (zeroed here)
+  int Wm;                         // the MODEL's hidden width (<= W): parameters are [Wm, *]; everything staged here is
+                                  // zero-padded to the kernel width W (siren.py:88 makes widths like 114)
+  float* w0p;                     // [W, 2] layer-0 weight, padded
+  float* b0p;                     // [W]    layer-0 bias, padded
 };
 __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const PrepArgs a) {
   __shared__ float tile[32][33];
@@ -568,30 +572,36 @@ __global__ void __launch_bounds__(256) tc_prep_weights_kernel(const PrepArgs a) 
     a.pace[threadIdx.x] = 0u;
   const int l = blockIdx.z;
   const float* w = a.w[l];
-  const int W = a.W;
+  const int W = a.W, Wm = a.Wm;
   if (blockIdx.x == 1 % gridDim.x && blockIdx.y == 0 && l == 0 && a.wl16) {
     for (int i = threadIdx.x; i < 16 * W; i += 256) {
       const int c = i / W, n = i % W;
-      a.wl16[i] = __float2half_rn(c < a.C ? a.w_last[c * W + n] : 0.f);
+      a.wl16[i] = __float2half_rn((c < a.C && n < Wm) ? a.w_last[c * Wm + n] : 0.f);
     }
     for (int i = threadIdx.x; i < W * 16; i += 256) {
       const int n = i / 16, c = i % 16;
       const int off = (n % 8) * 8 + (n / 8) * 128 + (c / 8) * 64 + (c % 8);
-      a.wlt16[off] = __float2half_rn(c < a.C ? a.omega_prev_last * a.w_last[c * W + n] : 0.f);
+      a.wlt16[off] = __float2half_rn((c < a.C && n < Wm) ? a.omega_prev_last * a.w_last[c * Wm + n] : 0.f);
     }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0) {
     for (int i = threadIdx.x; i < W; i += 256) {
-      a.bias_w[l * W + i] = a.omega_h * a.bias[l][i];
-      a.bias_raw[l * W + i] = a.bias[l][i];
-      if (l == 0)
-        a.tab0[i] = make_float4(a.omega0 * a.w0[2 * i], a.omega0 * a.w0[2 * i + 1], a.omega0 * a.b0[i], 0.f);
+      const float bv = i < Wm ? a.bias[l][i] : 0.f;
+      a.bias_w[l * W + i] = a.omega_h * bv;
+      a.bias_raw[l * W + i] = bv;
+      if (l == 0) {
+        const float wh = i < Wm ? a.w0[2 * i] : 0.f, ww = i < Wm ? a.w0[2 * i + 1] : 0.f, b0 = i < Wm ? a.b0[i] : 0.f;
+        a.tab0[i] = make_float4(a.omega0 * wh, a.omega0 * ww, a.omega0 * b0, 0.f);
+        a.w0p[2 * i] = wh;
+        a.w0p[2 * i + 1] = ww;
+        a.b0p[i] = b0;
+      }
     }
   }
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int r = ty; r < 32; r += 8) {
-    const float v = w[(by + r) * W + bx + tx];
+    const float v = (by + r < Wm && bx + tx < Wm) ? w[(by + r) * Wm + bx + tx] : 0.f;
     tile[r][tx] = v;
     a.wh[(size_t(l) * W + by + r) * W + bx + tx] = __float2half_rn(v);
   }

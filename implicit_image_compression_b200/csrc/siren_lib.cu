@@ -57,7 +57,8 @@ struct sirenb200_plan {
   sirenb200_config_t cfg;
   int device = 0;
   int nsm = 0;
-  int D = 0, W = 0, C = 0;
+  int D = 0, W = 0, C = 0;  // W = kernel width (tensor-core path: the model width padded to 128 / 256 / 512)
+  int Wm = 0;               // the model's hidden width
   int rows = 0;
   int64_t npix = 0, npix_pad = 0;
   int ntiles = 0;
@@ -89,7 +90,9 @@ struct sirenb200_plan {
   __half* wth = nullptr;  // [(D-2)][W, W]
   float4* tab0 = nullptr; // [W] layer-0 epilogue table (fused forward)
   float* bias_w = nullptr;  // [(D-2)][W] omega * bias
-  float* bias_raw = nullptr;  // [(D-2)][W] bias (contiguous copy for the fused forward)
+  float* bias_raw = nullptr;  // [(D-2)][W] hidden-layer biases, zero-padded to the kernel width
+  float* w0p = nullptr;       // [W, 2] layer-0 weight, zero-padded
+  float* b0p = nullptr;       // [W]    layer-0 bias, zero-padded
   CUtensorMap tm_act{}, tm_dz{};
   __half* wl16 = nullptr;   // [16, W] last-layer weights for the tensor-core last layer
   __half* wlt16 = nullptr;  // [W, 64]
@@ -309,6 +312,9 @@ int tc_prep(sirenb200_plan* p, const float* const* prm, cudaStream_t st, float* 
     pa.wlt16 = p->wlt16;
     pa.bias_raw = p->bias_raw;
     pa.pace = p->pace;
+    pa.Wm = p->Wm;
+    pa.w0p = p->w0p;
+    pa.b0p = p->b0p;
     {
       ProfScope ps(p, PK_PREP, st);
       tc_prep_weights_kernel<<<dim3(W / 32, W / 32, nh), 256, 0, st>>>(pa);
@@ -335,7 +341,7 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     const int need = cdiv(ch.npix_pad, 256 / (W / 8));
     if (grid > need) grid = need;
     ProfScope ps(p, PK_FIRST, st);
-    tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(cs, prm[0], prm[1], omega_of(p, 0),
+    tc_first_layer_kernel<W><<<grid, 256, 0, st>>>(cs, p->w0p, p->b0p, omega_of(p, 0),
                                                   p->act + ch.p0 * W, ch.npix, ch.npix_pad);
   }
   LAUNCH_CHECK();
@@ -348,14 +354,14 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     ra.o_row0 = int(l * p->npix_pad + ch.p0);
     ra.valid_rows = int(ch.npix);
     ra.omega = omega_of(p, l);
-    ra.bias = prm[2 * l + 1];
+    ra.bias = p->bias_raw + size_t(l - 1) * W;  // staged (zero-padded) copy of prm[2 * l + 1]
     ra.b_early = (l >= 2) ? 1 : 0;  // layer 1 follows the weight-staging kernel directly
     int rc;
     if constexpr (kCanGen) {
       if (l == 1 && gen_first) {
         ra.gen_coord = cs;
-        ra.gen_w0 = prm[0];
-        ra.gen_b0 = prm[1];
+        ra.gen_w0 = p->w0p;
+        ra.gen_b0 = p->b0p;
         ra.gen_omega = omega_of(p, 0);
         ra.gen_tl = p->dbg_timeline;
         rc = launch_rowgemm<W, MODE_FWD, true>(p, p->tm_act, p->tm_w[0], p->tm_act, p->tm_act, ra, st);
@@ -429,7 +435,7 @@ int launch_tail(sirenb200_plan* p, const float* const* prm, const float* img, fl
     ta.dz_row0 = int(nh * p->npix_pad + ch.p0);
     ta.npix = ch.npix;
     ta.omega = omega_of(p, nh);
-    ta.bias = prm[2 * nh + 1];
+    ta.bias = p->bias_raw + size_t(nh - 1) * W;
     ta.b_last = prm[2 * (D - 1) + 1];
     ta.img = img + ch.p0 * C;
     ta.pred = pred ? pred + ch.p0 * C : nullptr;
@@ -607,32 +613,33 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
 // descriptors of every partial buffer -> the caller's gradient tensors (order = model.parameters())
 void tc_build_reduce(const sirenb200_plan* p, float* const* grads, float scale, float* stats, int nchunks,
                      ReduceArgs& ra) {
-  const int D = p->D, C = p->C, W = p->W, nh = D - 2;
+  const int D = p->D, C = p->C, W = p->W, Wm = p->Wm, nh = D - 2;
+  const bool padded = Wm != W;
   int nd = 0;
-  auto add = [&](float* dst, const float* src, int n, int nsplit, int64_t stride) {
+  // n gradient elements; cols > 0: the gradient is a [n / cols, cols] matrix inside a [*, W]-pitched partial slab
+  auto add = [&](float* dst, const float* src, int n, int nsplit, int64_t stride, int cols) {
     ra.d[nd].dst = dst;
     ra.d[nd].src = src;
     ra.d[nd].n = n;
     ra.d[nd].nsplit = nsplit;
     ra.d[nd].split_stride = stride;
     // weight-gradient partials (few splits, many elements, 16-byte aligned rows): vectorised path
-    ra.d[nd].vec = (n >= 4096 && n % 4 == 0 && stride % 4 == 0 && nsplit <= 64 &&
+    ra.d[nd].vec = (!padded && n >= 4096 && n % 4 == 0 && stride % 4 == 0 && nsplit <= 64 &&
                     (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0)
                        ? 1 : 0;
-    ra.d[nd].cols = 0;
-    ra.d[nd].cols_pad = 0;
+    ra.d[nd].cols = padded ? cols : 0;
+    ra.d[nd].cols_pad = padded ? W : 0;
     ++nd;
   };
-  add(grads[0], p->l0_part, 2 * W, p->l0_used, 3 * W);
-  add(grads[1], p->l0_part + 2 * W, W, p->l0_used, 3 * W);
+  add(grads[0], p->l0_part, 2 * Wm, p->l0_used, 3 * W, 0);   // [W, 2] block: the model's rows come first
+  add(grads[1], p->l0_part + 2 * W, Wm, p->l0_used, 3 * W, 0);
   for (int l = 1; l <= nh; ++l) {
-    add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, W * W, p->active_splits,
-        int64_t(nh) * W * W);
-    add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, W, p->active_splits, int64_t(nh) * W);
+    add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, Wm * Wm, p->active_splits, int64_t(nh) * W * W, Wm);
+    add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, Wm, p->active_splits, int64_t(nh) * W, 0);
   }
   const int64_t lstride = int64_t(C) * W + C + 1;
-  add(grads[2 * (D - 1)], p->last_part, C * W, p->last_grid * nchunks, lstride);
-  add(grads[2 * (D - 1) + 1], p->last_part + C * W, C, p->last_grid * nchunks, lstride);
+  add(grads[2 * (D - 1)], p->last_part, C * Wm, p->last_grid * nchunks, lstride, Wm);
+  add(grads[2 * (D - 1) + 1], p->last_part + C * W, C, p->last_grid * nchunks, lstride, 0);
   ra.ndesc = nd;
   int chunks = 0;
   for (int i = 0; i < nd; ++i) {
@@ -880,10 +887,10 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
   if (prop.major != 10)
     return fail(SIRENB200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", dev,
                 prop.major, prop.minor);
-  if (cfg->precision == SIRENB200_PREC_F16TC && !tc_supported(cfg->hidden))
+  if (cfg->precision == SIRENB200_PREC_F16TC && (cfg->hidden > 512 || (!tc_supported(cfg->hidden) && cfg->depth < 3)))
     return fail(SIRENB200_ERR_INVALID,
-                "tensor-core path supports hidden in {128, 256, 512}; got %d (use SIRENB200_PREC_FP32)",
-                cfg->hidden);
+                "tensor-core path supports hidden <= 512 (any width with depth >= 3: zero-padded to 128 / 256 / 512); "
+                "got hidden %d depth %d (use SIRENB200_PREC_FP32)", cfg->hidden, cfg->depth);
   if (cfg->precision != SIRENB200_PREC_F16TC && cfg->precision != SIRENB200_PREC_FP32)
     return fail(SIRENB200_ERR_INVALID, "unknown precision %d", cfg->precision);
 
@@ -892,7 +899,10 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
   p->device = dev;
   p->nsm = prop.multiProcessorCount;
   p->D = cfg->depth;
+  p->Wm = cfg->hidden;
   p->W = cfg->hidden;
+  if (cfg->precision == SIRENB200_PREC_F16TC)  // kernel width: the tcgen05 kernels exist for 128 / 256 / 512 columns
+    p->W = cfg->hidden <= 128 ? 128 : (cfg->hidden <= 256 ? 256 : 512);
   p->C = cfg->out_features;
   p->rows = cfg->row_end - cfg->row_begin;
   p->npix = int64_t(p->rows) * cfg->width;
@@ -958,6 +968,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     ALLOC(p->wlt16, int64_t(W) * 64);
     ALLOC(p->bias_w, int64_t(nh > 0 ? nh : 1) * W);
     ALLOC(p->bias_raw, int64_t(nh > 0 ? nh : 1) * W);
+    ALLOC(p->w0p, 2 * W);
+    ALLOC(p->b0p, W);
     // pixel splits of the weight-gradient GEMM: one CTA per (layer, 128-row block, column part, split).
     // One wave of CTAs when that fills the machine (>= 93 % of the SMs), otherwise two balanced waves
     // (hidden 512, depth 6: 32 x 4 = 128 jobs would leave 20 SMs idle; 32 x 9 = 288 = 2 x 144 does not).
@@ -1061,7 +1073,7 @@ int sirenb200_destroy(sirenb200_handle_t p) {
   void* ptrs[] = {p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
                   p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
                   p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
-                  p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline,
+                  p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline, p->w0p, p->b0p,
                   p->wl16,   p->wlt16};
   for (void* q : ptrs)
     if (q) cudaFree(q);

@@ -9,9 +9,13 @@ import torch
 from . import _lib
 
 
-def default_precision(hidden):
-    """fp16 tensor-core path when the hidden width has a tcgen05 kernel, else the fp32 CUDA-core path."""
-    return _lib.PREC_F16TC if hidden in (128, 256, 512) else _lib.PREC_FP32
+def default_precision(hidden, depth=3):
+    """fp16 tensor-core path for hidden widths 64..512 (any width: the library zero-pads it to the 128 / 256 / 512
+    columns its tcgen05 kernels are built for — models/siren.py:88 produces widths like 114), else the fp32
+    CUDA-core path (tiny plumbing models, hidden > 512, depth 2)."""
+    if hidden in (128, 256, 512) or (64 < hidden <= 512 and depth >= 3):
+        return _lib.PREC_F16TC
+    return _lib.PREC_FP32
 
 
 class SirenEngine:
@@ -25,7 +29,7 @@ class SirenEngine:
             raise _lib.SirenB200Error(f"engine device must be CUDA, got {self.device}")
         row_end = height if row_end is None else row_end
         if precision is None:
-            precision = default_precision(hidden)
+            precision = default_precision(hidden, depth)
         self.cfg = _lib.Config(depth=depth, hidden=hidden, in_features=2, out_features=out_features,
                                first_omega=float(first_omega), hidden_omega=float(hidden_omega),
                                outermost_linear=int(bool(outermost_linear)), height=height, width=width,

@@ -106,7 +106,7 @@ class Siren(nn.Module):
 
     def _precision_code(self):
         if self.precision in (None, "auto"):
-            return default_precision(self.hidden_size)
+            return default_precision(self.hidden_size, self.depth)
         return {"fp32": _lib.PREC_FP32, "f16tc": _lib.PREC_F16TC}[self.precision]
 
     def engine_for(self, grid, row_begin=0, row_end=None, height=None):

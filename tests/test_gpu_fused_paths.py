@@ -185,3 +185,36 @@ def test_depth8_hidden512_vs_oracle():
     assert abs(stats[1] - loss_ref.item()) <= 2e-4 * loss_ref.item()
     for i, (a, b) in enumerate(zip(grads, grads_ref)):
         assert _rel(a, b) <= 1.5e-2, f"gradient {i}: {_rel(a, b):.3e}"
+
+
+@pytest.mark.parametrize("hidden,depth", [(114, 6), (192, 4), (300, 3), (65, 5)])
+def test_any_hidden_width_on_tensor_cores_vs_oracle(hidden, depth):
+    """siren.py:88 turns mlp.hidden_size x sqrt(density) into widths like 114 (conf/masking/Small_Dense.yaml): the
+    tensor-core path zero-pads them to its kernel widths.  Forward, loss and every gradient against the oracle, then
+    a short fit against the fp32 CUDA-core path."""
+    get_grid, synth_image, Fitter, Siren, th = _pkg()
+    H, W = 60, 84
+    torch.manual_seed(0)
+    model = Siren(depth=depth, hidden_size=hidden, first_omega_0=50, hidden_omega_0=30)
+    assert model._precision_code() == 1  # f16tc by default
+    ref = [p.detach().clone() for p in model.parameters()]
+    model = model.cuda()
+    grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
+    with torch.no_grad():
+        pred = model(grid)
+    want = O.siren_forward(ref, grid.cpu(), 50.0, 30.0)
+    assert (pred.cpu() - want).abs().max().item() <= 5e-4
+    grads = [torch.empty_like(p) for p in model.hot_parameters()]
+    stats = model.engine_for(grid).forward_backward(model.kernel_parameters(), img, grads).tolist()
+    loss_ref, grads_ref = O.siren_loss_and_grads(ref, grid.cpu(), img.cpu(), 50.0, 30.0)
+    assert abs(stats[1] - loss_ref.item()) <= 1e-4 * loss_ref.item()
+    for i, (a, b) in enumerate(zip(grads, grads_ref)):
+        assert a.shape == b.shape
+        assert _rel(a, b) <= 1.5e-2, f"gradient {i}: {_rel(a, b):.3e}"
+    losses = {}
+    for precision in ("f16tc", "fp32"):
+        torch.manual_seed(0)
+        m = Siren(depth=depth, hidden_size=hidden, first_omega_0=50, hidden_omega_0=30, precision=precision).cuda()
+        optim, sched = th.get_optimizer_lr_scheduler(m, {"name": "adam", "lr": 3e-4})
+        losses[precision] = Fitter(m, optim, grid, img, sched).steps(12).tolist()
+    np.testing.assert_allclose(losses["f16tc"], losses["fp32"], rtol=3e-2)
