@@ -1180,6 +1180,109 @@ __global__ void kmeans_linspace_kernel(const float* mm, int k, float* cent) {
 }
 
 // ------------------------------------------------------------------------------------------
+// QAT activation fake-quant: torch's FusedMovingAvgObsFakeQuantize on an nn.Linear output (what
+// torch.quantization.prepare_qat attaches for quant/context.py:35-47; per-tensor affine quint8, reduce_range ->
+// [0, 127], MovingAverageMinMaxObserver with averaging constant 0.01).  state (device, 4 floats):
+// {running min, running max, scale, zero point}; running min/max start at +inf / -inf.
+//   1. actq_minmax_kernel   : per-block min / max of the tensor
+//   2. actq_update_kernel   : observer update (training) + ChooseQuantizationParams (fbgemm's rule, double
+//                             arithmetic, exactly aten/native/quantized/cpu/fused_obs_fake_quant.cpp)
+//   3. actq_apply_kernel    : q = nearbyint(x * (1/scale)) + zp; out = (clamp(q) - zp) * scale; mask = q in range
+//                             (the straight-through gradient mask), optionally a = sin(omega * out)
+// ------------------------------------------------------------------------------------------
+constexpr int kActqBlocks = 256;
+__global__ void __launch_bounds__(256) actq_minmax_kernel(const float* x, int64_t n, float* partial) {
+  float lo = INFINITY, hi = -INFINITY;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+  __shared__ float slo[256], shi[256];
+  slo[threadIdx.x] = lo;
+  shi[threadIdx.x] = hi;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) {
+      slo[threadIdx.x] = fminf(slo[threadIdx.x], slo[threadIdx.x + k]);
+      shi[threadIdx.x] = fmaxf(shi[threadIdx.x], shi[threadIdx.x + k]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = slo[0];
+    partial[2 * blockIdx.x + 1] = shi[0];
+  }
+}
+__global__ void actq_update_kernel(const float* partial, int nblocks, float* state, int training, float avg_const,
+                                   int qmin, int qmax) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float rmin = state[0], rmax = state[1];
+  if (training) {
+    float cmin = INFINITY, cmax = -INFINITY;
+    for (int i = 0; i < nblocks; ++i) {
+      cmin = fminf(cmin, partial[2 * i]);
+      cmax = fmaxf(cmax, partial[2 * i + 1]);
+    }
+    if (isinf(rmin) || isinf(rmax)) {
+      rmin = cmin;
+      rmax = cmax;
+    } else {
+      rmin = __fadd_rn(rmin, __fmul_rn(avg_const, __fsub_rn(cmin, rmin)));
+      rmax = __fadd_rn(rmax, __fmul_rn(avg_const, __fsub_rn(cmax, rmax)));
+    }
+    state[0] = rmin;
+    state[1] = rmax;
+  }
+  // quant_utils::ChooseQuantizationParams(min, max, qmin, qmax)
+  double mn = fmin(double(rmin), 0.0), mx = fmax(double(rmax), 0.0);
+  double scale = (mx - mn) / double(qmax - qmin);
+  if (float(scale) == 0.0f || isinf(1.0f / float(scale))) scale = 0.1;
+  const double kSmall = 6.1e-5;
+  if (scale < kSmall) {
+    const float org = float(scale);
+    scale = kSmall;
+    if (mn == 0.0) {
+      mx = kSmall * (qmax - qmin);
+    } else if (mx == 0.0) {
+      mn = -kSmall * (qmax - qmin);
+    } else {
+      const float amp = float(kSmall / org);
+      mn *= amp;
+      mx *= amp;
+    }
+  }
+  const double zmin = qmin - mn / scale, zmax = qmax - mx / scale;
+  const double emin = fabs(double(qmin)) - fabs(mn / scale), emax = fabs(double(qmax)) - fabs(mx / scale);
+  const double z0 = emin < emax ? zmin : zmax;
+  int zp;
+  if (z0 < qmin) zp = qmin;
+  else if (z0 > qmax) zp = qmax;
+  else zp = int(nearbyint(z0));
+  state[2] = float(scale);
+  state[3] = float(zp);
+}
+__global__ void __launch_bounds__(256) actq_apply_kernel(const float* x, int64_t n, const float* state, int qmin,
+                                                         int qmax, float* out, unsigned char* mask, float* act,
+                                                         float omega) {
+  const float scale = state[2], zp = state[3];
+  const float inv = __fdiv_rn(1.0f, scale);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float q = __fadd_rn(rintf(__fmul_rn(x[i], inv)), zp);
+    const bool in = q >= float(qmin) && q <= float(qmax);
+    const float qc = fminf(fmaxf(q, float(qmin)), float(qmax));
+    const float v = __fmul_rn(__fsub_rn(qc, zp), scale);
+    out[i] = v;
+    if (mask) mask[i] = in ? 1 : 0;
+    if (act) act[i] = sinf(v * omega);
+  }
+}
+__global__ void __launch_bounds__(256) mul_mask_u8_kernel(float* g, const unsigned char* mask, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    if (!mask[i]) g[i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
 // step_end_kernel: everything of a fit step that follows the last GEMM, in ONE launch.
 //   phase 1  every block reduces ITS chunks of the split-K / per-CTA gradient partials (x scale / G);
 //            block 0 also sums the squared-error partials (F.mse_loss, train_helper.py:151-154)

@@ -121,6 +121,13 @@ struct sirenb200_plan {
   int dw_ctas = 0;             // CTAs of that launch that run the reduction
   int merged_splits = 0;       // pixel splits of the reduction role
   int pace_window = 192;       // tiles the two roles may drift apart
+  // QAT activation fake-quant (fp32 handles): observer state is caller-owned, masks / partials live here
+  float* actq_state = nullptr;          // [D][4] {running min, running max, scale, zero point} (device, caller's)
+  bool actq_on = false;
+  int actq_training = 0, actq_qmin = 0, actq_qmax = 127;
+  float actq_avg = 0.01f;
+  unsigned char* actq_mask = nullptr;   // [(D-1) * npix * W + npix * C] straight-through masks
+  float* actq_partial = nullptr;        // [2 * kActqBlocks]
   bool defer_reduce = false;   // transient: tc_run leaves the partial reduction to the fused step-end kernel
   unsigned long long* bar = nullptr;  // grid-barrier counter of step_end_kernel
 
@@ -707,6 +714,23 @@ int launch_simt(const SimtGemmArgs& a, int splits, cudaStream_t st) {
   return 0;
 }
 
+// FusedMovingAvgObsFakeQuantize on one tensor: x <- fake_quant(x) in place, optional act = sin(omega x), mask
+int actq_run(sirenb200_plan* p, float* x, int64_t n, float* state, unsigned char* mask, float* act, float omega,
+             cudaStream_t st) {
+  if (p->actq_training) {
+    actq_minmax_kernel<<<kActqBlocks, 256, 0, st>>>(x, n, p->actq_partial);
+    LAUNCH_CHECK();
+  }
+  actq_update_kernel<<<1, 32, 0, st>>>(p->actq_partial, kActqBlocks, state, p->actq_training, p->actq_avg, p->actq_qmin,
+                                       p->actq_qmax);
+  LAUNCH_CHECK();
+  int grid = cdiv(n, 256 * 4);
+  if (grid > p->nsm * 8) grid = p->nsm * 8;
+  actq_apply_kernel<<<grid, 256, 0, st>>>(x, n, state, p->actq_qmin, p->actq_qmax, x, mask, act, omega);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
                 float* pred, cudaStream_t st) {
   const int D = p->D, W = p->W, C = p->C;
@@ -731,6 +755,10 @@ int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const floa
     a.omega = omega_of(p, l);
     int rc = launch_simt<OP_NT_SINE>(a, 1, st);
     if (rc) return rc;
+    if (p->actq_on) {  // z <- fake_quant(z), a <- sin(omega z_q)   (activation_post_process of the qat Linear)
+      rc = actq_run(p, a.Z, n * W, p->actq_state + 4 * l, p->actq_mask + size_t(l) * n * W, a.Out, a.omega, st);
+      if (rc) return rc;
+    }
     in = a.Out;
     in_dim = W;
   }
@@ -748,6 +776,11 @@ int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const floa
     a.ldo = C;
     int rc = launch_simt<OP_NT_LIN>(a, 1, st);
     if (rc) return rc;
+    if (p->actq_on) {
+      rc = actq_run(p, p->y32, n * C, p->actq_state + 4 * (D - 1), p->actq_mask + size_t(D - 1) * n * W, nullptr, 0.f,
+                    st);
+      if (rc) return rc;
+    }
   }
   LossArgs la{};
   la.y = p->y32;
@@ -771,6 +804,18 @@ int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads
   const float* g = p->g32;  // dL/dz of layer l (seed units)
   int gdim = C;
   int pp = 0;
+  auto mask_grad = [&](float* gbuf, int layer, int64_t count) -> int {
+    // straight-through estimator of the activation fake-quant: no gradient where the value was clipped
+    int grid = cdiv(count, 256 * 4);
+    if (grid > p->nsm * 8) grid = p->nsm * 8;
+    mul_mask_u8_kernel<<<grid, 256, 0, st>>>(gbuf, p->actq_mask + size_t(layer) * n * W, count);
+    LAUNCH_CHECK();
+    return 0;
+  };
+  if (p->actq_on) {
+    int rc = mask_grad(p->g32, D - 1, n * C);
+    if (rc) return rc;
+  }
   for (int l = D - 1; l >= 0; --l) {
     const float* xin = (l == 0) ? p->x32 : p->a32 + size_t(l - 1) * n * W;
     const int xdim = (l == 0) ? p->cfg.in_features : W;
@@ -817,6 +862,10 @@ int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads
       b.omega = omega_of(p, l - 1);
       rc = launch_simt<OP_NN_DCOS>(b, 1, st);
       if (rc) return rc;
+      if (p->actq_on) {
+        rc = mask_grad(p->dz32[pp], l - 1, n * W);
+        if (rc) return rc;
+      }
       g = p->dz32[pp];
       gdim = W;
       pp ^= 1;
@@ -1070,7 +1119,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
 
 int sirenb200_destroy(sirenb200_handle_t p) {
   if (!p) return 0;
-  void* ptrs[] = {p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
+  void* ptrs[] = {p->actq_mask, p->actq_partial, p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
                   p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
                   p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
                   p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline, p->w0p, p->b0p,
@@ -1198,6 +1247,52 @@ int sirenb200_backward(sirenb200_handle_t h, const float* const* prm, const floa
     rc = tc_dispatch(h, prm, 2, dpred, nullptr, grads, 1.0f, stats, st);
   }
   return rc;
+}
+
+int sirenb200_set_act_quant(sirenb200_handle_t h, float* state, int32_t enable, int32_t training, float averaging_const,
+                            int32_t qmin, int32_t qmax) {
+  if (!h) return fail(SIRENB200_ERR_INVALID, "null handle");
+  if (!enable) {
+    h->actq_on = false;
+    return 0;
+  }
+  if (h->cfg.precision != SIRENB200_PREC_FP32)
+    return fail(SIRENB200_ERR_INVALID, "activation fake-quant runs on the fp32 path (create the handle with SIRENB200_PREC_FP32)");
+  if (!state || qmax <= qmin) return fail(SIRENB200_ERR_INVALID, "set_act_quant: bad argument");
+  if (!h->actq_mask) {
+    const int64_t bytes = int64_t(h->D - 1) * h->npix * h->W + h->npix * h->C;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->actq_mask), size_t(bytes)));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->actq_partial), 2 * kActqBlocks * sizeof(float)));
+    h->bytes += bytes + 2 * kActqBlocks * int64_t(sizeof(float));
+  }
+  h->actq_state = state;
+  h->actq_on = true;
+  h->actq_training = training ? 1 : 0;
+  h->actq_avg = averaging_const;
+  h->actq_qmin = qmin;
+  h->actq_qmax = qmax;
+  return 0;
+}
+
+int sirenb200_fakequant_per_tensor(const float* x, int64_t n, float* state, int32_t training, float averaging_const,
+                                   int32_t qmin, int32_t qmax, float* out, uint8_t* mask, sirenb200_stream_t stream) {
+  if (!x || !state || !out || n < 1 || qmax <= qmin) return fail(SIRENB200_ERR_INVALID, "fakequant_per_tensor: bad argument");
+  keep_pool_memory();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* partial = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partial), 2 * kActqBlocks * sizeof(float), st));
+  if (training) {
+    actq_minmax_kernel<<<kActqBlocks, 256, 0, st>>>(x, n, partial);
+    LAUNCH_CHECK();
+  }
+  actq_update_kernel<<<1, 32, 0, st>>>(partial, kActqBlocks, state, training ? 1 : 0, averaging_const, qmin, qmax);
+  LAUNCH_CHECK();
+  int grid = cdiv(n, 256 * 4);
+  if (grid > 148 * 8) grid = 148 * 8;
+  actq_apply_kernel<<<grid, 256, 0, st>>>(x, n, state, qmin, qmax, out, mask, nullptr, 0.f);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaFreeAsync(partial, st));
+  return 0;
 }
 
 int sirenb200_eval_metrics(const float* pred, const float* img, int64_t n, float* out,

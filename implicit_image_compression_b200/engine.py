@@ -127,6 +127,20 @@ class SirenEngine:
         _lib.check(self.lib.sirenb200_backward(self.handle, _lib.ptr_array(params), dpred.data_ptr(),
                                                _lib.ptr_array(grads), self._stream()))
 
+    def set_act_quant(self, state, training, averaging_const=0.01, qmin=0, qmax=127):
+        """QAT activation fake-quant on every layer's pre-activation (fp32 engines).  state: [depth, 4] fp32 CUDA
+        tensor {running min, running max, scale, zero point}; None switches it off."""
+        if state is None:
+            _lib.check(self.lib.sirenb200_set_act_quant(self.handle, None, 0, 0, 0.0, 0, 1))
+            self._act_state = None
+            return
+        _lib.require_cuda(state, "state")
+        if state.dtype != torch.float32 or tuple(state.shape) != (self.depth, 4) or not state.is_contiguous():
+            raise _lib.SirenB200Error("activation-quant state must be a contiguous [depth, 4] fp32 tensor")
+        self._act_state = state  # keep-alive
+        _lib.check(self.lib.sirenb200_set_act_quant(self.handle, state.data_ptr(), 1, int(bool(training)),
+                                                    float(averaging_const), int(qmin), int(qmax)))
+
     def workspace_bytes(self):
         return int(self.lib.sirenb200_workspace_bytes(self.handle))
 
@@ -190,6 +204,20 @@ def kmeans_quantize(weight, bits, iter_limit=5, tol=1e-4, init_centers=None):
         ncent.data_ptr(), labels.data_ptr(), w_out.data_ptr(), torch.cuda.current_stream().cuda_stream))
     k = int(ncent.item())
     return cent[:k].clone(), labels, w_out
+
+
+def fakequant_per_tensor(x, state, training=True, averaging_const=0.01, qmin=0, qmax=127, want_mask=False):
+    """torch.fused_moving_avg_obs_fake_quant on a CUDA tensor: returns fake_quant(x) (and the straight-through
+    mask); `state` ([4] fp32: running min, running max, scale, zero point) is updated in place."""
+    _lib.require_cuda(x, "x")
+    lib = _lib.load()
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_mask else None
+    _lib.check(lib.sirenb200_fakequant_per_tensor(
+        x.data_ptr(), x.numel(), state.data_ptr(), int(bool(training)), float(averaging_const), int(qmin), int(qmax),
+        out.data_ptr(), None if mask is None else mask.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return (out, mask) if want_mask else out
 
 
 def fakequant_per_channel(weight, row_min=None, row_max=None, neg_div=128.0, pos_div=127.0):

@@ -123,6 +123,13 @@ class Siren(nn.Module):
                               self._precision_code(), grid.device)
             self._engines[key] = eng
         eng.bind_grid(grid)
+        aq = self.__dict__.get("_act_quant")
+        if aq is not None:  # QAT activation observers (pipeline/quant/context.py).  torch's observers keep updating
+            # in eval mode too (observer_enabled does not follow module.training); only convert() freezes them
+            eng.set_act_quant(aq["state"], not aq.get("frozen", False), aq["averaging_constant"],
+                              aq["qmin"], aq["qmax"])
+        elif getattr(eng, "_act_state", None) is not None:
+            eng.set_act_quant(None, False)
         return eng
 
     def run_weight_transforms(self):
@@ -157,6 +164,8 @@ class Siren(nn.Module):
                 new.__dict__[k] = []
             elif k == "_step_fitters":
                 new.__dict__[k] = {}
+            elif k == "_act_quant":
+                continue
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
         return new

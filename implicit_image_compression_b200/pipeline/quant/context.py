@@ -1,12 +1,16 @@
 """`with Quantize(model, optim, cfg.quant) as q: ...; q.convert()` (reference: pipeline/quant/context.py).
 
 KMeans : weights are re-clustered at weight load before every fused forward (kmeans.py).
-QAT    : weights-only quantisation-aware training.  Each nn.Linear weight is fake-quantised at weight load
-         (per-output-channel symmetric int8, running min/max with averaging constant 0.01, exactly the
-         weight half of torch's default 'fbgemm' QAT qconfig) and the straight-through gradient is applied
-         to the fp32 master weight.  Activation observers and the int8 `torch.quantization.convert`
-         inference graph are "next" (SURVEY.md §8f rank 2); `convert()` returns the model with dequantised
-         weights plus `weight_codes` (int8) and `weight_scales` on every Linear.
+QAT    : torch's default 'fbgemm' QAT qconfig, as torch.quantization.prepare_qat applies it to the reference model.
+         Weights: each nn.Linear weight is fake-quantised at weight load (per-output-channel symmetric int8,
+         running min/max with averaging constant 0.01); the straight-through gradient goes to the fp32 master.
+         Activations: the OUTPUT of every nn.Linear goes through FusedMovingAvgObsFakeQuantize (per-tensor affine
+         quint8 with reduce_range = [0, 127], moving-average min/max) — sirenb200_set_act_quant, on the fp32
+         engine (`activations=False` in the quant config keeps the weights-only tensor-core variant).
+         `convert()` freezes the observers and returns the model in eval mode with, on every Linear,
+         `weight_codes` (int8), `weight_scales`, `act_scale`, `act_zero_point` — the tensors of torch's converted
+         int8 module; its forward computes what the int8 graph computes (fake-quantised values are exactly
+         representable, so quantise -> int8 GEMM -> requantise equals the float evaluation up to fp32 summation).
 """
 import torch
 from torch import nn
@@ -62,20 +66,30 @@ class Quantize:
         self.compress.update_weights()
         return self.model
 
-    # ------------------------------------------------------------------ QAT (weights only)
+    # ------------------------------------------------------------------ QAT
     def _prepare_QAT(self):
         if not hasattr(self.model, "_weight_transforms"):
             raise _lib.SirenB200Error("QAT needs the fused Siren model")
+        qc = dict(self.quant_conf)
         self._observers = {}
         self._targets = [(n, m) for n, m in self.model.named_modules() if isinstance(m, nn.Linear)]
         for name, _ in self._targets:
             self._observers[name] = _QATWeightObserver()
         self.model._weight_transforms.append(self._fake_quant_weights)
+        self._activations = bool(qc.get("activations", True))
+        if self._activations:
+            dev = next(self.model.parameters()).device
+            state = torch.tensor([[float("inf"), float("-inf"), 1.0, 0.0]] * self.model.depth, dtype=torch.float32,
+                                 device=dev)
+            self.model.precision = "fp32"  # activation fake-quant lives on the fp32 engine
+            self.model._act_quant = {"state": state, "averaging_constant": 0.01, "qmin": 0, "qmax": 127}
 
     def _fake_quant_weights(self, model):
         for name, m in self._targets:
             w = m.weight.data
-            if model.training:
+            if not getattr(self, "_frozen", False):
+                # torch's FusedMovingAvgObsFakeQuantize updates its observer on EVERY forward, eval_epoch's included
+                # (observer_enabled does not follow module.training); convert() is what freezes it
                 lo, hi = self._observers[name].update(w)
             else:
                 ob = self._observers[name]
@@ -85,9 +99,18 @@ class Quantize:
             m.weight_codes, m.weight_scales = codes, scales
 
     def _convert_QAT(self):
+        """context.py:28-29 (torch.quantization.convert(model.eval())): freeze everything and expose the int8
+        module's tensors."""
         self.model.eval()
+        self._frozen = True
         self._fake_quant_weights(self.model)
         self.model._weight_transforms.remove(self._fake_quant_weights)
         for _, m in self._targets:
             m.weight.data = self.model._param_override.pop(m.weight)
+        if self._activations:
+            aq = self.model._act_quant
+            aq["frozen"] = True
+            for i, layer in enumerate(self.model.layers):
+                layer.linear.act_scale = aq["state"][i, 2].clone()
+                layer.linear.act_zero_point = aq["state"][i, 3].to(torch.int32)
         return self.model

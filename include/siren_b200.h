@@ -145,6 +145,21 @@ int sirenb200_fakequant_per_channel(const float* w, int32_t rows, int32_t cols, 
                                     const float* row_max, float neg_div, float pos_div, int8_t* codes,
                                     float* scales, float* w_out, sirenb200_stream_t stream);
 
+/* QAT activation fake-quant (quant/context.py:35-47: torch.quantization.prepare_qat puts a
+ * FusedMovingAvgObsFakeQuantize — per-tensor affine quint8 with reduce_range, i.e. [0, 127], moving-average min/max
+ * observer with averaging constant 0.01 — on the OUTPUT of every nn.Linear, models/siren.py:62).  fp32 handles only.
+ * state: device float[depth][4] = {running min, running max, scale, zero point} per layer, owned by the caller;
+ * running min / max start at +inf / -inf.  training != 0: the observers are updated from the current batch before
+ * quantising (model.train()); 0: frozen (model.eval(), and what the converted int8 model computes).  With it
+ * enabled, sirenb200_forward / forward_backward quantise every layer's pre-activation and the backward applies the
+ * straight-through mask.  enable = 0 switches it off. */
+int sirenb200_set_act_quant(sirenb200_handle_t h, float* state, int32_t enable, int32_t training,
+                            float averaging_const, int32_t qmin, int32_t qmax);
+/* The same operator on one tensor (torch.fused_moving_avg_obs_fake_quant): out = fake_quant(x) (may alias x),
+ * mask[n] (optional) = 1 where the value was not clipped, state updated as above. */
+int sirenb200_fakequant_per_tensor(const float* x, int64_t n, float* state, int32_t training, float averaging_const,
+                                   int32_t qmin, int32_t qmax, float* out, uint8_t* mask, sirenb200_stream_t stream);
+
 /* Optional per-kernel timing for bench.py's roofline: while enabled, tagged launches of this handle are
  * bracketed by cudaEvent pairs on the launching stream.  profile_read synchronises the recorded events and
  * returns, per kind, the summed device time (ms) and the launch count into HOST arrays of n_kinds entries.

@@ -341,3 +341,49 @@ def fake_quant_per_channel_weight(weight, row_min=None, row_max=None, neg_div=12
     scale = scale.clamp(min=torch.finfo(torch.float32).eps)
     q = torch.clamp(torch.round(weight * (1.0 / scale)[:, None]), -128, 127)  # torch.round = RNE
     return q.to(torch.int8), scale, q * scale[:, None]
+
+
+# ----------------------------------------------------------------------------------------------------
+# QAT activation fake-quant
+# ----------------------------------------------------------------------------------------------------
+def fused_obs_fake_quant(x, state, training=True, averaging_const=0.01, qmin=0, qmax=127):
+    """What torch.quantization.prepare_qat puts on every nn.Linear output of the reference model
+    (pipeline/quant/context.py:35-47 -> torch FusedMovingAvgObsFakeQuantize; third-party arithmetic: PyTorch,
+    aten/src/ATen/native/quantized/cpu/fused_obs_fake_quant.cpp + fbgemm's ChooseQuantizationParams), restated:
+    state = [running min, running max, scale, zero point] (python floats, running min/max start at +-inf).
+    Returns (fake_quant(x), mask, new_state).  Pinned against the installed torch by tests/test_oracle_golden.py."""
+    f32 = np.float32
+    rmin, rmax = state[0], state[1]
+    if training:
+        cmin, cmax = f32(x.min().item()), f32(x.max().item())
+        if math.isinf(rmin) or math.isinf(rmax):
+            rmin, rmax = cmin, cmax
+        else:
+            rmin = f32(f32(rmin) + f32(averaging_const) * f32(cmin - f32(rmin)))
+            rmax = f32(f32(rmax) + f32(averaging_const) * f32(cmax - f32(rmax)))
+    mn, mx = min(float(rmin), 0.0), max(float(rmax), 0.0)
+    scale = (mx - mn) / (qmax - qmin)
+    if f32(scale) == 0.0 or math.isinf(1.0 / f32(scale)):
+        scale = 0.1
+    small = 6.1e-5
+    if scale < small:
+        org = f32(scale)
+        scale = small
+        if mn == 0.0:
+            mx = small * (qmax - qmin)
+        elif mx == 0.0:
+            mn = -small * (qmax - qmin)
+        else:
+            amp = f32(small / org)
+            mn *= amp
+            mx *= amp
+    zmin, zmax = qmin - mn / scale, qmax - mx / scale
+    emin, emax = abs(qmin) - abs(mn / scale), abs(qmax) - abs(mx / scale)
+    z0 = zmin if emin < emax else zmax
+    zp = qmin if z0 < qmin else (qmax if z0 > qmax else int(np.rint(z0)))
+    s32 = f32(scale)
+    inv = f32(1.0) / s32
+    q = np.rint(x.detach().numpy().astype(f32) * inv) + f32(zp)
+    mask = (q >= qmin) & (q <= qmax)
+    out = (np.clip(q, qmin, qmax) - f32(zp)).astype(f32) * s32
+    return torch.from_numpy(out), torch.from_numpy(mask), [float(rmin), float(rmax), float(s32), float(zp)]

@@ -123,3 +123,24 @@ def test_erk_densities_match_reference_init(golden):
     for n in names:
         mask = (torch.rand(shapes[n]) < probs[n]).float()
         assert torch.equal(mask, torch.from_numpy(g["init_mask/" + n])), n
+
+
+def test_oracle_act_fake_quant_is_pinned_by_installed_torch():
+    """The activation fake-quant restatement against torch.fused_moving_avg_obs_fake_quant itself (the operator the
+    reference's prepare_qat installs): outputs, running min/max, scale and zero point bit for bit."""
+    rng = np.random.RandomState(0)
+    torch.manual_seed(0)
+    for trial in range(60):
+        n = int(rng.randint(1, 1500))
+        x = torch.randn(n) * float(10 ** rng.uniform(-6, 2)) + float(rng.uniform(-1, 1) * 10 ** rng.uniform(-6, 1))
+        rmin, rmax = torch.tensor(float("inf")), torch.tensor(float("-inf"))
+        scale, zp = torch.tensor([1.0]), torch.tensor([0], dtype=torch.int32)
+        state = [float("inf"), float("-inf"), 1.0, 0.0]
+        for it in range(3):
+            xx = x * (1 + 0.3 * it) - 0.1 * it * x.abs().max()
+            want = torch.fused_moving_avg_obs_fake_quant(xx, torch.tensor([1]), torch.tensor([1]), rmin, rmax, scale,
+                                                         zp, 0.01, 0, 127, 0, False, False)
+            got, _, state = O.fused_obs_fake_quant(xx, state)
+            assert torch.equal(got, want)
+            assert state[0] == float(rmin) and state[1] == float(rmax)
+            assert state[2] == float(scale) and state[3] == float(zp)

@@ -187,7 +187,52 @@ def quant_case():
     print("quant ok")
 
 
+def qat_case():
+    """Quantize(QAT) of the reference on its own Siren (quant/context.py:28-47): prepare_qat, 6 train_epoch steps
+    with an eval_epoch in between, convert() -> per-step losses, activation observers, int8 weights."""
+    out = {}
+    model = build(0, 4, 32)
+    grid = ns.get_grid(12, 12)
+    img = synth_image(12, 12, 2)
+    optim, sched = ns.get_optimizer_lr_scheduler(model, AD(name="adam", lr=3e-4), quantize_mode=True)
+    for i, p in enumerate(model.parameters()):
+        out[f"param{i}"] = t2n(p)
+    out["grid"], out["img"] = t2n(grid), t2n(img)
+    model.train()  # prepare_qat asserts training mode on current torch (SURVEY.md App. A.8)
+    qcfg = AD(name="QAT", qconfig="fbgemm", num_steps=6)
+    losses, evals = [], []
+    with ns.Quantize(model, optim, qcfg) as q:
+        for i in range(6):
+            losses.append(ns.train_epoch(model, optim, grid, img, lr_scheduler=sched))
+            if i == 2:
+                _, l_, p_, _ = ns.eval_epoch(model, grid, img)
+                evals.append(l_)
+        for i, layer in enumerate(model.layers):
+            app = layer.linear.activation_post_process
+            out[f"act_min{i}"] = t2n(app.activation_post_process.min_val)
+            out[f"act_max{i}"] = t2n(app.activation_post_process.max_val)
+            out[f"act_scale{i}"] = t2n(app.scale)
+            out[f"act_zp{i}"] = t2n(app.zero_point)
+            out[f"w_scale{i}"] = t2n(layer.linear.weight_fake_quant.scale)
+        for i, p in enumerate(model.parameters()):
+            out[f"param_after{i}"] = t2n(p)
+    out["losses"] = np.array(losses, dtype=np.float64)
+    out["eval_losses"] = np.array(evals, dtype=np.float64)
+    qm = q.convert()
+    for i, layer in enumerate(qm.layers):
+        lin = layer.linear
+        out[f"int8_w{i}"] = t2n(lin.weight().int_repr())
+        out[f"int8_w_scale{i}"] = t2n(lin.weight().q_per_channel_scales()).astype(np.float32)
+        out[f"int8_out_scale{i}"] = np.float32(lin.scale)
+        out[f"int8_out_zp{i}"] = np.int32(lin.zero_point)
+    np.savez_compressed(os.path.join(OUT, "qat.npz"), **out)
+    print("qat ok", losses)
+
+
 if __name__ == "__main__":
+    if "--only-qat" in sys.argv:
+        qat_case()
+        sys.exit(0)
     fit_case("d3_w16", 3, 16, 8, 10, 20)
     fit_case("d4_w128", 4, 128, 24, 32, 10)
     fit_case("d3_w256", 3, 256, 16, 24, 3, keep_traj=False)
@@ -206,5 +251,6 @@ if __name__ == "__main__":
                               decay_schedule="cosine", end_when=12, interval=4))
     decay_case()
     quant_case()
+    qat_case()
     copy  # noqa
     print("golden written to", OUT)
