@@ -22,7 +22,9 @@ enum SimtOp {
   OP_NT_SINE = 0,  // C = A[M,K] * B[N,K]^T + bias ; Z <- C, Out <- sin(omega*C)     (forward)
   OP_NT_LIN = 1,   // C = A * B^T + bias ; Out <- C                                   (last layer)
   OP_NN_DCOS = 2,  // C = A[M,K] * B[K,N] ; Out <- C * omega*cos(omega*Z)              (dX + dsine)
-  OP_TN_PART = 3   // C = A[K,M]^T * B[K,N] over k in this split ; Out[split] <- C     (dW partial)
+  OP_TN_PART = 3,  // C = A[K,M]^T * B[K,N] over k in this split ; Out[split] <- C     (dW partial)
+  OP_NT_RELU = 4,  // C = A * B^T + bias ; Z <- C, Out <- max(C, 0)                     (FourierNet forward, fourier.py:44-52)
+  OP_NN_DRELU = 5  // C = A[M,K] * B[K,N] ; Out <- C * [Z > 0]                          (dX + dReLU)
 };
 
 struct SimtGemmArgs {
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmArgs a) {
     for (int i = threadIdx.x; i < 16 * 64; i += 256) {
       int kk, nn;
       float v = 0.f;
-      if (OP == OP_NT_SINE || OP == OP_NT_LIN) {  // B is [N, K]
+      if (OP == OP_NT_SINE || OP == OP_NT_LIN || OP == OP_NT_RELU) {  // B is [N, K]
         nn = i >> 4;
         kk = i & 15;
         if (k0 + kk < k_end && n0 + nn < a.N) v = a.B[int64_t(n0 + nn) * a.ldb + k0 + kk];
@@ -118,6 +120,12 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmArgs a) {
       } else if (OP == OP_NN_DCOS) {
         const float z = a.Z[int64_t(m) * a.ldo + n];
         a.Out[int64_t(m) * a.ldo + n] = c * (a.omega * cosf(z * a.omega));
+      } else if (OP == OP_NT_RELU) {
+        c += a.bias[n];
+        a.Z[int64_t(m) * a.ldo + n] = c;
+        a.Out[int64_t(m) * a.ldo + n] = fmaxf(c, 0.f);
+      } else if (OP == OP_NN_DRELU) {
+        a.Out[int64_t(m) * a.ldo + n] = a.Z[int64_t(m) * a.ldo + n] > 0.f ? c : 0.f;
       } else {
         a.Out[(int64_t(blockIdx.z) * a.M + m) * a.ldo + n] = c;
       }
@@ -125,6 +133,31 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemmArgs a) {
     if (OP == OP_TN_PART && a.ColSum && blockIdx.x == 0 && tx == 0)
       a.ColSum[int64_t(blockIdx.z) * a.M + m] = csum[i];
   }
+}
+
+// FourierNet's input encoding (fourier.py:20-25): xp = (2 pi x) @ B, features = [sin(xp) | cos(xp)], x = the RAW grid
+// coordinates in [0, 1] (h, w).  enc: [npix, 2 * half] fp32.
+__global__ void fourier_encode_kernel(CoordSrc c, const float* B, int half, float* enc, int64_t npix) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (idx >= npix * half) return;
+  const int64_t p = idx / half;
+  const int j = int(idx - p * half);
+  float gh, gw;
+  const int64_t pp = p + c.p_offset;
+  if (c.coords) {
+    const float2 v = reinterpret_cast<const float2*>(c.coords)[pp];
+    gh = v.x;
+    gw = v.y;
+  } else {
+    const unsigned pu = unsigned(pp);
+    const int r = int(pu / unsigned(c.width)), col = int(pu - unsigned(r) * unsigned(c.width));
+    gh = __ldg(c.lin_h + c.row_begin + r);
+    gw = __ldg(c.lin_w + col);
+  }
+  const float two_pi = 6.283185307179586f;
+  const float xp = fmaf(__fmul_rn(two_pi, gw), B[half + j], __fmul_rn(__fmul_rn(two_pi, gh), B[j]));
+  enc[p * (2 * half) + j] = sinf(xp);
+  enc[p * (2 * half) + half + j] = cosf(xp);
 }
 
 // materialise x = (grid - 0.5) * 2 as [npix, 2] fp32 (fp32 path only)
@@ -150,12 +183,29 @@ struct LossArgs {
   int mode;
   int outermost_linear;
   float omega;
+  int out_kind;        // 0: pred = o / 2 + 0.5 (siren.py:131); 1: pred = sigmoid(y) (fourier.py:55-56)
 };
 __global__ void __launch_bounds__(256) simt_loss_kernel(const LossArgs a) {
   float lsum = 0.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < a.n;
        i += int64_t(gridDim.x) * blockDim.x) {
     const float z = a.y[i];
+    if (a.out_kind == 1) {
+      const float pred = 1.0f / (1.0f + expf(-z));
+      if (a.pred) a.pred[i] = pred;
+      if (a.mode != 0) {
+        float g;
+        if (a.mode == 1) {
+          const float d = pred - a.img[i];
+          lsum += d * d;
+          g = 2.0f * d;  // the caller's scale is 1 / (H W C): d(mean sq err)/d(pred) = 2 d / (H W C)
+        } else {
+          g = a.img[i];
+        }
+        a.g[i] = g * pred * (1.0f - pred);
+      }
+      continue;
+    }
     const float o = a.outermost_linear ? z : sinf(z * a.omega);
     const float pred = o / 2 + 0.5f;
     if (a.pred) a.pred[i] = pred;

@@ -128,6 +128,12 @@ struct sirenb200_plan {
   float actq_avg = 0.01f;
   unsigned char* actq_mask = nullptr;   // [(D-1) * npix * W + npix * C] straight-through masks
   float* actq_partial = nullptr;        // [2 * kActqBlocks]
+  // model family on the fp32 path: 0 = Siren, 1 = FourierNet (models/fourier.py: Fourier-feature encoding, ReLU, sigmoid)
+  int model_kind = 0;
+  int nlin = 0;                // linear layers (Siren: depth; FourierNet: depth - 1)
+  int k0 = 2;                  // input features of the first linear layer (FourierNet: map_size)
+  const float* encB = nullptr; // FourierNet: encoding.B [2, map_size / 2] (device, caller's)
+  float* enc32 = nullptr;      // FourierNet: [npix, map_size] encoded coordinates
   bool defer_reduce = false;   // transient: tc_run leaves the partial reduction to the fused step-end kernel
   unsigned long long* bar = nullptr;  // grid-barrier counter of step_end_kernel
 
@@ -733,13 +739,23 @@ int actq_run(sirenb200_plan* p, float* x, int64_t n, float* state, unsigned char
 
 int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const float* img_or_dpred,
                 float* pred, cudaStream_t st) {
-  const int D = p->D, W = p->W, C = p->C;
+  const int L = p->nlin, W = p->W, C = p->C;
+  const bool fourier = p->model_kind == 1;
   const int64_t n = p->npix;
-  simt_coords_kernel<<<cdiv(n, 256), 256, 0, st>>>(p->coord, p->x32, n);
-  LAUNCH_CHECK();
-  const float* in = p->x32;
-  int in_dim = p->cfg.in_features;
-  for (int l = 0; l < D - 1; ++l) {
+  const float* in;
+  int in_dim = p->k0;
+  if (fourier) {
+    if (!p->encB) return fail(SIRENB200_ERR_STATE, "FourierNet: call sirenb200_set_fourier_encoding first");
+    const int half = p->k0 / 2;
+    fourier_encode_kernel<<<cdiv(n * half, 256), 256, 0, st>>>(p->coord, p->encB, half, p->enc32, n);
+    LAUNCH_CHECK();
+    in = p->enc32;
+  } else {
+    simt_coords_kernel<<<cdiv(n, 256), 256, 0, st>>>(p->coord, p->x32, n);
+    LAUNCH_CHECK();
+    in = p->x32;
+  }
+  for (int l = 0; l < L - 1; ++l) {
     SimtGemmArgs a{};
     a.A = in;
     a.B = prm[2 * l];
@@ -753,7 +769,7 @@ int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const floa
     a.ldb = in_dim;
     a.ldo = W;
     a.omega = omega_of(p, l);
-    int rc = launch_simt<OP_NT_SINE>(a, 1, st);
+    int rc = fourier ? launch_simt<OP_NT_RELU>(a, 1, st) : launch_simt<OP_NT_SINE>(a, 1, st);
     if (rc) return rc;
     if (p->actq_on) {  // z <- fake_quant(z), a <- sin(omega z_q)   (activation_post_process of the qat Linear)
       rc = actq_run(p, a.Z, n * W, p->actq_state + 4 * l, p->actq_mask + size_t(l) * n * W, a.Out, a.omega, st);
@@ -765,8 +781,8 @@ int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const floa
   {
     SimtGemmArgs a{};
     a.A = in;
-    a.B = prm[2 * (D - 1)];
-    a.bias = prm[2 * (D - 1) + 1];
+    a.B = prm[2 * (L - 1)];
+    a.bias = prm[2 * (L - 1) + 1];
     a.Out = p->y32;
     a.M = int(n);
     a.N = C;
@@ -777,7 +793,7 @@ int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const floa
     int rc = launch_simt<OP_NT_LIN>(a, 1, st);
     if (rc) return rc;
     if (p->actq_on) {
-      rc = actq_run(p, p->y32, n * C, p->actq_state + 4 * (D - 1), p->actq_mask + size_t(D - 1) * n * W, nullptr, 0.f,
+      rc = actq_run(p, p->y32, n * C, p->actq_state + 4 * (L - 1), p->actq_mask + size_t(L - 1) * n * W, nullptr, 0.f,
                     st);
       if (rc) return rc;
     }
@@ -791,7 +807,8 @@ int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const floa
   la.n = n * C;
   la.mode = mode;
   la.outermost_linear = p->cfg.outermost_linear;
-  la.omega = omega_of(p, D - 1);
+  la.omega = omega_of(p, L - 1);
+  la.out_kind = fourier ? 1 : 0;
   simt_loss_kernel<<<256, 256, 0, st>>>(la);
   LAUNCH_CHECK();
   return 0;
@@ -799,7 +816,8 @@ int f32_forward(sirenb200_plan* p, const float* const* prm, int mode, const floa
 
 int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads, float scale,
                  float* stats, cudaStream_t st) {
-  const int D = p->D, W = p->W, C = p->C;
+  const int D = p->nlin, W = p->W, C = p->C;  // D = number of linear layers here
+  const bool fourier = p->model_kind == 1;
   const int64_t n = p->npix;
   const float* g = p->g32;  // dL/dz of layer l (seed units)
   int gdim = C;
@@ -817,8 +835,8 @@ int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads
     if (rc) return rc;
   }
   for (int l = D - 1; l >= 0; --l) {
-    const float* xin = (l == 0) ? p->x32 : p->a32 + size_t(l - 1) * n * W;
-    const int xdim = (l == 0) ? p->cfg.in_features : W;
+    const float* xin = (l == 0) ? (fourier ? p->enc32 : p->x32) : p->a32 + size_t(l - 1) * n * W;
+    const int xdim = (l == 0) ? p->k0 : W;
     // dW_l = g^T xin (split over pixels), db_l = column sums of g
     SimtGemmArgs a{};
     a.A = g;
@@ -860,7 +878,7 @@ int f32_backward(sirenb200_plan* p, const float* const* prm, float* const* grads
       b.ldb = W;
       b.ldo = W;
       b.omega = omega_of(p, l - 1);
-      rc = launch_simt<OP_NN_DCOS>(b, 1, st);
+      rc = fourier ? launch_simt<OP_NN_DRELU>(b, 1, st) : launch_simt<OP_NN_DCOS>(b, 1, st);
       if (rc) return rc;
       if (p->actq_on) {
         rc = mask_grad(p->dz32[pp], l - 1, n * W);
@@ -943,11 +961,22 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
   if (cfg->precision != SIRENB200_PREC_F16TC && cfg->precision != SIRENB200_PREC_FP32)
     return fail(SIRENB200_ERR_INVALID, "unknown precision %d", cfg->precision);
 
+  const int model_kind = cfg->reserved[0], map_size = cfg->reserved[1];
+  if (model_kind != 0 && model_kind != 1) return fail(SIRENB200_ERR_INVALID, "unknown model kind %d", model_kind);
+  if (model_kind == 1) {  // FourierNet (models/fourier.py)
+    if (cfg->precision != SIRENB200_PREC_FP32)
+      return fail(SIRENB200_ERR_INVALID, "FourierNet runs on the fp32 path (SIRENB200_PREC_FP32)");
+    if (map_size < 2 || (map_size & 1)) return fail(SIRENB200_ERR_INVALID, "FourierNet: map_size %d must be even", map_size);
+    if (cfg->depth < 3) return fail(SIRENB200_ERR_INVALID, "FourierNet: depth %d < 3", cfg->depth);
+  }
   sirenb200_plan* p = new sirenb200_plan();
   p->cfg = *cfg;
   p->device = dev;
   p->nsm = prop.multiProcessorCount;
-  p->D = cfg->depth;
+  p->model_kind = model_kind;
+  p->nlin = model_kind == 1 ? cfg->depth - 1 : cfg->depth;
+  p->k0 = model_kind == 1 ? map_size : cfg->in_features;
+  p->D = p->nlin;  // every per-layer loop below counts LINEAR layers
   p->Wm = cfg->hidden;
   p->W = cfg->hidden;
   if (cfg->precision == SIRENB200_PREC_F16TC)  // kernel width: the tcgen05 kernels exist for 128 / 256 / 512 columns
@@ -998,8 +1027,9 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     if (splits < 1) splits = 1;
     p->simt_splits = splits;
     p->simt_split_len = cdiv(cdiv(p->npix, splits), 16) * 16;
+    if (p->model_kind == 1) ALLOC(p->enc32, p->npix * p->k0);
     int64_t big = int64_t(W) * W;
-    if (big < 2 * int64_t(W)) big = 2 * int64_t(W);
+    if (big < int64_t(p->k0) * W) big = int64_t(p->k0) * W;
     if (big < int64_t(C) * W) big = int64_t(C) * W;
     ALLOC(p->part32, int64_t(splits) * (big + W + 16));
   } else {
@@ -1119,7 +1149,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
 
 int sirenb200_destroy(sirenb200_handle_t p) {
   if (!p) return 0;
-  void* ptrs[] = {p->actq_mask, p->actq_partial, p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
+  void* ptrs[] = {p->enc32, p->actq_mask, p->actq_partial, p->bar, p->pace, p->gstate, p->loss_part, p->eval_acc, p->x32,     p->z32,     p->a32,
                   p->y32,    p->g32,       p->dz32[0],  p->dz32[1], p->part32,  p->act,
                   p->dz,     p->wh,        p->wth,      p->dw_part, p->db_part, p->last_part,
                   p->l0_part, p->tab0,     p->bias_w,   p->bias_raw, p->dbg_timeline, p->w0p, p->b0p,
@@ -1247,6 +1277,13 @@ int sirenb200_backward(sirenb200_handle_t h, const float* const* prm, const floa
     rc = tc_dispatch(h, prm, 2, dpred, nullptr, grads, 1.0f, stats, st);
   }
   return rc;
+}
+
+int sirenb200_set_fourier_encoding(sirenb200_handle_t h, const float* B) {
+  if (!h || !B) return fail(SIRENB200_ERR_INVALID, "null argument");
+  if (h->model_kind != 1) return fail(SIRENB200_ERR_STATE, "not a FourierNet handle");
+  h->encB = B;
+  return 0;
 }
 
 int sirenb200_set_act_quant(sirenb200_handle_t h, float* state, int32_t enable, int32_t training, float averaging_const,

@@ -20,7 +20,7 @@ def default_precision(hidden, depth=3):
 
 class SirenEngine:
     def __init__(self, depth, hidden, first_omega, hidden_omega, outermost_linear, out_features,
-                 height, width, row_begin=0, row_end=None, precision=None, device=None):
+                 height, width, row_begin=0, row_end=None, precision=None, device=None, model_kind=0, map_size=0):
         if not torch.cuda.is_available():
             raise _lib.SirenB200Error("no CUDA device: siren-b200 needs an sm_100a GPU (no CPU fallback)")
         self.lib = _lib.load()
@@ -34,6 +34,9 @@ class SirenEngine:
                                first_omega=float(first_omega), hidden_omega=float(hidden_omega),
                                outermost_linear=int(bool(outermost_linear)), height=height, width=width,
                                row_begin=row_begin, row_end=row_end, precision=precision)
+        self.cfg.reserved[0], self.cfg.reserved[1] = int(model_kind), int(map_size)
+        self.model_kind = int(model_kind)
+        self.num_linear = depth - 1 if model_kind == 1 else depth  # FourierNet: depth - 1 nn.Linear layers
         self.depth, self.hidden, self.out_features = depth, hidden, out_features
         self.height, self.width = height, width
         self.row_begin, self.row_end = row_begin, row_end
@@ -91,8 +94,8 @@ class SirenEngine:
         return torch.cuda.current_stream().cuda_stream
 
     def _check_params(self, params):
-        if len(params) != 2 * self.depth:
-            raise _lib.SirenB200Error(f"expected {2 * self.depth} parameter tensors, got {len(params)}")
+        if len(params) != 2 * self.num_linear:
+            raise _lib.SirenB200Error(f"expected {2 * self.num_linear} parameter tensors, got {len(params)}")
         for p in params:
             if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
                 raise _lib.SirenB200Error("parameters must be contiguous fp32 CUDA tensors "
@@ -135,11 +138,17 @@ class SirenEngine:
             self._act_state = None
             return
         _lib.require_cuda(state, "state")
-        if state.dtype != torch.float32 or tuple(state.shape) != (self.depth, 4) or not state.is_contiguous():
+        if state.dtype != torch.float32 or tuple(state.shape) != (self.num_linear, 4) or not state.is_contiguous():
             raise _lib.SirenB200Error("activation-quant state must be a contiguous [depth, 4] fp32 tensor")
         self._act_state = state  # keep-alive
         _lib.check(self.lib.sirenb200_set_act_quant(self.handle, state.data_ptr(), 1, int(bool(training)),
                                                     float(averaging_const), int(qmin), int(qmax)))
+
+    def set_fourier_encoding(self, B):
+        """FourierNet: encoding.B [2, map_size / 2] (fourier.py:16-25)."""
+        _lib.require_cuda(B, "B")
+        self._enc_B = B.detach().to(torch.float32).contiguous()
+        _lib.check(self.lib.sirenb200_set_fourier_encoding(self.handle, self._enc_B.data_ptr()))
 
     def workspace_bytes(self):
         return int(self.lib.sirenb200_workspace_bytes(self.handle))

@@ -53,7 +53,9 @@ typedef struct {
   int32_t row_begin;        /* this handle processes image rows [row_begin, row_end) (pixel sharding) */
   int32_t row_end;
   int32_t precision;        /* sirenb200_precision */
-  int32_t reserved[4];
+  int32_t reserved[4];      /* [0] model family: 0 = Siren, 1 = FourierNet (models/fourier.py:28-69; fp32 path; `depth`
+                             *     is then FourierNet's depth, i.e. depth - 1 linear layers, ReLU between them,
+                             *     sigmoid on the output); [1] FourierNet map_size; [2], [3] zero */
 } sirenb200_config_t;
 
 int sirenb200_version(void);
@@ -68,6 +70,11 @@ int64_t sirenb200_workspace_bytes(sirenb200_handle_t h);
  * [rows*width, 2] coordinate tensor (values in [0,1], (h, w) order) for arbitrary grids. */
 int sirenb200_set_grid_lut(sirenb200_handle_t h, const float* lin_h, const float* lin_w);
 int sirenb200_set_grid_coords(sirenb200_handle_t h, const float* coords);
+
+/* FourierNet only: encoding.B (models/fourier.py:16-25), device fp32 [2, map_size / 2] row-major, read on every
+ * forward (it is a frozen nn.Parameter of the model).  Parameter tables of a FourierNet handle are
+ * [w0, b0, w1, b1, ...] of its depth - 1 nn.Linear layers. */
+int sirenb200_set_fourier_encoding(sirenb200_handle_t h, const float* B);
 
 /* Siren.forward (models/siren.py:123-134): pred[rows, width, out_features] fp32 in [0,1] space. */
 int sirenb200_forward(sirenb200_handle_t h, const float* const* h_params, float* pred,

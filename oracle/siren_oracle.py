@@ -387,3 +387,45 @@ def fused_obs_fake_quant(x, state, training=True, averaging_const=0.01, qmin=0, 
     mask = (q >= qmin) & (q <= qmax)
     out = (np.clip(q, qmin, qmax) - f32(zp)).astype(f32) * s32
     return torch.from_numpy(out), torch.from_numpy(mask), [float(rmin), float(rmax), float(s32), float(zp)]
+
+
+# ----------------------------------------------------------------------------------------------------
+# FourierNet
+# ----------------------------------------------------------------------------------------------------
+def fourier_forward(B, params, grid, keep=False):
+    """implicit_image/models/fourier.py:20-25,58-69 — x = grid.view(N, 2) (RAW [0,1] coordinates);
+    enc = [sin(2 pi x B) | cos(2 pi x B)]; (Linear, ReLU) x (depth - 2); Linear; Sigmoid.
+    params = [w0, b0, w1, b1, ...] of the depth - 1 nn.Linear layers."""
+    h, w, _ = grid.shape
+    x = grid.reshape(-1, 2).to(F32)
+    xp = (2 * np.pi * x) @ B
+    a = torch.cat([torch.sin(xp), torch.cos(xp)], dim=-1)
+    nlin = len(params) // 2
+    zs, acts = [], [a]
+    for l in range(nlin):
+        z = torch.addmm(params[2 * l + 1], a, params[2 * l].t())
+        zs.append(z)
+        if l == nlin - 1:
+            pred = torch.sigmoid(z)
+            break
+        a = torch.relu(z)
+        acts.append(a)
+    out = pred.reshape(h, w, -1)
+    return (out, zs, acts) if keep else out
+
+
+def fourier_loss_and_grads(B, params, grid, img):
+    """F.mse_loss + explicit backward of the chain above (utils/train_helper.py:151-161 on a FourierNet)."""
+    pred, zs, acts = fourier_forward(B, params, grid, keep=True)
+    d = pred.reshape(-1, pred.shape[-1]) - img.reshape(-1, img.shape[-1])
+    loss = (d * d).mean()
+    p = pred.reshape(d.shape)
+    g = (2.0 / d.numel()) * d * p * (1 - p)
+    nlin = len(params) // 2
+    grads = [None] * (2 * nlin)
+    for l in range(nlin - 1, -1, -1):
+        grads[2 * l] = g.t() @ acts[l]
+        grads[2 * l + 1] = g.sum(0)
+        if l > 0:
+            g = (g @ params[2 * l]) * (zs[l - 1] > 0).to(F32)
+    return loss, grads

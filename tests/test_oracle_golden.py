@@ -144,3 +144,18 @@ def test_oracle_act_fake_quant_is_pinned_by_installed_torch():
             assert torch.equal(got, want)
             assert state[0] == float(rmin) and state[1] == float(rmax)
             assert state[2] == float(scale) and state[3] == float(zp)
+
+
+def test_oracle_fouriernet_vs_reference_golden(golden):
+    g = golden("fourier.npz")
+    names = [str(n) for n in g["names"]]
+    B = torch.from_numpy(g["param/encoding.B"])
+    params = [torch.from_numpy(g["param/" + n]) for n in names if n != "encoding.B"]
+    grid, img = torch.from_numpy(g["grid"]), torch.from_numpy(g["img"])
+    pred = O.fourier_forward(B, params, grid)
+    assert (pred - torch.from_numpy(g["pred"])).abs().max().item() <= 2e-6
+    loss, grads = O.fourier_loss_and_grads(B, params, grid, img)
+    assert abs(loss.item() - float(g["loss"])) <= 2e-6 * float(g["loss"])
+    for n, gr in zip([n for n in names if n != "encoding.B"], grads):
+        want = torch.from_numpy(g["grad/" + n])
+        assert ((gr.reshape(want.shape) - want).norm() / want.norm()).item() <= 5e-6, n

@@ -187,6 +187,35 @@ def quant_case():
     print("quant ok")
 
 
+def fourier_case():
+    """FourierNet (models/fourier.py) of the reference: prediction, loss, gradients at init and a short Adam fit."""
+    torch.manual_seed(0)
+    model = ns.model_registry["fourier"](name="fourier", depth=5, hidden_size=48, map_size=32, map_scale=16,
+                                         small_dense_density=1.0)
+    H, W = 20, 28
+    grid = ns.get_grid(H, W)
+    img = synth_image(H, W, 1)
+    out = {"depth": 5, "hidden": 48, "map_size": 32, "map_scale": 16, "grid": t2n(grid), "img": t2n(img)}
+    names = [n for n, _ in model.named_parameters()]
+    out["names"] = np.array(names)
+    for n, p in model.named_parameters():
+        out["param/" + n] = t2n(p)
+    pred = model(grid)
+    loss = torch.nn.functional.mse_loss(pred, img)
+    loss.backward()
+    out["pred"], out["loss"] = t2n(pred), np.float32(loss.item())
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            out["grad/" + n] = t2n(p.grad)
+    optim, sched = ns.get_optimizer_lr_scheduler(model, AD(name="adam", lr=3e-4))
+    losses = [ns.train_epoch(model, optim, grid, img, lr_scheduler=sched) for _ in range(10)]
+    out["losses"] = np.array(losses, dtype=np.float64)
+    _, l_, psnr, _ = ns.eval_epoch(model, grid, img)
+    out["eval_loss"], out["eval_psnr"] = np.float64(l_), np.float64(psnr)
+    np.savez_compressed(os.path.join(OUT, "fourier.npz"), **out)
+    print("fourier ok", losses[:3])
+
+
 def qat_case():
     """Quantize(QAT) of the reference on its own Siren (quant/context.py:28-47): prepare_qat, 6 train_epoch steps
     with an eval_epoch in between, convert() -> per-step losses, activation observers, int8 weights."""
@@ -233,6 +262,9 @@ if __name__ == "__main__":
     if "--only-qat" in sys.argv:
         qat_case()
         sys.exit(0)
+    if "--only-fourier" in sys.argv:
+        fourier_case()
+        sys.exit(0)
     fit_case("d3_w16", 3, 16, 8, 10, 20)
     fit_case("d4_w128", 4, 128, 24, 32, 10)
     fit_case("d3_w256", 3, 256, 16, 24, 3, keep_traj=False)
@@ -252,5 +284,6 @@ if __name__ == "__main__":
     decay_case()
     quant_case()
     qat_case()
+    fourier_case()
     copy  # noqa
     print("golden written to", OUT)
