@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "sirenb200_profile_read", "sirenb200_debug_timeline", "sirenb200_sched_step", "sirenb200_adam_step_dev",
     "sirenb200_comm_create", "sirenb200_comm_handle", "sirenb200_comm_connect", "sirenb200_comm_allreduce",
     "sirenb200_comm_destroy", "sirenb200_fit_steps", "sirenb200_fit_step", "sirenb200_set_act_quant",
-    "sirenb200_fakequant_per_tensor", "sirenb200_set_fourier_encoding",
+    "sirenb200_fakequant_per_tensor", "sirenb200_set_fourier_encoding", "sirenb200_pack_stream",
 ]
 
 PROFILE_KINDS = ["weight_staging", "first_layer", "fwd_gemm", "last_layer_loss", "dx_gemm", "dw_gemm",
@@ -96,6 +96,8 @@ def load():
     lib.sirenb200_fit_steps.argtypes = [vp, c_int32, vp, POINTER(FitArgs), vp]
     lib.sirenb200_fit_step.argtypes = [vp, vp, POINTER(FitArgs), vp]
     lib.sirenb200_set_fourier_encoding.argtypes = [vp, vp]
+    lib.sirenb200_pack_stream.argtypes = [c_int32, vpp, vpp, POINTER(c_int32), POINTER(c_int64), POINTER(c_int64),
+                                          POINTER(c_int64), vp, vp]
     lib.sirenb200_set_act_quant.argtypes = [vp, vp, c_int32, c_int32, c_float, c_int32, c_int32]
     lib.sirenb200_fakequant_per_tensor.argtypes = [vp, c_int64, vp, c_int32, c_float, c_int32, c_int32, vp, vp, vp]
     lib.sirenb200_kmeans_quantize.argtypes = [vp, c_int64, c_int32, c_int32, c_float, vp, vp, vp, vp,

@@ -1333,6 +1333,67 @@ __global__ void __launch_bounds__(256) mul_mask_u8_kernel(float* g, const unsign
 }
 
 // ------------------------------------------------------------------------------------------
+// Device-side packing for the entropy coder (pipeline/entropy_coding/__init__.py:15-41,70-120): the byte stream
+// the reference builds on the host — `model.half()` tensors and uint8 k-means codes written back to back in
+// state_dict order — is assembled by ONE kernel into one contiguous device buffer (one D2H copy feeds zstd), and
+// taken apart again by one kernel (`decompress_state_dict`: fp16 -> fp32, weight = centroids[labels]).
+// ------------------------------------------------------------------------------------------
+constexpr int kPackMaxItems = 96;
+enum PackKind {
+  PACK_F32_TO_F16 = 0,   // float -> IEEE half (round to nearest even, as tensor.half())
+  PACK_I64_TO_U8 = 1,    // int64 labels -> uint8
+  PACK_I64_TO_U16 = 2,   // int64 labels -> uint16
+  PACK_RAW = 3,          // byte copy (count = bytes)
+  UNPACK_F16_TO_F32 = 4, // half -> float
+  UNPACK_GATHER_U8 = 5,  // weight[i] = float(centroids_f16[codes_u8[i]])   (aux = stream offset of the centroids)
+  UNPACK_GATHER_U16 = 6
+};
+struct PackItem {
+  const void* src;     // pack: the tensor; unpack: unused
+  void* dst;           // unpack: the destination tensor; pack: unused
+  long long offset;    // byte offset inside the stream
+  long long count;     // elements (PACK_RAW: bytes)
+  long long aux;       // UNPACK_GATHER_*: byte offset of the fp16 code book inside the stream
+  int kind;
+  int pad_;
+};
+struct PackArgs {
+  PackItem item[kPackMaxItems];
+  int nitems;
+  unsigned char* stream;
+};
+__global__ void __launch_bounds__(256) pack_stream_kernel(const PackArgs a) {
+  const PackItem it = a.item[blockIdx.y];
+  unsigned char* base = a.stream + it.offset;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < it.count; i += (long long)gridDim.x * blockDim.x) {
+    switch (it.kind) {
+      case PACK_F32_TO_F16:
+        reinterpret_cast<__half*>(base)[i] = __float2half_rn(static_cast<const float*>(it.src)[i]);
+        break;
+      case PACK_I64_TO_U8:
+        base[i] = static_cast<unsigned char>(static_cast<const long long*>(it.src)[i]);
+        break;
+      case PACK_I64_TO_U16:
+        reinterpret_cast<unsigned short*>(base)[i] = static_cast<unsigned short>(static_cast<const long long*>(it.src)[i]);
+        break;
+      case PACK_RAW:
+        base[i] = static_cast<const unsigned char*>(it.src)[i];
+        break;
+      case UNPACK_F16_TO_F32:
+        static_cast<float*>(it.dst)[i] = __half2float(reinterpret_cast<const __half*>(base)[i]);
+        break;
+      case UNPACK_GATHER_U8:
+        static_cast<float*>(it.dst)[i] = __half2float(reinterpret_cast<const __half*>(a.stream + it.aux)[base[i]]);
+        break;
+      case UNPACK_GATHER_U16:
+        static_cast<float*>(it.dst)[i] =
+            __half2float(reinterpret_cast<const __half*>(a.stream + it.aux)[reinterpret_cast<const unsigned short*>(base)[i]]);
+        break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // step_end_kernel: everything of a fit step that follows the last GEMM, in ONE launch.
 //   phase 1  every block reduces ITS chunks of the split-K / per-CTA gradient partials (x scale / G);
 //            block 0 also sums the squared-error partials (F.mse_loss, train_helper.py:151-154)

@@ -1332,6 +1332,37 @@ int sirenb200_fakequant_per_tensor(const float* x, int64_t n, float* state, int3
   return 0;
 }
 
+int sirenb200_pack_stream(int32_t n_items, const void* const* h_src, void* const* h_dst, const int32_t* h_kind,
+                          const int64_t* h_count, const int64_t* h_offset, const int64_t* h_aux, uint8_t* stream_buf,
+                          sirenb200_stream_t stream) {
+  if (n_items < 1 || n_items > kPackMaxItems || !h_kind || !h_count || !h_offset || !stream_buf)
+    return fail(SIRENB200_ERR_INVALID, "pack_stream: bad argument (1 <= items <= %d)", kPackMaxItems);
+  PackArgs a{};
+  long long most = 1;
+  for (int i = 0; i < n_items; ++i) {
+    const int k = h_kind[i];
+    if (k < PACK_F32_TO_F16 || k > UNPACK_GATHER_U16) return fail(SIRENB200_ERR_INVALID, "pack_stream: kind %d", k);
+    const bool unpack = k >= UNPACK_F16_TO_F32;
+    if ((unpack && (!h_dst || !h_dst[i])) || (!unpack && (!h_src || !h_src[i])) || h_count[i] < 0 || h_offset[i] < 0)
+      return fail(SIRENB200_ERR_INVALID, "pack_stream: item %d is incomplete", i);
+    a.item[i].src = h_src ? h_src[i] : nullptr;
+    a.item[i].dst = h_dst ? h_dst[i] : nullptr;
+    a.item[i].offset = h_offset[i];
+    a.item[i].count = h_count[i];
+    a.item[i].aux = h_aux ? h_aux[i] : 0;
+    a.item[i].kind = k;
+    if (h_count[i] > most) most = h_count[i];
+  }
+  a.nitems = n_items;
+  a.stream = stream_buf;
+  int gx = cdiv(most, 256 * 4);
+  if (gx > 1024) gx = 1024;
+  if (gx < 1) gx = 1;
+  pack_stream_kernel<<<dim3(gx, n_items), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int sirenb200_eval_metrics(const float* pred, const float* img, int64_t n, float* out,
                            sirenb200_stream_t stream) {
   if (!pred || !img || !out || n <= 0) return fail(SIRENB200_ERR_INVALID, "bad argument");

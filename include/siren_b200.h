@@ -167,6 +167,17 @@ int sirenb200_set_act_quant(sirenb200_handle_t h, float* state, int32_t enable, 
 int sirenb200_fakequant_per_tensor(const float* x, int64_t n, float* state, int32_t training, float averaging_const,
                                    int32_t qmin, int32_t qmax, float* out, uint8_t* mask, sirenb200_stream_t stream);
 
+/* Device-side packing for the entropy coder (pipeline/entropy_coding/__init__.py:15-41,70-120): assembles — or takes
+ * apart — the byte stream the reference writes with NumpyParser / zstd, i.e. the tensors of
+ * linear_state_dict(model.half()) back to back.  One kernel for all items (<= 96).  Per item i: kind
+ *   0 fp32 -> fp16, 1 int64 -> uint8, 2 int64 -> uint16, 3 raw bytes            (pack:   h_src[i] -> stream + offset)
+ *   4 fp16 -> fp32, 5 / 6 weight = fp16 code book [at stream + h_aux[i]] gathered by uint8 / uint16 codes
+ *                                                                              (unpack: stream + offset -> h_dst[i])
+ * count = elements (kind 3: bytes), offsets in bytes.  Host zstd / lzma stay on the host (out of scope). */
+int sirenb200_pack_stream(int32_t n_items, const void* const* h_src, void* const* h_dst, const int32_t* h_kind,
+                          const int64_t* h_count, const int64_t* h_offset, const int64_t* h_aux, uint8_t* stream_buf,
+                          sirenb200_stream_t stream);
+
 /* Optional per-kernel timing for bench.py's roofline: while enabled, tagged launches of this handle are
  * bracketed by cudaEvent pairs on the launching stream.  profile_read synchronises the recorded events and
  * returns, per kind, the summed device time (ms) and the launch count into HOST arrays of n_kinds entries.

@@ -81,6 +81,8 @@ def _install_stubs():
         mod("torchtyping", TensorType=_TensorType)
     if "torch_scatter" not in sys.modules:
         mod("torch_scatter", scatter_mean=_scatter_mean)
+    if "zstandard" not in sys.modules:  # only the 'zstd' stream needs it; the 'plain' stream is pure Python
+        mod("zstandard")
 
 
 _cache = {}
@@ -117,3 +119,10 @@ def load():
     ns.AttrDict = AttrDict
     _cache["ns"] = ns
     return ns
+
+
+def importlib_import(name):
+    """Import another module of the (already loaded, stubbed) reference package, e.g. the entropy coder."""
+    import importlib
+    load()
+    return importlib.import_module(name)

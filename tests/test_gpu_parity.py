@@ -389,7 +389,9 @@ def test_quantize_context_qat_weights_only():
     grid, img = get_grid(24, 32, "cuda"), synth_image(24, 32, 0, device="cuda")
     optim, sched = th.get_optimizer_lr_scheduler(model, {"name": "adam", "lr": 3e-4}, quantize_mode=True)
     master0 = [p.detach().clone() for p in model.parameters()]
-    with Quantize(model, optim, dict(name="QAT", qconfig="fbgemm")) as q:
+    # activations=False: the weights-only variant, which stays on the tensor-core path (the full QAT of the
+    # reference — weights AND activation observers — is tests/test_gpu_qat.py)
+    with Quantize(model, optim, dict(name="QAT", qconfig="fbgemm", activations=False)) as q:
         l0 = th.train_epoch(model, optim, grid, img, lr_scheduler=sched)
         # gradients were taken at the fake-quantised weights and applied to the fp32 master weights
         wq = O.fake_quant_per_channel_weight(master0[2].cpu())[2]

@@ -216,6 +216,37 @@ def fourier_case():
     print("fourier ok", losses[:3])
 
 
+def entropy_case():
+    """compress_state_dict / decompress_state_dict of the reference (pipeline/entropy_coding/__init__.py) with the
+    'plain' stream on a k-means-quantised model: the exact bytes of compressed_weights.data and the decoded tensors."""
+    import json
+    import tempfile
+    ec = ref_import.importlib_import("implicit_image.pipeline.entropy_coding")
+    model = build(0, 4, 32)
+    grid = ns.get_grid(12, 12)
+    img = synth_image(12, 12, 2)
+    optim, sched = ns.get_optimizer_lr_scheduler(model, AD(name="adam", lr=3e-4), quantize_mode=True)
+    qcfg = AD(name="KMeans", bits=4, skip_ll=["layers.0.linear", "layers.3.linear"], num_steps=2)
+    out = {}
+    with ns.Quantize(model, optim, qcfg) as q:
+        for _ in range(2):
+            ns.train_epoch(model, optim, grid, img, lr_scheduler=sched)
+        ns.eval_epoch(model, grid, img)
+    qm = q.convert()
+    for k, v in qm.state_dict().items():
+        out["sd/" + k] = t2n(v)
+    with tempfile.TemporaryDirectory() as d:
+        size = ec.compress_state_dict(qm.half(), d, stream_name="plain")
+        out["bytes"] = np.frombuffer(open(os.path.join(d, "compressed_weights.data"), "rb").read(), dtype=np.uint8)
+        out["meta_json"] = np.array(open(os.path.join(d, "meta_data.json")).read())
+        assert size == out["bytes"].size
+        dec = ec.decompress_state_dict(d, stream_name="plain")
+    for k, v in dec.items():
+        out["dec/" + k] = t2n(v)
+    np.savez_compressed(os.path.join(OUT, "entropy.npz"), **out)
+    print("entropy ok", size, "bytes")
+
+
 def qat_case():
     """Quantize(QAT) of the reference on its own Siren (quant/context.py:28-47): prepare_qat, 6 train_epoch steps
     with an eval_epoch in between, convert() -> per-step losses, activation observers, int8 weights."""
@@ -262,6 +293,9 @@ if __name__ == "__main__":
     if "--only-qat" in sys.argv:
         qat_case()
         sys.exit(0)
+    if "--only-entropy" in sys.argv:
+        entropy_case()
+        sys.exit(0)
     if "--only-fourier" in sys.argv:
         fourier_case()
         sys.exit(0)
@@ -285,5 +319,6 @@ if __name__ == "__main__":
     quant_case()
     qat_case()
     fourier_case()
+    entropy_case()
     copy  # noqa
     print("golden written to", OUT)
