@@ -1067,7 +1067,9 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       // merged dX + dW launches: the reduction role gets ~30 % of the SMs (its MMA time per tile is ~2/5 of the
       // dX role's epilogue-bound time, and its loads come from L2), as (W/128 row blocks) x (column parts) x splits
       const char* env = getenv("SIRENB200_BWD_MERGED");
-      p->bwd_merged = nh > 0 && !(env && atoi(env) == 0);
+      // (hidden 512 keeps the separate launches: measured at config 3, 18.1 steps/s separate vs 15.1 merged — its
+      // reduction role needs 8 CTAs per pixel split and streams twice the operand bytes per tile)
+      p->bwd_merged = nh > 0 && (env ? atoi(env) != 0 : W <= 256);
       const int per_split = (W / 128) * (W / (W < 256 ? W : 256));
       int want = (p->nsm * 30) / 100;
       env = getenv("SIRENB200_DW_CTAS");

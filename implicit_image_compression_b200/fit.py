@@ -128,7 +128,10 @@ class Fitter:
     def _prepare_graph(self):
         opt = self.optim
         group = opt.param_groups[0]
-        params = group["params"]
+        # the tensors the kernels train: the model's hot parameters, in the optimizer's order (frozen extras such as
+        # FourierNet's encoding.B are in the optimizer but never get a gradient)
+        hot = {id(p) for p in self.flat.params}
+        params = [p for p in group["params"] if id(p) in hot]
         key = tuple(p.data_ptr() for p in params) + (self.img.data_ptr(),)
         if key == self._graph_key:
             return

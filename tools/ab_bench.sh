@@ -5,7 +5,7 @@ out=$1; shift
 i=0
 for envs in "$@"; do
   i=$((i+1))
-  env $envs python bench.py --quick --steps 50 --warmup 5 > gpurun_out/${out}_$i.json 2> gpurun_out/${out}_$i.err
+  env $envs python bench.py --quick --steps ${STEPS:-50} --warmup 5 $BENCH_ARGS > gpurun_out/${out}_$i.json 2> gpurun_out/${out}_$i.err
   python - "$envs" gpurun_out/${out}_$i.json <<'PY'
 import json, sys
 try:
