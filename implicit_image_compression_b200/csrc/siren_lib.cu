@@ -1270,6 +1270,7 @@ int sirenb200_backward(sirenb200_handle_t h, const float* const* prm, const floa
     la.mode = 2;
     la.outermost_linear = h->cfg.outermost_linear;
     la.omega = omega_of(h, h->D - 1);
+    la.out_kind = h->model_kind == 1 ? 1 : 0;
     simt_loss_kernel<<<256, 256, 0, st>>>(la);
     LAUNCH_CHECK();
     rc = f32_backward(h, prm, grads, 1.0f, stats, st);
