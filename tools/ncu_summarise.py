@@ -40,6 +40,7 @@ def launches(path):
 
 
 KIND = [("rowgemm_kernel<256, 256, 0", "fwd_gemm"), ("rowgemm_kernel<256, 256, 1", "dx_gemm"),
+        ("bwd_merged_kernel<256", "dx_gemm_merged"), ("step_end_kernel", "reduce_partials"),
         ("colgemm_kernel", "dw_gemm"), ("last_layer_tc_kernel", "last_layer_loss"), ("tail_tc_kernel", "last_layer_loss"),
         ("tc_last_layer_kernel", "last_layer_loss"), ("tc_layer0_grad_kernel", "layer0_grad"),
         ("tc_first_layer_kernel", "first_layer")]
