@@ -1575,8 +1575,7 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
 
   // ---- exchange over NVLink peer memory ----
   if (comm) {
-    if (b == 0 && tid == 0)
-      *reinterpret_cast<float4*>(mine + a.stats_off) = make_float4(sse, 0.f, 0.f, 0.f);
+    if (b == 0 && tid == 0) mine[a.stats_off] = sse;  // (the 4 stats floats need not be 16-byte aligned)
     __syncthreads();
     if (tid < a.world) {
       const int q = tid;
