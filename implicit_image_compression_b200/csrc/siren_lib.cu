@@ -53,6 +53,9 @@ inline int cdiv(int64_t a, int64_t b) { return int((a + b - 1) / b); }
 
 }  // namespace
 
+constexpr int kTimelineSlots = 3 * 4 * 8 * 16 + 12 * 16;
+constexpr int kStallLaunches = 12;  // slots: 0..5 forward layer l, 6..11 backward layer l
+
 struct sirenb200_plan {
   sirenb200_config_t cfg;
   int device = 0;
@@ -94,6 +97,9 @@ struct sirenb200_plan {
   float* w0p = nullptr;       // [W, 2] layer-0 weight, zero-padded
   float* b0p = nullptr;       // [W]    layer-0 bias, zero-padded
   CUtensorMap tm_act{}, tm_dz{};
+  CUtensorMap tm_act_c{}, tm_dz_c{};  // chunked 3-D views (one box = a whole reduction operand of a 128-pixel stage)
+  CUtensorMap tm_act_c2{};            // ... of one CTA of a pair (two activation chunks)
+  bool bwd_pair = true;               // merged backward launch: reduction role on CTA pairs (SIRENB200_PAIR=0: off)
   __half* wl16 = nullptr;   // [16, W] last-layer weights for the tensor-core last layer
   __half* wlt16 = nullptr;  // [W, 64]
   CUtensorMap tm_wl{}, tm_wlt{};
@@ -104,6 +110,7 @@ struct sirenb200_plan {
   int l0_used = 0;          // partial rows of l0_part written by the last backward
   int last_rowgemm_grid = 0;
   bool gen_first = true;    // layer 0 generated inside the first hidden GEMM (SIRENB200_GEN_FIRST=0: own kernel)
+  long long* dbg_stall = nullptr;     // SIRENB200_STALLS=1: wait-cycle counters, [launch slot][160][16] (debug)
   long long* dbg_timeline = nullptr;  // SIRENB200_TIMELINE=1: 3*4*8*16 clock64 slots (debug)
   std::vector<CUtensorMap> tm_w, tm_wt;
   float* dw_part = nullptr;  // [splits][D-2][W][W]
@@ -120,7 +127,9 @@ struct sirenb200_plan {
   bool bwd_merged = true;      // dX GEMM and weight-gradient reduction of a layer in ONE launch (SIRENB200_BWD_MERGED=0: separate)
   int dw_ctas = 0;             // CTAs of that launch that run the reduction
   int merged_splits = 0;       // pixel splits of the reduction role
-  int pace_window = 192;       // tiles the two roles may drift apart
+  int pace_window = 192;       // tiles the reduction role may run ahead of the dX role
+  int pace_window_dx = 192;    // ... the dX role ahead of the reduction role (negative: it follows that far behind)
+  int stall_slot = 0;
   // QAT activation fake-quant (fp32 handles): observer state is caller-owned, masks / partials live here
   float* actq_state = nullptr;          // [D][4] {running min, running max, scale, zero point} (device, caller's)
   bool actq_on = false;
@@ -220,6 +229,27 @@ cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// ... as clusters of two CTAs (the two SMs of a TPC): CTA pairs for cta_group::2 MMAs
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pairs(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                         Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <int W, int MODE, bool GEN = false, bool RED = false>
 int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const CUtensorMap& tmE, const CUtensorMap& tmO, const RowGemmArgs& args,
@@ -237,10 +267,12 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   const int items = args.num_tiles * NPARTS;
   int grid = items < p->nsm ? items : p->nsm;
   const uint32_t idesc = umma_idesc(128, NT, 0, 0, 0, 0);
+  RowGemmArgs ra = args;
+  ra.stall = p->dbg_stall ? p->dbg_stall + int64_t(p->stall_slot % kStallLaunches) * 160 * 16 : nullptr;
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
-    launch_ex(kfn, dim3(grid), dim3(GEN ? 544 : (RED ? 640 : 384)), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, tmA,
-              tmB, tmE, tmO, args, idesc);
+    launch_ex(kfn, dim3(grid), dim3(rowgemm_threads(MODE, GEN, RED)), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, tmA,
+              tmB, tmE, tmO, ra, idesc);
   }
   LAUNCH_CHECK();
   p->last_rowgemm_grid = grid;
@@ -261,7 +293,7 @@ int launch_colgemm(sirenb200_plan* p, const ColGemmJobs& jobs, cudaStream_t st) 
   const int grid = jobs.num_problems * jobs.mblocks * jobs.nparts * jobs.splits;
   {
     ProfScope ps(p, PK_DW_GEMM, st);
-    launch_ex(kfn, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_dz, p->tm_act, jobs,
+    launch_ex(kfn, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_dz_c, p->tm_act_c, jobs,
               umma_idesc(128, NT, 0, 0, 1, 1), umma_idesc(128, 16, 0, 0, 1, 1));
   }
   LAUNCH_CHECK();
@@ -369,6 +401,7 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     ra.omega = omega_of(p, l);
     ra.bias = p->bias_raw + size_t(l - 1) * W;  // staged (zero-padded) copy of prm[2 * l + 1]
     ra.b_early = (l >= 2) ? 1 : 0;  // layer 1 follows the weight-staging kernel directly
+    p->stall_slot = l;
     int rc;
     if constexpr (kCanGen) {
       if (l == 1 && gen_first) {
@@ -509,21 +542,46 @@ int launch_bwd_merged(sirenb200_plan* p, const RowGemmArgs& ra, const ColGemmJob
   constexpr int NPARTS = W / NT;
   using RCfg = RowGemmCfg<W, NT, MODE_DX, NPARTS>;
   using CCfg = ColGemmCfg<NT>;
-  constexpr uint32_t SMEM = RCfg::SMEM_BYTES > CCfg::SMEM_BYTES ? RCfg::SMEM_BYTES : CCfg::SMEM_BYTES;
-  auto kfn = bwd_merged_kernel<W, RED>;
-  static bool attr_set[64] = {};
-  if (!attr_set[p->device & 63]) {
-    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)));
-    attr_set[p->device & 63] = true;
-  }
+  constexpr uint32_t SMEM1 = RCfg::SMEM_BYTES > CCfg::SMEM_BYTES ? RCfg::SMEM_BYTES : CCfg::SMEM_BYTES;
+  constexpr uint32_t SMEM = SMEM1 > ColGemm2Cfg::SMEM_BYTES ? SMEM1 : ColGemm2Cfg::SMEM_BYTES;
   const int dw = jobs.num_problems * jobs.mblocks * jobs.nparts * jobs.splits;
   int dx = p->nsm - dw;
   if (dx > ra.num_tiles * NPARTS) dx = ra.num_tiles * NPARTS;
+  // CTA pairs for the reduction role: hidden 256 (one pair = both 128-row blocks of dW), both roles' CTA counts even
+  const bool pair = W == 256 && p->bwd_pair && jobs.mblocks == 2 && jobs.nparts == 1 && dx % 2 == 0 && dw % 2 == 0 &&
+                    jobs.interleave == 1;
+  RowGemmArgs rb = ra;
+  ColGemmJobs cj = jobs;
+  rb.stall = p->dbg_stall ? p->dbg_stall + int64_t(p->stall_slot % kStallLaunches) * 160 * 16 : nullptr;
+  cj.stall = rb.stall ? rb.stall + int64_t(dx) * 16 : nullptr;
+  const dim3 block(rowgemm_threads(MODE_DX, false, RED));
+  const bool pdl = p->pdl && !p->prof_on;
+  static bool attr_set[64][2] = {};
   {
     ProfScope ps(p, PK_DX_GEMM, st);
-    launch_ex(kfn, dim3(dx + dw), dim3(RED ? 640 : 384), SMEM, st, p->pdl && !p->prof_on, p->tm_dz, p->tm_wt[l - 1],
-              p->tm_act, ra, umma_idesc(128, NT, 0, 0, 0, 0), jobs, umma_idesc(128, NT, 0, 0, 1, 1),
-              umma_idesc(128, 16, 0, 0, 1, 1), dx, p->pace + 2 * l, p->pace_window);
+    if constexpr (W == 256) {
+      if (pair) {
+        auto kfn = bwd_merged_kernel<W, RED, true>;
+        if (!attr_set[p->device & 63][1]) {
+          CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)));
+          attr_set[p->device & 63][1] = true;
+        }
+        launch_pairs(kfn, dim3(dx + dw), block, SMEM, st, pdl, p->tm_dz, p->tm_wt[l - 1], p->tm_act, p->tm_dz_c,
+                     p->tm_act_c2, rb, umma_idesc(128, NT, 0, 0, 0, 0), cj, 0u, 0u, dx, p->pace + 2 * l,
+                     p->pace_window, p->pace_window_dx);
+      }
+    }
+    if (!pair) {
+      auto kfn = bwd_merged_kernel<W, RED, false>;
+      if (!attr_set[p->device & 63][0]) {
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)));
+        attr_set[p->device & 63][0] = true;
+      }
+      launch_ex(kfn, dim3(dx + dw), block, SMEM, st, pdl, p->tm_dz, p->tm_wt[l - 1], p->tm_act,
+                p->tm_dz_c, p->tm_act_c, rb,
+                umma_idesc(128, NT, 0, 0, 0, 0), cj, umma_idesc(128, NT, 0, 0, 1, 1),
+                umma_idesc(128, 16, 0, 0, 1, 1), dx, p->pace + 2 * l, p->pace_window, p->pace_window_dx);
+    }
   }
   LAUNCH_CHECK();
   p->last_rowgemm_grid = dx;
@@ -566,6 +624,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     ra.o_row0 = int((l - 1) * p->npix_pad + ch.p0);
     ra.valid_rows = int(ch.npix);
     ra.b_early = 1;  // omega W^T was staged at the start of the step, at least two kernels ago
+    p->stall_slot = 6 + l;
     int rc;
     bool done = false;
     if (merged) {
@@ -1064,14 +1123,15 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     if (splits > p->ntiles) splits = p->ntiles;
     p->col_splits = splits;  // (re-clamped to the chunk size below)
     {
-      // merged dX + dW launches: the reduction role gets ~30 % of the SMs (its MMA time per tile is ~2/5 of the
-      // dX role's epilogue-bound time, and its loads come from L2), as (W/128 row blocks) x (column parts) x splits
+      // merged dX + dW launches: the reduction role gets ~35 % of the SMs (52 of 148: its MMAs are busy ~1.1 k cycles
+      // per tile and CTA against ~3.7 k of epilogue per tile on a dX CTA; A/B at c2: 44 / 52 / 60 CTAs = 1037 / 1045 /
+      // 1030 steps/s), as (W/128 row blocks) x (column parts) x splits
       const char* env = getenv("SIRENB200_BWD_MERGED");
       // (hidden 512 keeps the separate launches: measured at config 3, 18.1 steps/s separate vs 15.1 merged — its
       // reduction role needs 8 CTAs per pixel split and streams twice the operand bytes per tile)
       p->bwd_merged = nh > 0 && (env ? atoi(env) != 0 : W <= 256);
       const int per_split = (W / 128) * (W / (W < 256 ? W : 256));
-      int want = (p->nsm * 30) / 100;
+      int want = (p->nsm * 35 + 50) / 100;
       env = getenv("SIRENB200_DW_CTAS");
       if (env && atoi(env) > 0) want = atoi(env);
       int ms = want / per_split;
@@ -1080,7 +1140,11 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->dw_ctas = ms * per_split;
       if (p->dw_ctas >= p->nsm) p->bwd_merged = false;
       env = getenv("SIRENB200_PACE_WINDOW");
-      if (env && atoi(env) > 0) p->pace_window = atoi(env);
+      if (env && atoi(env) > 0) p->pace_window = p->pace_window_dx = atoi(env);
+      env = getenv("SIRENB200_PACE_DX");
+      if (env) p->pace_window_dx = atoi(env);
+      env = getenv("SIRENB200_PAIR");
+      p->bwd_pair = !(env && atoi(env) == 0);
       if (p->bwd_merged) p->merged_splits = ms;
     }
     const int slabs = (p->bwd_merged && p->merged_splits > splits) ? p->merged_splits : splits;
@@ -1125,6 +1189,15 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     }
     int trc = make_tmap_16bit(&p->tm_act, p->act, uint64_t(D - 1) * p->npix_pad, W, 128, false);
     trc |= make_tmap_16bit(&p->tm_dz, p->dz, uint64_t(D - 1) * p->npix_pad, W, 128, false);
+    if (nh > 0) {
+      // weight-gradient reduction: one box per operand and stage = {64 columns, pixel rows, chunks}; dz chunks
+      // = one 128-row block of dW, activation chunks = one column part of dW
+      const uint32_t ychunks = (W < 256 ? W : 256) / 64;
+      trc |= make_tmap_16bit_chunks(&p->tm_dz_c, p->dz, uint64_t(D - 1) * p->npix_pad, W, 128, 2);
+      trc |= make_tmap_16bit_chunks(&p->tm_act_c, p->act, uint64_t(D - 1) * p->npix_pad, W, 128, ychunks);
+      // (CTA pairs: each CTA loads half of the activation columns)
+      trc |= make_tmap_16bit_chunks(&p->tm_act_c2, p->act, uint64_t(D - 1) * p->npix_pad, W, 128, 2);
+    }
     p->tm_w.resize(nh > 0 ? nh : 0);
     p->tm_wt.resize(nh > 0 ? nh : 0);
     for (int l = 0; l < nh; ++l) {
@@ -1139,9 +1212,12 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       sirenb200_destroy(p);
       return fail(SIRENB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", trc);
     }
-    if (getenv("SIRENB200_TIMELINE")) {
-      ALLOC(p->dbg_timeline, 3 * 4 * 8 * 16 + 12 * 16);
-      cudaMemset(p->dbg_timeline, 0, (3 * 4 * 8 * 16 + 12 * 16) * sizeof(long long));
+    if (getenv("SIRENB200_TIMELINE") || getenv("SIRENB200_STALLS")) {
+      // timeline slots, then (SIRENB200_STALLS) kStallLaunches x 160 CTAs x 16 wait-cycle counters
+      const int64_t n = kTimelineSlots + (getenv("SIRENB200_STALLS") ? int64_t(kStallLaunches) * 160 * 16 : 0);
+      ALLOC(p->dbg_timeline, n);
+      cudaMemset(p->dbg_timeline, 0, n * sizeof(long long));
+      if (getenv("SIRENB200_STALLS")) p->dbg_stall = p->dbg_timeline + kTimelineSlots;
     }
   }
 #undef ALLOC

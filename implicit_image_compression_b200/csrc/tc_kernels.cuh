@@ -105,23 +105,44 @@ __device__ __forceinline__ void load_xy(const CoordSrc& c, int64_t p, float& xh,
 struct PaceCtx {
   unsigned int* mine;         // tiles (x my_per_tile) this role has issued; null = no pacing
   const unsigned int* other;  // the other role's counter
-  int window;                 // tiles
+  int window;                 // this role may run `window` tiles AHEAD of the other's frontier; negative: it stays
+                              // |window| tiles BEHIND it (it then finds every tile in L2)
   int my_per_tile, other_per_tile;
+  int total;                  // tiles of the launch: a follower's target is clamped to the leader's last tile
 };
-__device__ __forceinline__ void pace_wait(const PaceCtx& pc, int tile) {
+// `seen`: the caller's copy of the other role's frontier (monotonic): the counter - one L2 line that every CTA of
+// the launch updates, ~1 k cycles per read - is only read again when the copy no longer covers the request.
+__device__ __forceinline__ void pace_wait(const PaceCtx& pc, int tile, int& seen) {
   if (!pc.mine) return;
+  int need = tile - pc.window;  // the other role's frontier must have reached this tile
+  if (need > pc.total) need = pc.total;
+  if (need <= seen) return;
   // the other role's frontier ends at the last tile once all its CTAs are done, so this can only wait on a role
   // that is still running; bounded anyway (~0.1 ms) so that a pacing mistake costs time, never a hang
   for (int spins = 0; spins < 1024; ++spins) {
     unsigned int v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(pc.other) : "memory");
-    if (unsigned(tile) <= v / unsigned(pc.other_per_tile) + unsigned(pc.window)) return;
+    seen = int(v / unsigned(pc.other_per_tile));
+    if (need <= seen) return;
     __nanosleep(64);
   }
 }
 __device__ __forceinline__ void pace_post(const PaceCtx& pc, unsigned int n = 1u) {
   if (pc.mine) atomicAdd(pc.mine, n);
 }
+
+// Debug stall accounting: cycles spent inside a wait, accumulated per single-thread role (no cost when off
+// beyond a predicated branch).
+#define SB_WAIT_TIMED(st, acc, stmt)            \
+  do {                                          \
+    if (st) {                                   \
+      const long long _t0 = clock64();          \
+      stmt;                                     \
+      (acc) += clock64() - _t0;                 \
+    } else {                                    \
+      stmt;                                     \
+    }                                           \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------
 // rowgemm
@@ -152,7 +173,7 @@ struct RowGemmCfg {
   static constexpr uint32_t OFF_CONST = OFF_EO + SEO * kChunkBytes;
   static constexpr uint32_t CONST_BYTES = (MODE == MODE_FWD) ? NDIM * NPARTS * 4 : 0;
   static constexpr uint32_t OFF_BAR = OFF_CONST + CONST_BYTES;
-  static constexpr int NUM_BARS = 2 * SA + 1 + 2 * SEO + 4 + 4;
+  static constexpr int NUM_BARS = 2 * SA + 1 + 3 * SEO + 4 + 4;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;  // + align slack
   static constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * NDIM);
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of shared memory");
@@ -181,6 +202,8 @@ struct RowGemmArgs {
   // 1: the resident B operand was written at least two kernels ago, so it may be fetched BEFORE waiting for
   // the predecessor kernel (programmatic dependent launch); 0: fetch it after the wait
   int b_early;
+  // SIRENB200_STALLS (debug): cycles each single-thread role of a CTA spent waiting, stall[cta * 16 + k]
+  long long* stall;
   long long* gen_tl;  // SIRENB200_TIMELINE: clock64 stamps of block 0 (debug)
 };
 
@@ -192,17 +215,33 @@ struct RowGemmArgs {
       args.gen_tl[((role) * 8 + (tile_i)) * 8 + (k)] = clock64();                   \
   } while (0)
 
+#ifndef SB_DX_EPW
+#define SB_DX_EPW 16
+#endif
+__host__ __device__ constexpr int rowgemm_epi_warps(int mode, bool gen, bool red) {
+  return (mode == MODE_DX && !gen && !red) ? SB_DX_EPW : 8;
+}
+__host__ __device__ constexpr int rowgemm_threads(int mode, bool gen, bool red) {
+  return gen ? 576 : (red ? 640 : 32 * (4 + rowgemm_epi_warps(mode, gen, red)));
+}
+
 template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
-// 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue-input producer, 3 = spare, 4..11 = epilogue
-// (two warps per TMEM lane quadrant; each takes 32 of the 64 columns of every output chunk);
+// warps: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue-input producer (MODE_DX), 3 = store warp,
+// 4..4+EPW-1 = epilogue (EPW / 4 warps per TMEM lane quadrant; each takes 64 / (EPW / 4) of the 64 columns of
+// every output chunk; EPW = 16 for the plain dX GEMM, 8 otherwise);
 // GEN: warps 0, 2, 3 and 12..16 = A-operand generators (network layer 0), two per 64-wide k-block; the
-// weight load moves to warp 1.
+// weight load moves to warp 1 and the store warp is warp 17;  RED: warps 12..19 = layer-0 gradient reducers.
 // `cta` / `ncta`: index of this CTA among the CTAs of the role and their number (== cta / ncta when the
 // whole grid runs this body).
 __device__ __forceinline__ void
 rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmE, const CUtensorMap& tmO,
              const RowGemmArgs& args, const uint32_t idesc, const int cta, const int ncta, const PaceCtx pace) {
   using C = RowGemmCfg<KDIM, NDIM, MODE, NPARTS>;
+  // epilogue warps: 8 (two per TMEM lane quadrant, 32 of a chunk's 64 columns each), or 16 for the plain dX GEMM
+  // (four per quadrant, 16 columns each): its cvt -> FFMA -> MUFU.SQRT -> FMUL -> F2FP chains need more than two
+  // warps per scheduler to hide their latency (stall accounting: the 8-warp epilogue was busy 5.1 k cycles per tile)
+  constexpr int EPW = rowgemm_epi_warps(MODE, GEN, RED);
+  constexpr int CPW = 64 / (EPW / 4);
   const int num_items = args.num_tiles * NPARTS;  // item = (tile, output part)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -216,12 +255,18 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   uint64_t* red_full = eo_empty + C::SEO;
   uint64_t* tm_full = red_full + 4;  // red_full: one per 64-column chunk index (RED)
   uint64_t* tm_empty = tm_full + 2;
+  uint64_t* o_ready = tm_empty + 2;  // [SEO] every epilogue warp has written (and fenced) its part of the chunk
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // The finished chunks are taken to HBM by a dedicated store warp (the spare warp 3; with GEN, where warp 3
+  // generates, the last warp): the epilogue warps hand a chunk over through o_ready and go straight on to the next
+  // one, so neither a CTA-wide barrier nor the TMA issue / wait_group latency sits on their path.
+  constexpr int STW = GEN ? 17 : 3;
 
   if (threadIdx.x == 0) {
+    for (int i = 0; i < C::SEO; ++i) mbar_init(&o_ready[i], EPW);
     for (int i = 0; i < C::SA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -234,7 +279,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     for (int i = 0; i < 4; ++i) mbar_init(&red_full[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tm_full[i], 1);
-      mbar_init(&tm_empty[i], 8);
+      mbar_init(&tm_empty[i], EPW);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -248,7 +293,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   }
   if (MODE == MODE_FWD && warp >= 4) {
     float* cst = reinterpret_cast<float*>(smem + C::OFF_CONST);
-    for (int i = threadIdx.x - 128; i < NDIM * NPARTS; i += 256) cst[i] = args.omega * args.bias[i];
+    for (int i = threadIdx.x - 128; i < NDIM * NPARTS; i += 32 * EPW) cst[i] = args.omega * args.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -271,7 +316,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   }
 
   // generator index (GEN only): warps 0, 2, 3, 12, 13, 14, 15, 16 -> 0..7
-  const int gi = !GEN ? -1 : (warp == 0 ? 0 : (warp == 2 || warp == 3) ? warp - 1 : (warp >= 12 ? warp - 9 : -1));
+  const int gi = !GEN ? -1 : (warp == 0 ? 0 : (warp == 2 || warp == 3) ? warp - 1 : ((warp >= 12 && warp <= 16) ? warp - 9 : -1));
   if (GEN && gi >= 0) {
     // ===================== A generator: layer 0 of the network -> A ring (+ stash) =====================
     // Two warps per 64-wide k-block (16 of the 32 four-row iterations each): the 8 column groups x 3
@@ -367,20 +412,28 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     // ===================== TMA producer: B once, then A k-blocks =====================
     if (lane == 0) {
       uint32_t ia = 0;
+      long long st_pace = 0, st_aempty = 0;
+      int pace_seen = 0;
+      const long long st_begin = args.stall ? clock64() : 0;
       for (int it = cta; !GEN && it < num_items; it += ncta) {
         const int t = it / NPARTS, part = it % NPARTS;
         const int row = args.a_row0 + t * kRowsPerTile;
-        pace_wait(pace, t);
+        SB_WAIT_TIMED(args.stall, st_pace, pace_wait(pace, t, pace_seen));
         pace_post(pace);
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
-          mbar_wait(&a_empty[s], ph ^ 1u);
+          SB_WAIT_TIMED(args.stall, st_aempty, mbar_wait(&a_empty[s], ph ^ 1u));
           mbar_expect_tx(&a_full[s], C::A_STAGE);
           tma_load_2d(smem + C::OFF_A + s * C::A_STAGE, &tmA, &a_full[s], kb * 64, row);
           if (C::STREAM_B)
             tma_load_2d(smem + C::OFF_A + s * C::A_STAGE + kChunkBytes, &tmB, &a_full[s], kb * 64,
                         part * NDIM);
         }
+      }
+      if (args.stall && !GEN) {
+        args.stall[cta * 16 + 0] = st_pace;
+        args.stall[cta * 16 + 1] = st_aempty;
+        args.stall[cta * 16 + 2] = clock64() - st_begin;
       }
     }
   } else if (warp == 1) {
@@ -389,16 +442,18 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       if (!C::STREAM_B) mbar_wait(b_full, 0);
       tc_fence_after();
       uint32_t ia = 0, it = 0;
+      long long st_tmempty = 0, st_afull = 0;
+      const long long st_begin = args.stall ? clock64() : 0;
       for (int item = cta; item < num_items; item += ncta, ++it) {
         const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
         SB_DBG_G(4, it, 0);
-        mbar_wait(&tm_empty[acc], aph ^ 1u);
+        SB_WAIT_TIMED(args.stall, st_tmempty, mbar_wait(&tm_empty[acc], aph ^ 1u));
         SB_DBG_G(4, it, 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * NDIM;
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
-          mbar_wait(&a_full[s], ph);
+          SB_WAIT_TIMED(args.stall, st_afull, mbar_wait(&a_full[s], ph));
           SB_DBG_G(4, it, 2 + (kb & 3));
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + C::OFF_A + s * C::A_STAGE);
@@ -415,22 +470,29 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
         umma_commit(&tm_full[acc]);
         SB_DBG_G(4, it, 6);
       }
+      if (args.stall) {
+        args.stall[cta * 16 + 3] = st_tmempty;
+        args.stall[cta * 16 + 4] = st_afull;
+        args.stall[cta * 16 + 5] = clock64() - st_begin;
+      }
     }
   } else if (warp == 2) {
     // ===================== epilogue-input producer (MODE_DX only) =====================
     if (MODE == MODE_DX && lane == 0) {
       uint32_t ic = 0;
+      long long st_eoempty = 0;
       for (int item = cta; item < num_items; item += ncta) {
         const int t = item / NPARTS, part = item % NPARTS;
         const int row = args.e_row0 + t * kRowsPerTile;
         for (int nb = 0; nb < C::NB; ++nb, ++ic) {
           const uint32_t s = ic % C::SEO, ph = (ic / C::SEO) & 1u;
-          mbar_wait(&eo_empty[s], ph ^ 1u);
+          SB_WAIT_TIMED(args.stall, st_eoempty, mbar_wait(&eo_empty[s], ph ^ 1u));
           mbar_expect_tx(&eo_full[s], kChunkBytes);
           tma_load_2d(smem + C::OFF_EO + s * kChunkBytes, &tmE, &eo_full[s], part * NDIM + nb * 64,
                       row);
         }
       }
+      if (args.stall) args.stall[cta * 16 + 6] = st_eoempty;
     }
   } else if (RED && warp >= 12) {
     // ===================== layer-0 gradient: reduce each finished dz[0] chunk over its 128 pixels =========
@@ -509,19 +571,21 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
         part_out[2 * WFULL + c0 + 1] = acc[pp][5];
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < 4 + EPW) {
     // ===================== epilogue: TMEM -> f() -> smem -> TMA store =====================
     const int q = warp & 3;
-    const int hb = (warp - 4) >> 2;  // which 32 of the 64 columns of a chunk this warp handles
+    const int hb = (warp - 4) >> 2;  // which CPW of the 64 columns of a chunk this warp handles
     const int r_in_tile = q * 32 + lane;
     const bool issuer = (threadIdx.x == 128);
     const float* cst = reinterpret_cast<const float*>(smem + C::OFF_CONST);
     uint32_t it = 0, ic = 0;
+    long long st_tmfull = 0, st_eo = 0;
+    const long long st_begin = args.stall ? clock64() : 0;
     for (int item = cta; item < num_items; item += ncta, ++it) {
       const int t = item / NPARTS, part = item % NPARTS;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       if (issuer) SB_DBG_G(5, it, 0);
-      mbar_wait(&tm_full[acc], aph);
+      SB_WAIT_TIMED(args.stall, st_tmfull, mbar_wait(&tm_full[acc], aph));
       if (issuer) SB_DBG_G(5, it, 1);
       tc_fence_after();
       const bool row_valid = (t * kRowsPerTile + r_in_tile) < args.valid_rows;
@@ -529,36 +593,42 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
         const uint32_t s = ic % C::SEO, ph = (ic / C::SEO) & 1u;
         const uint32_t buf = smem_u32(smem + C::OFF_EO + s * kChunkBytes);
         const uint32_t row_addr = buf + r_in_tile * 128;
-        if (MODE == MODE_DX)
-          mbar_wait(&eo_full[s], ph);
-        else
-          mbar_wait(&eo_empty[s], ph ^ 1u);
         {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + acc * NDIM + nb * 64 + hb * 32, v);
-          tmem_ld_wait();
-          uint32_t o[16];
+          uint32_t v[CPW];
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * NDIM + nb * 64 + hb * CPW;
+          if constexpr (CPW == 32) {
+            tmem_ld_32x32(taddr, v);
+          } else {
+            tmem_ld_32x16(taddr, v);
+          }
+          if (MODE == MODE_DX)
+            SB_WAIT_TIMED(args.stall, st_eo, mbar_wait(&eo_full[s], ph));
+          else
+            SB_WAIT_TIMED(args.stall, st_eo, mbar_wait(&eo_empty[s], ph ^ 1u));
+          uint32_t o[CPW / 2];
           if (MODE == MODE_FWD) {
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = part * NDIM + nb * 64 + hb * 32 + 2 * j;
+            for (int j = 0; j < CPW / 2; ++j) {
+              const int col = part * NDIM + nb * 64 + hb * CPW + 2 * j;
               const float t0 = fmaf(__uint_as_float(v[2 * j]), args.omega, cst[col]);
               const float t1 = fmaf(__uint_as_float(v[2 * j + 1]), args.omega, cst[col + 1]);
               o[j] = sine_signed_half2(t0, t1);
             }
           } else {
-            uint32_t e[16];
+            uint32_t e[CPW / 2];
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
+            for (int c4 = 0; c4 < CPW / 8; ++c4) {
+              const uint32_t chunk = uint32_t(hb * (CPW / 8) + c4) ^ uint32_t(r_in_tile & 7);
               const uint4 ld = ld_shared_v4(row_addr + (chunk << 4));
               e[4 * c4 + 0] = ld.x;
               e[4 * c4 + 1] = ld.y;
               e[4 * c4 + 2] = ld.z;
               e[4 * c4 + 3] = ld.w;
             }
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CPW / 2; ++j) {
               float g0 = __uint_as_float(v[2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
               float g1 = __uint_as_float(v[2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
               if (!row_valid) g0 = g1 = 0.0f;
@@ -566,32 +636,51 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
             }
           }
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint32_t chunk = uint32_t(hb * 4 + c4) ^ uint32_t(r_in_tile & 7);
+          for (int c4 = 0; c4 < CPW / 8; ++c4) {
+            const uint32_t chunk = uint32_t(hb * (CPW / 8) + c4) ^ uint32_t(r_in_tile & 7);
             st_shared_v4(row_addr + (chunk << 4), o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2],
                          o[4 * c4 + 3]);
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 256);
-        if (issuer) {
-          tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, part * NDIM + nb * 64,
-                       args.o_row0 + t * kRowsPerTile);
-          tma_store_commit();
-          if (RED) mbar_arrive(&red_full[nb]);
-          if (ic > 0) {
-            // all but the newest store have finished reading shared memory
-            tma_store_wait_read<1>();
-            mbar_arrive(&eo_empty[(ic - 1) % C::SEO]);
-          }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_ready[s]);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tm_empty[acc]);
       if (issuer) SB_DBG_G(5, it, 2);
     }
-    if (issuer) tma_store_wait_all<0>();
+    if (issuer && args.stall) {
+      args.stall[cta * 16 + 7] = st_tmfull;
+      args.stall[cta * 16 + 8] = st_eo;
+      args.stall[cta * 16 + 11] = clock64() - st_begin;
+    }
+  } else if (warp == STW) {
+    // ===================== store warp: finished chunks -> HBM, staging buffers back to their producer ==========
+    if (lane == 0) {
+      uint32_t ic = 0;
+      long long st_ready = 0, st_rd = 0;
+      for (int item = cta; item < num_items; item += ncta) {
+        const int t = item / NPARTS, part = item % NPARTS;
+        for (int nb = 0; nb < C::NB; ++nb, ++ic) {
+          const uint32_t s = ic % C::SEO, ph = (ic / C::SEO) & 1u;
+          SB_WAIT_TIMED(args.stall, st_ready, mbar_wait(&o_ready[s], ph));
+          tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, part * NDIM + nb * 64,
+                       args.o_row0 + t * kRowsPerTile);
+          tma_store_commit();
+          if (RED) mbar_arrive(&red_full[nb]);
+          // this warp has nothing else to do: wait for the store to have read the buffer and hand it straight back
+          SB_WAIT_TIMED(args.stall, st_rd, tma_store_wait_read<0>());
+          mbar_arrive(&eo_empty[s]);
+        }
+      }
+      if (args.stall) {
+        args.stall[cta * 16 + 9] = st_ready;
+        args.stall[cta * 16 + 10] = st_rd;
+      }
+      tma_store_wait_all<0>();
+    }
   }
 
   tc_fence_before();
@@ -603,7 +692,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
 }
 
 template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
-__global__ void __launch_bounds__(GEN ? 544 : (RED ? 640 : 384), 1)
+__global__ void __launch_bounds__(rowgemm_threads(MODE, GEN, RED), 1)
 rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
                const RowGemmArgs args, const uint32_t idesc) {
@@ -618,10 +707,15 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int NY>
 struct ColGemmCfg {
   static_assert(NY % 64 == 0 && NY >= 64 && NY <= 256, "operand width");
+  static constexpr int PXS = 128;                       // pixels per pipeline stage (one tile)
   static constexpr int XC = 2;        // X chunks per stage (M = 128 output rows)
   static constexpr int YC = NY / 64;  // Y chunks per stage
-  static constexpr uint32_t STAGE_BYTES = (XC + YC) * kChunkBytes;
-  static constexpr int STAGES = (2 * STAGE_BYTES + 8192 <= 232448) ? ((3 * STAGE_BYTES + 8192 <= 232448) ? 3 : 2) : 1;
+  static constexpr int SUB = 128 / PXS;                 // stages per 128-pixel tile
+  static constexpr uint32_t CHUNK = PXS * 128;          // one {64 x PXS-row} fp16 box
+  static constexpr uint32_t STAGE_BYTES = (XC + YC) * CHUNK;
+  static constexpr int STAGES = (2 * STAGE_BYTES + 8192 <= 232448)
+                                    ? ((4 * STAGE_BYTES + 8192 <= 232448) ? 4 : ((3 * STAGE_BYTES + 8192 <= 232448) ? 3 : 2))
+                                    : 1;
   static constexpr uint32_t OFF_ONES = STAGES * STAGE_BYTES;
   static constexpr uint32_t ONES_BYTES = 1024;
   static constexpr uint32_t OFF_BAR = OFF_ONES + ONES_BYTES;
@@ -652,6 +746,7 @@ struct ColGemmJobs {
   int prob_total;       // problems per split slab in the partial buffers
   int interleave;       // 1: split s visits tiles s, s+splits, ... (sweeps the image front to back,
                         //    in step with a concurrently running rowgemm); 0: contiguous tile ranges
+  long long* stall;     // SIRENB200_STALLS (debug): stall[job * 16 + k]
 };
 
 template <int NY>
@@ -659,6 +754,7 @@ __device__ __forceinline__ void
 colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& jobs, const uint32_t idesc_main,
              const uint32_t idesc_ones, const int job, const PaceCtx pace) {
   using C = ColGemmCfg<NY>;
+  constexpr int PXS = C::PXS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -717,36 +813,47 @@ colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < ntiles; ++i) {
-        const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
-        const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile;
-        pace_wait(pace, tile_begin + i * tile_step);
-        pace_post(pace);
-        mbar_wait(&empty[s], ph ^ 1u);
+      long long st_pace = 0, st_empty = 0;
+      int pace_seen = 0;
+      const long long st_begin = jobs.stall ? clock64() : 0;
+      for (int ii = 0; ii < ntiles * C::SUB; ++ii) {
+        const int i = ii / C::SUB, sub = ii % C::SUB;
+        const uint32_t s = ii % C::STAGES, ph = (ii / C::STAGES) & 1u;
+        const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile + sub * PXS;
+        if (sub == 0) {
+          SB_WAIT_TIMED(jobs.stall, st_pace, pace_wait(pace, tile_begin + i * tile_step, pace_seen));
+          pace_post(pace);
+        }
+        SB_WAIT_TIMED(jobs.stall, st_empty, mbar_wait(&empty[s], ph ^ 1u));
         mbar_expect_tx(&full[s], C::STAGE_BYTES);
         uint8_t* st = smem + s * C::STAGE_BYTES;
-        for (int c = 0; c < C::XC; ++c)
-          tma_load_2d(st + c * kChunkBytes, &tmX, &full[s], mb * 128 + c * 64,
-                      jobs.x_row0[prob] + prow);
-        for (int c = 0; c < C::YC; ++c)
-          tma_load_2d(st + (C::XC + c) * kChunkBytes, &tmY, &full[s], part * NY + c * 64,
-                      jobs.y_row0[prob] + prow);
+        // one box per operand: {64 columns, PXS pixel rows, XC / YC chunks} (make_tmap_16bit_chunks) - a single
+        // thread pays ~100 cycles per TMA instruction, six 2-D boxes per stage cost half the MMA time of a stage
+        tma_load_3d(st, &tmX, &full[s], 0, jobs.x_row0[prob] + prow, mb * C::XC);
+        tma_load_3d(st + C::XC * C::CHUNK, &tmY, &full[s], 0, jobs.y_row0[prob] + prow, part * C::YC);
+      }
+      if (jobs.stall) {
+        jobs.stall[job * 16 + 0] = st_pace;
+        jobs.stall[job * 16 + 1] = st_empty;
+        jobs.stall[job * 16 + 2] = clock64() - st_begin;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t ones_addr = smem_u32(smem + C::OFF_ONES);
       const uint64_t d_ones = umma_smem_desc(ones_addr, 128, 256, 0);
-      for (int i = 0; i < ntiles; ++i) {
+      long long st_full = 0;
+      const long long st_begin = jobs.stall ? clock64() : 0;
+      for (int i = 0; i < ntiles * C::SUB; ++i) {
         const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
-        mbar_wait(&full[s], ph);
+        SB_WAIT_TIMED(jobs.stall, st_full, mbar_wait(&full[s], ph));
         tc_fence_after();
         const uint32_t x_addr = smem_u32(smem + s * C::STAGE_BYTES);
-        const uint32_t y_addr = x_addr + C::XC * kChunkBytes;
+        const uint32_t y_addr = x_addr + C::XC * C::CHUNK;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
-          const uint64_t dx = umma_smem_desc(x_addr + k * 2048, kChunkBytes, 1024, 2);
-          const uint64_t dy = umma_smem_desc(y_addr + k * 2048, kChunkBytes, 1024, 2);
+        for (int k = 0; k < PXS / 16; ++k) {  // 16 pixels per MMA
+          const uint64_t dx = umma_smem_desc(x_addr + k * 2048, C::CHUNK, 1024, 2);
+          const uint64_t dy = umma_smem_desc(y_addr + k * 2048, C::CHUNK, 1024, 2);
           const uint32_t accum = (i | k) != 0 ? 1u : 0u;
           umma_f16(tmem_base, dx, dy, idesc_main, accum);
           umma_f16(tmem_base + NY, dx, d_ones, idesc_ones, accum);
@@ -754,6 +861,10 @@ colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& 
         umma_commit(&empty[s]);
       }
       umma_commit(done);
+      if (jobs.stall) {
+        jobs.stall[job * 16 + 4] = st_full;
+        jobs.stall[job * 16 + 5] = clock64() - st_begin;
+      }
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
@@ -804,6 +915,171 @@ colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& 
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// The same reduction on CTA PAIRS (hidden 256): the two CTAs that used to compute the two 128-row blocks of dW from
+// the same pixel tiles now issue ONE cta_group::2 MMA (M = 256 = all dz features, N = 256).  Each CTA loads only
+// its 128 dz features AND only its half of the activation columns (64 KiB per 128-pixel stage instead of 96), reads
+// a third less operand data out of shared memory per MMA, and the smaller stage buys a third ring stage - the
+// one-CTA version waited for its loads a third of the time with two.  job = (pixel split, CTA rank).
+// ------------------------------------------------------------------------------------------
+struct ColGemm2Cfg {
+  static constexpr int XC = 2, YC = 2;
+  static constexpr uint32_t STAGE_BYTES = (XC + YC) * kChunkBytes;  // per CTA
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t OFF_ONES = STAGES * STAGE_BYTES;
+  static constexpr uint32_t OFF_BAR = OFF_ONES + 1024;
+  static constexpr int NUM_BARS = 2 * STAGES + 1;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;  // 256 (dW rows of this CTA) + 16 (db), power of two
+};
+
+__device__ __forceinline__ void
+colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& jobs, const int job,
+              const PaceCtx pace) {
+  using C = ColGemm2Cfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* full = bars;               // used in the leader: bytes of BOTH CTAs' loads
+  uint64_t* empty = bars + C::STAGES;  // each CTA's own; the leader's commits arrive on both
+  uint64_t* done = empty + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // == job & 1: which 128 dz features / which half of the columns
+  const bool leader = rank == 0;
+  const int split = job >> 1;
+  const int tile_begin = split, tile_step = jobs.splits;
+  const int ntiles = split < jobs.tiles_total ? (jobs.tiles_total - split + jobs.splits - 1) / jobs.splits : 0;
+  const int prob = 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  if (warp >= 4) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(smem + C::OFF_ONES);
+    for (int i = threadIdx.x - 128; i < 256; i += int(blockDim.x) - 128) ones[i] = 0x3C003C00u;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anything of ours can arrive on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      long long st_pace = 0, st_empty = 0;
+      int pace_seen = 0;
+      const long long st_begin = jobs.stall ? clock64() : 0;
+      for (int i = 0; i < ntiles; ++i) {
+        const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
+        const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile;
+        SB_WAIT_TIMED(jobs.stall, st_pace, pace_wait(pace, tile_begin + i * tile_step, pace_seen));
+        pace_post(pace);
+        SB_WAIT_TIMED(jobs.stall, st_empty, mbar_wait(&empty[s], ph ^ 1u));
+        if (leader) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+        uint8_t* st = smem + s * C::STAGE_BYTES;
+        tma_load_3d_2sm(st, &tmX, &full[s], 0, jobs.x_row0[prob] + prow, int(rank) * C::XC);
+        tma_load_3d_2sm(st + C::XC * kChunkBytes, &tmY, &full[s], 0, jobs.y_row0[prob] + prow, int(rank) * C::YC);
+      }
+      if (jobs.stall) {
+        jobs.stall[job * 16 + 0] = st_pace;
+        jobs.stall[job * 16 + 1] = st_empty;
+        jobs.stall[job * 16 + 2] = clock64() - st_begin;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc_main = umma_idesc(256, 256, 0, 0, 1, 1);
+      const uint32_t idesc_ones = umma_idesc(256, 16, 0, 0, 1, 1);
+      const uint64_t d_ones = umma_smem_desc(smem_u32(smem + C::OFF_ONES), 128, 256, 0);
+      long long st_full = 0;
+      const long long st_begin = jobs.stall ? clock64() : 0;
+      for (int i = 0; i < ntiles; ++i) {
+        const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
+        SB_WAIT_TIMED(jobs.stall, st_full, mbar_wait(&full[s], ph));
+        tc_fence_after();
+        const uint32_t x_addr = smem_u32(smem + s * C::STAGE_BYTES);
+        const uint32_t y_addr = x_addr + C::XC * kChunkBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
+          const uint64_t dx = umma_smem_desc(x_addr + k * 2048, kChunkBytes, 1024, 2);
+          const uint64_t dy = umma_smem_desc(y_addr + k * 2048, kChunkBytes, 1024, 2);
+          const uint32_t accum = (i | k) != 0 ? 1u : 0u;
+          umma_f16_2sm(tmem_base, dx, dy, idesc_main, accum);
+          umma_f16_2sm(tmem_base + 256, dx, d_ones, idesc_ones, accum);
+        }
+        umma_commit_2sm(&empty[s]);
+      }
+      umma_commit_2sm(done);
+      if (jobs.stall) {
+        jobs.stall[job * 16 + 4] = st_full;
+        jobs.stall[job * 16 + 5] = clock64() - st_begin;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    const int q = warp & 3;
+    const int m = int(rank) * 128 + q * 32 + lane;  // dW row (dz feature) of this thread
+    const size_t slab = size_t(split) * jobs.prob_total + jobs.prob0 + prob;
+    float* dw = jobs.dw_partial + (slab * jobs.nx + m) * size_t(jobs.ny_total);
+    float* dbp = jobs.db_partial + slab * jobs.nx + m;
+    if (ntiles > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      for (int cb = 0; cb < 256 / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + cb * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          float4* dst = reinterpret_cast<float4*>(dw + cb * 32) + j;
+          if (jobs.accumulate) {
+            const float4 old = *dst;
+            o.x += old.x;
+            o.y += old.y;
+            o.z += old.z;
+            o.w += old.w;
+          }
+          *dst = o;
+        }
+      }
+      uint32_t b8[8];
+      tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + 256, b8);
+      tmem_ld_wait();
+      *dbp = __uint_as_float(b8[0]) + (jobs.accumulate ? *dbp : 0.f);
+    } else if (!jobs.accumulate) {
+      for (int j = 0; j < 256 / 4; ++j) reinterpret_cast<uint4*>(dw)[j] = make_uint4(0, 0, 0, 0);
+      *dbp = 0.0f;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs are done with the pair's tensor memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+  }
+}
+
 template <int NY>
 __global__ void __launch_bounds__(256, 1)
 colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
@@ -818,21 +1094,30 @@ colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // reduction's 2 x 201 MB per layer never reach HBM (autograd of nn.Linear: grad_input and grad_weight from ONE
 // pass over grad_output, siren.py:62).  pace_counters: two zeroed uint32 (dX, dW) owned by this launch.
 // ------------------------------------------------------------------------------------------
-template <int W, bool RED>
-__global__ void __launch_bounds__(RED ? 640 : 384, 1)
+// PAIR: launched as 2-CTA clusters; the reduction role runs on CTA pairs (colgemm2_body, hidden 256); the dX role's
+// CTAs ignore their cluster.
+template <int W, bool RED, bool PAIR = false>
+__global__ void __launch_bounds__(rowgemm_threads(MODE_DX, false, RED), 1)
 bwd_merged_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmWt,
-                  const __grid_constant__ CUtensorMap tmAct, const RowGemmArgs rargs, const uint32_t idesc_row,
+                  const __grid_constant__ CUtensorMap tmAct, const __grid_constant__ CUtensorMap tmDzR,
+                  const __grid_constant__ CUtensorMap tmActR, const RowGemmArgs rargs, const uint32_t idesc_row,
                   const ColGemmJobs jobs, const uint32_t idesc_main, const uint32_t idesc_ones, const int dx_ctas,
-                  unsigned int* pace_counters, const int window) {
+                  unsigned int* pace_counters, const int window, const int window_dx) {
   constexpr int NT = W < 256 ? W : 256;
   constexpr int NPARTS = W / NT;
   if (int(blockIdx.x) < dx_ctas) {
-    const PaceCtx pc{pace_counters, pace_counters + 1, window, NPARTS, jobs.mblocks * jobs.nparts};
+    const PaceCtx pc{pace_counters, pace_counters + 1, window_dx, NPARTS, jobs.mblocks * jobs.nparts, rargs.num_tiles};
     rowgemm_body<W, NT, MODE_DX, false, NPARTS, false, RED>(tmDz, tmWt, tmAct, tmDz, rargs, idesc_row,
                                                             int(blockIdx.x), dx_ctas, pc);
   } else {
-    const PaceCtx pc{pace_counters + 1, pace_counters, window, jobs.mblocks * jobs.nparts, NPARTS};
-    colgemm_body<NT>(tmDz, tmAct, jobs, idesc_main, idesc_ones, int(blockIdx.x) - dx_ctas, pc);
+    const PaceCtx pc{pace_counters + 1, pace_counters, window, jobs.mblocks * jobs.nparts, NPARTS, jobs.tiles_total};
+    // (tmDzR / tmActR: the reduction role's views of dz / act: one box per operand and stage)
+    if constexpr (PAIR) {
+      static_assert(!PAIR || W == 256, "CTA-pair reduction: hidden 256");
+      colgemm2_body(tmDzR, tmActR, jobs, int(blockIdx.x) - dx_ctas, pc);
+    } else {
+      colgemm_body<NT>(tmDzR, tmActR, jobs, idesc_main, idesc_ones, int(blockIdx.x) - dx_ctas, pc);
+    }
   }
 }
 
@@ -1480,7 +1765,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
         }
         if (did) {
           idle = 0;
-        } else if (++idle > (1u << 27)) {
+        } else if (++idle > (1u << 24)) {
           printf("sirenb200: tail kernel MMA loop stalled block %d (gemm tile %u kb %u, chain tile %u state %u)\n",
                  blockIdx.x, ig, kbg, ic, cst);
           __trap();

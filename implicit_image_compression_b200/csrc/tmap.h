@@ -45,4 +45,22 @@ inline int make_tmap_16bit(CUtensorMap* out, const void* base, uint64_t rows, ui
   return r == CUDA_SUCCESS ? 0 : -int(r);
 }
 
+// The same row-major [rows, cols] tensor seen as [cols / 64 chunks][rows][64 columns]: ONE box {64, box_rows, chunks}
+// lands in shared memory as `chunks` consecutive {64 x box_rows} tiles, each in the 128B-swizzled layout the 2-D map
+// above produces - a whole multi-chunk operand with a single TMA instruction.  Coordinates: (0, row, first chunk).
+inline int make_tmap_16bit_chunks(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                                  uint32_t box_rows, uint32_t box_chunks) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[3] = {64, rows, cols / 64};
+  cuuint64_t strides[2] = {cols * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, box_chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  memset(out, 0, sizeof(*out));
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -int(r);
+}
+
 }  // namespace sb

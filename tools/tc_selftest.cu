@@ -93,17 +93,17 @@ static int test_rowgemm(int rows, bool timing) {
         using C = RowGemmCfg<W, W, MODE_FWD>;
         auto kfn = rowgemm_kernel<W, W, MODE_FWD, false>;
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        kfn<<<grid, 384, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
+        kfn<<<grid, rowgemm_threads(MODE_FWD, false, false), C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
       } else if (mode == 1) {
         using C = RowGemmCfg<W, W, MODE_DX>;
         auto kfn = rowgemm_kernel<W, W, MODE_DX, false>;
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        kfn<<<grid, 384, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
+        kfn<<<grid, rowgemm_threads(MODE_DX, false, false), C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
       } else {
         using C = RowGemmCfg<W, W, MODE_DX>;
         auto kfn = rowgemm_kernel<W, W, MODE_DX, true>;
         CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        kfn<<<grid, 384, C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
+        kfn<<<grid, rowgemm_threads(MODE_DX, false, false), C::SMEM_BYTES>>>(tmA, tmB, tmE, tmO, args, idesc);
       }
     };
     launch();
@@ -217,8 +217,12 @@ static int test_colgemm(int rows, bool timing) {
     CK(cudaMalloc(&jobs.dw_partial, size_t(jobs.splits) * nprob * NX * NY * 4));
     CK(cudaMalloc(&jobs.db_partial, size_t(jobs.splits) * nprob * NX * 4));
     CUtensorMap tmX, tmY;
-    if (make_tmap_16bit(&tmX, dX, uint64_t(nprob) * rows_pad, NX, 128, xfmt == 1) ||
-        make_tmap_16bit(&tmY, dY, uint64_t(nprob) * rows_pad, NY, 128, false)) {
+    if (xfmt == 1) {
+      printf("colgemm: bf16 X operands are no longer built (fp16 only)\n");
+      return 1;
+    }
+    if (make_tmap_16bit_chunks(&tmX, dX, uint64_t(nprob) * rows_pad, NX, 128, 2) ||
+        make_tmap_16bit_chunks(&tmY, dY, uint64_t(nprob) * rows_pad, NY, 128, NY / 64)) {
       printf("tensor map encode failed\n");
       return 1;
     }
