@@ -69,6 +69,19 @@ __device__ __forceinline__ float cos_from_signed_half(uint32_t h16) {
   return __uint_as_float(__float_as_uint(c) ^ ((h16 & 1u) << 31));
 }
 
+// dZ pair of the layer below: {acc0 * cos0, acc1 * cos1} as packed 16-bit floats, cos = +-sqrt(1 - a^2) rebuilt from
+// the signed-half pair `e`.  The sign goes on AFTER rounding, as one XOR on the packed pair (rounding is symmetric,
+// so the bits equal pack(acc * cos_from_signed_half(.))): one instruction per element less than two float XORs.
+template <bool OUT_BF16>
+__device__ __forceinline__ uint32_t dz_pair_from_signed_half(float acc0, float acc1, uint32_t e) {
+  const float a0 = __half2float(__ushort_as_half(static_cast<unsigned short>(e & 0xFFFFu)));
+  const float a1 = __half2float(__ushort_as_half(static_cast<unsigned short>(e >> 16)));
+  const float c0 = fast_sqrt(__saturatef(fmaf(-a0, a0, 1.0f)));
+  const float c1 = fast_sqrt(__saturatef(fmaf(-a1, a1, 1.0f)));
+  const uint32_t mag = OUT_BF16 ? pack_bf16x2(acc0 * c0, acc1 * c1) : pack_f16x2(acc0 * c0, acc1 * c1);
+  return mag ^ ((e << 15) & 0x80008000u);
+}
+
 // Where the input coordinates of pixel p (local index inside this handle's rows) come from.
 struct CoordSrc {
   const float* lin_h;   // [H] or null
@@ -219,18 +232,18 @@ struct RowGemmArgs {
 #define SB_DX_EPW 16
 #endif
 __host__ __device__ constexpr int rowgemm_epi_warps(int mode, bool gen, bool red) {
-  return (mode == MODE_DX && !gen && !red) ? SB_DX_EPW : 8;
+  return (mode == MODE_DX && !gen) ? SB_DX_EPW : 8;
 }
 __host__ __device__ constexpr int rowgemm_threads(int mode, bool gen, bool red) {
-  return gen ? 576 : (red ? 640 : 32 * (4 + rowgemm_epi_warps(mode, gen, red)));
+  return gen ? 576 : 32 * (4 + rowgemm_epi_warps(mode, gen, red) + (red ? 8 : 0));
 }
 
 template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
 // warps: 0 = TMA producer, 1 = MMA issuer, 2 = epilogue-input producer (MODE_DX), 3 = store warp,
 // 4..4+EPW-1 = epilogue (EPW / 4 warps per TMEM lane quadrant; each takes 64 / (EPW / 4) of the 64 columns of
-// every output chunk; EPW = 16 for the plain dX GEMM, 8 otherwise);
+// every output chunk; EPW = 16 for the dX GEMMs, 8 otherwise);
 // GEN: warps 0, 2, 3 and 12..16 = A-operand generators (network layer 0), two per 64-wide k-block; the
-// weight load moves to warp 1 and the store warp is warp 17;  RED: warps 12..19 = layer-0 gradient reducers.
+// weight load moves to warp 1 and the store warp is warp 17;  RED: 8 more warps = layer-0 gradient reducers.
 // `cta` / `ncta`: index of this CTA among the CTAs of the role and their number (== cta / ncta when the
 // whole grid runs this body).
 __device__ __forceinline__ void
@@ -494,13 +507,13 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       }
       if (args.stall) args.stall[cta * 16 + 6] = st_eoempty;
     }
-  } else if (RED && warp >= 12) {
+  } else if (RED && warp >= 4 + EPW) {
     // ===================== layer-0 gradient: reduce each finished dz[0] chunk over its 128 pixels =========
     static_assert(!RED || (MODE == MODE_DX && NPARTS <= 2 && C::NB <= 4), "RED: dX of the first hidden layer");
     // two warps per 64-column chunk (64 pixel rows each); lane -> columns part*NDIM + nb*64 + 2*lane, +1.
     // With two output parts (hidden 512) every tile is visited twice, once per part; each part has its own
     // accumulators.
-    const int nb = (warp - 12) >> 1, half = (warp - 12) & 1;
+    const int nb = (warp - 4 - EPW) >> 1, half = (warp - 4 - EPW) & 1;
     if (nb < C::NB) {
       const CoordSrc& cs = args.gen_coord;
       float acc[NPARTS][6];
@@ -629,10 +642,9 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < CPW / 2; ++j) {
-              float g0 = __uint_as_float(v[2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
-              float g1 = __uint_as_float(v[2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
-              if (!row_valid) g0 = g1 = 0.0f;
-              o[j] = OUT_BF16 ? pack_bf16x2(g0, g1) : pack_f16x2(g0, g1);
+              const uint32_t g = dz_pair_from_signed_half<OUT_BF16>(__uint_as_float(v[2 * j]),
+                                                                    __uint_as_float(v[2 * j + 1]), e[j]);
+              o[j] = row_valid ? g : 0u;
             }
           }
 #pragma unroll
@@ -666,12 +678,17 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
         for (int nb = 0; nb < C::NB; ++nb, ++ic) {
           const uint32_t s = ic % C::SEO, ph = (ic / C::SEO) & 1u;
           SB_WAIT_TIMED(args.stall, st_ready, mbar_wait(&o_ready[s], ph));
-          tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, part * NDIM + nb * 64,
-                       args.o_row0 + t * kRowsPerTile);
-          tma_store_commit();
-          if (RED) mbar_arrive(&red_full[nb]);
-          // this warp has nothing else to do: wait for the store to have read the buffer and hand it straight back
-          SB_WAIT_TIMED(args.stall, st_rd, tma_store_wait_read<0>());
+          if (RED) {
+            // dz[0] has no reader but the reducer warps of this CTA (nothing lies below layer 0): it never goes
+            // to HBM - 2 bytes per pixel and feature that the step used to write for nobody
+            mbar_arrive(&red_full[nb]);
+          } else {
+            tma_store_2d(&tmO, smem + C::OFF_EO + s * kChunkBytes, part * NDIM + nb * 64,
+                         args.o_row0 + t * kRowsPerTile);
+            tma_store_commit();
+            // this warp has nothing else to do: wait for the store to have read the buffer, hand it straight back
+            SB_WAIT_TIMED(args.stall, st_rd, tma_store_wait_read<0>());
+          }
           mbar_arrive(&eo_empty[s]);
         }
       }
@@ -1418,10 +1435,9 @@ last_layer_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_con
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float g0 = __uint_as_float(v[2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
-          float g1 = __uint_as_float(v[2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
-          if (!row_valid) g0 = g1 = 0.0f;
-          o[j] = pack_f16x2(g0, g1);
+          const uint32_t g = dz_pair_from_signed_half<false>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]),
+                                                             e[j]);
+          o[j] = row_valid ? g : 0u;
         }
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
@@ -1544,19 +1560,23 @@ struct TailCfg {
   static_assert(W == 128 || W == 256, "tail kernel: hidden 128 or 256");
   static constexpr int NCH = W / 64;   // 64-wide chunks of the tile == k-blocks of the GEMM
   static constexpr int CPH = NCH / 2;  // chunks per half of T (dA and the dz stores go half by half)
-  static constexpr int S = 2;          // ring stages
+  // Two rings: the activation k-blocks come from HBM (one tile ahead = NCH stages hides that latency), the weight
+  // k-blocks from L2 (two stages are enough).  With a shared two-stage ring of {A, W} pairs the GEMM of a tile took
+  // ~6 k cycles - one HBM latency per two k-blocks - and did not fit behind the previous tile's epilogues.
+  static constexpr int SA = NCH;       // activation ring stages (16 KiB each)
+  static constexpr int SW = 2;         // weight ring stages (W * 128 bytes each)
   static constexpr uint32_t B_KB_BYTES = W * 128;
-  static constexpr uint32_t STAGE_BYTES = kChunkBytes + B_KB_BYTES;
   static constexpr uint32_t OFF_T = 0;
-  static constexpr uint32_t OFF_ST = NCH * kChunkBytes;
-  static constexpr uint32_t OFF_WL = OFF_ST + S * STAGE_BYTES;
+  static constexpr uint32_t OFF_A = NCH * kChunkBytes;
+  static constexpr uint32_t OFF_W = OFF_A + SA * kChunkBytes;
+  static constexpr uint32_t OFF_WL = OFF_W + SW * B_KB_BYTES;
   static constexpr uint32_t OFF_WLT = OFF_WL + NCH * 2048;
   static constexpr uint32_t WLT_BYTES = W * 32;
   static constexpr uint32_t OFF_G = OFF_WLT + WLT_BYTES;
   static constexpr uint32_t OFF_CONST = OFF_G + 4096;  // omega * bias [W] fp32
   static constexpr uint32_t OFF_RED = OFF_CONST + W * 4;
   static constexpr uint32_t OFF_BAR = OFF_RED + 16 * 8 * 4;
-  static constexpr int NUM_BARS = 2 * S + 8 + 4 + 4;
+  static constexpr int NUM_BARS = 2 * SA + 2 * SW + 8 + 4 + 4;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;
   static constexpr uint32_t TM_ACC = 0, TM_DA = W, TM_Y = W + W / 2, TM_DW = W + W / 2 + 16;
   static constexpr uint32_t TMEM_COLS = 512;
@@ -1587,9 +1607,11 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-  uint64_t* st_full = bars;              // [S]
-  uint64_t* st_empty = st_full + C::S;   // [S]
-  uint64_t* w_full = st_empty + C::S;
+  uint64_t* a_full = bars;                 // [SA]
+  uint64_t* a_empty = a_full + C::SA;      // [SA]
+  uint64_t* wk_full = a_empty + C::SA;     // [SW]
+  uint64_t* wk_empty = wk_full + C::SW;    // [SW]
+  uint64_t* w_full = wk_empty + C::SW;
   uint64_t* acc_full = w_full + 1;   // GEMM of the tile retired
   uint64_t* acc_free = acc_full + 1; // epilogue 1 has drained the accumulator (8 warps)
   uint64_t* t_ready = acc_free + 1;  // [4, two used] half of T written and fenced (16 warps each)
@@ -1606,9 +1628,13 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::S; ++i) {
-      mbar_init(&st_full[i], 1);
-      mbar_init(&st_empty[i], 1);
+    for (int i = 0; i < C::SA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < C::SW; ++i) {
+      mbar_init(&wk_full[i], 1);
+      mbar_init(&wk_empty[i], 1);
     }
     mbar_init(w_full, 1);
     mbar_init(acc_full, 1);
@@ -1652,17 +1678,29 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
   pdl_launch_dependents();
 
   if (warp == 0) {
-    // ===================== producer: A and W k-blocks =====================
+    // ===================== producer: activation k-blocks (HBM) =====================
     if (lane == 0) {
       uint32_t ia = 0;
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
         for (int kb = 0; kb < C::NCH; ++kb, ++ia) {
-          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
-          mbar_wait(&st_empty[s], ph ^ 1u);
-          mbar_expect_tx(&st_full[s], C::STAGE_BYTES);
-          uint8_t* stage = smem + C::OFF_ST + s * C::STAGE_BYTES;
-          tma_load_2d(stage, &tmAct, &st_full[s], kb * 64, args.a_row0 + t * kRowsPerTile);
-          tma_load_2d(stage + kChunkBytes, &tmW, &st_full[s], kb * 64, 0);
+          const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
+          mbar_wait(&a_empty[s], ph ^ 1u);
+          mbar_expect_tx(&a_full[s], kChunkBytes);
+          tma_load_2d(smem + C::OFF_A + s * kChunkBytes, &tmAct, &a_full[s], kb * 64,
+                      args.a_row0 + t * kRowsPerTile);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== producer: weight k-blocks (L2), the same four for every tile =====================
+    if (lane == 0) {
+      uint32_t iw = 0;
+      for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < C::NCH; ++kb, ++iw) {
+          const uint32_t s = iw % C::SW, ph = (iw / C::SW) & 1u;
+          mbar_wait(&wk_empty[s], ph ^ 1u);
+          mbar_expect_tx(&wk_full[s], C::B_KB_BYTES);
+          tma_load_2d(smem + C::OFF_W + s * C::B_KB_BYTES, &tmW, &wk_full[s], kb * 64, 0);
         }
       }
     }
@@ -1740,18 +1778,21 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
         }
         if (!did && ig < uint32_t(my_tiles)) {
           // next GEMM k-block: the accumulator must have been drained by epilogue 1 of the previous tile
-          const uint32_t s = ia % C::S, ph = (ia / C::S) & 1u;
-          if ((kbg > 0 || mbar_try_wait(acc_free, (ig & 1u) ^ 1u)) && mbar_try_wait(&st_full[s], ph)) {
+          const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
+          const uint32_t sw = ia % C::SW, phw = (ia / C::SW) & 1u;
+          if ((kbg > 0 || mbar_try_wait(acc_free, (ig & 1u) ^ 1u)) && mbar_try_wait(&a_full[s], ph) &&
+              mbar_try_wait(&wk_full[sw], phw)) {
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + C::OFF_ST + s * C::STAGE_BYTES);
-            const uint32_t b_addr = a_addr + kChunkBytes;
+            const uint32_t a_addr = smem_u32(smem + C::OFF_A + s * kChunkBytes);
+            const uint32_t b_addr = smem_u32(smem + C::OFF_W + sw * C::B_KB_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = umma_smem_desc(a_addr + k * 32, 0, 1024, 2);
               const uint64_t db = umma_smem_desc(b_addr + k * 32, 0, 1024, 2);
               umma_f16(tmem_base + C::TM_ACC, da, db, id_gemm, (kbg | uint32_t(k)) != 0 ? 1u : 0u);
             }
-            umma_commit(&st_empty[s]);
+            umma_commit(&a_empty[s]);
+            umma_commit(&wk_empty[sw]);
             ++ia;
             if (kbg == 0) SB_DBG_T(ig, 9);
             if (++kbg == uint32_t(C::NCH)) {
@@ -1934,9 +1975,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
           uint32_t o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float g0 = __uint_as_float(v[nbl & 1][2 * j]) * cos_from_signed_half(e[j] & 0xFFFFu);
-            const float g1 = __uint_as_float(v[nbl & 1][2 * j + 1]) * cos_from_signed_half(e[j] >> 16);
-            o[j] = pack_f16x2(g0, g1);
+            o[j] = dz_pair_from_signed_half<false>(__uint_as_float(v[nbl & 1][2 * j]),
+                                                   __uint_as_float(v[nbl & 1][2 * j + 1]), e[j]);
           }
           if (!row_valid) {  // padding rows of the last tile (their seed is zero, but keep dz exactly zero)
 #pragma unroll
