@@ -591,7 +591,11 @@ def run_gpu_arm(args):
     merged = os.environ.get("SIRENB200_BWD_MERGED", "1") != "0"
     alg_bytes = {  # algorithmic HBM bytes per launch (fp16 activations)
         "fwd_gemm": 2 * npix_rank * HIDDEN * 2,
-        "dx_gemm": 3 * npix_rank * HIDDEN * 2,   # merged launch: the weight-gradient role re-reads the same tiles from L2
+        # merged launch: reads dz[l] and act[l-1], writes dz[l-1]; the weight-gradient role re-reads the same tiles
+        # from L2.  The launch of the first hidden layer writes nothing (dz[0] is consumed on chip by the layer-0
+        # gradient reduction), so the average over the DEPTH-2 launches is (3 (DEPTH-3) + 2) / (DEPTH-2) tensors.
+        "dx_gemm": (3 * (DEPTH - 3) + (2 if os.environ.get("SIRENB200_FUSE_L0", "1") != "0" else 3)) / (DEPTH - 2)
+                   * npix_rank * HIDDEN * 2,
         "dw_gemm": (DEPTH - 2) * 2 * npix_rank * HIDDEN * 2,
         "last_layer_loss": 2 * npix_rank * HIDDEN * 2 + npix_rank * C * 4,
         "first_layer": npix_rank * HIDDEN * 2,

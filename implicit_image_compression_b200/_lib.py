@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "sirenb200_workspace_bytes", "sirenb200_set_grid_lut", "sirenb200_set_grid_coords",
     "sirenb200_forward", "sirenb200_forward_backward", "sirenb200_backward", "sirenb200_eval_metrics",
     "sirenb200_adam_step", "sirenb200_apply_mask", "sirenb200_kmeans_quantize",
+    "sirenb200_prune_threshold_search",
     "sirenb200_fakequant_per_channel", "sirenb200_launch_count", "sirenb200_profile_enable",
     "sirenb200_profile_read", "sirenb200_debug_timeline", "sirenb200_sched_step", "sirenb200_adam_step_dev",
     "sirenb200_comm_create", "sirenb200_comm_handle", "sirenb200_comm_connect", "sirenb200_comm_allreduce",
@@ -102,6 +103,7 @@ def load():
     lib.sirenb200_fakequant_per_tensor.argtypes = [vp, c_int64, vp, c_int32, c_float, c_int32, c_int32, vp, vp, vp]
     lib.sirenb200_kmeans_quantize.argtypes = [vp, c_int64, c_int32, c_int32, c_float, vp, vp, vp, vp,
                                               vp, vp]
+    lib.sirenb200_prune_threshold_search.argtypes = [vp, c_int64, c_int64, c_int64, ctypes.c_double, vp, vp, vp]
     lib.sirenb200_fakequant_per_channel.argtypes = [vp, c_int32, c_int32, vp, vp, c_float, c_float, vp, vp,
                                                     vp, vp]
     lib.sirenb200_debug_timeline.argtypes = [vp, POINTER(c_int64), c_int32]

@@ -1780,4 +1780,75 @@ __global__ void __launch_bounds__(kCommThreads) p2p_allreduce_kernel(const CommP
   if (threadIdx.x == 0) epoch_b[b] = epoch;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Global-magnitude prune threshold (reference: pipeline/masking/funcs/prune.py:54-104).  The reference multiplies a
+// persistent threshold up or down until the number of weights it removes is within `tolerance` of the target, each
+// probe being `(|w| > threshold).sum()` per layer.  Here the magnitudes of all masked layers are sorted ONCE (device
+// sort by the caller); a probe is then n_valid - upper_bound(threshold), and the whole search runs in ONE warp on
+// the device.  The arithmetic is the reference's: Python floats are IEEE doubles, the comparison with the fp32
+// weights rounds the threshold to fp32 (as torch does when it compares an fp32 tensor with a Python float), and
+// the products are kept unfused (__dmul_rn) so that the threshold trajectory is bit-identical.
+//   state[0] = threshold (in/out), state[1] = increment (in), result[0] = total_removed (out, as double)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long warp_upper_bound(const float* a, long long n, float t, int lane) {
+  // number of elements <= t in the ascending, NaN-free array a[0, n): 32-ary search, one probe per lane.
+  // invariant: a[i] <= t for i < lo, a[i] > t for i >= hi
+  long long lo = 0, hi = n;
+  while (hi - lo > 32) {
+    const long long step = (hi - lo + 31) / 32;
+    long long pos = lo + (lane + 1) * step - 1;
+    if (pos > hi - 1) pos = hi - 1;
+    const int k = __popc(__ballot_sync(0xffffffffu, a[pos] <= t));  // probes 0..k-1 hold (positions ascend)
+    if (k == 32) return hi;  // the last probe is a[hi - 1]
+    long long phi = lo + (k + 1) * step - 1;  // probe k: a[phi] > t
+    if (phi > hi - 1) phi = hi - 1;
+    lo += k * step;  // probe k-1 was not clamped (else all later probes would hold too)
+    hi = phi;
+  }
+  const long long pos = lo + lane;
+  return lo + __popc(__ballot_sync(0xffffffffu, pos < hi && a[pos] <= t));
+}
+
+__global__ void prune_threshold_search_kernel(const float* __restrict__ sorted_mags, long long n, long long nonzero_total,
+                                              long long tokill, double tolerance, double* state, double* result) {
+  const int lane = threadIdx.x & 31;
+  // NaNs sort last: n_valid = index of the first NaN
+  long long lo = 0, hi = n;
+  while (lo < hi) {  // plain binary search, uniform across the warp
+    const long long mid = (lo + hi) >> 1;
+    const float v = sorted_mags[mid];
+    if (v != v) hi = mid; else lo = mid + 1;
+  }
+  const long long n_valid = lo;
+  double threshold = state[0], increment = state[1];
+  long long total_removed = 0, prev_removed = 0;
+  int tries = 0;
+  const double tk = double(tokill);
+  const double upper = __dmul_rn(tk, __dadd_rn(1.0, tolerance)), lower = __dmul_rn(tk, __dsub_rn(1.0, tolerance));
+  const double band = __dmul_rn(tk, tolerance);
+  for (int guard = 0; guard < 1000000; ++guard) {
+    if (!(fabs(double(total_removed - tokill)) > band)) break;
+    const long long le = warp_upper_bound(sorted_mags, n_valid, __double2float_rn(threshold), lane);
+    total_removed = nonzero_total - (n_valid - le);
+    if (prev_removed == total_removed) {
+      if (++tries == 10) break;
+    } else {
+      tries = 0;
+    }
+    prev_removed = total_removed;
+    if (double(total_removed) > upper) {
+      threshold = __dmul_rn(threshold, __dsub_rn(1.0, increment));
+      increment = __dmul_rn(increment, 0.99);
+    } else if (double(total_removed) < lower) {
+      threshold = __dmul_rn(threshold, __dadd_rn(1.0, increment));
+      increment = __dmul_rn(increment, 0.99);
+    }
+  }
+  if (lane == 0) {
+    state[0] = threshold;
+    result[0] = double(total_removed);
+  }
+}
+
 }  // namespace sb

@@ -1556,6 +1556,17 @@ int sirenb200_apply_mask(float* w, const float* mask, int64_t n, sirenb200_strea
   return 0;
 }
 
+int sirenb200_prune_threshold_search(const float* sorted_mags, int64_t n, int64_t nonzero_total, int64_t tokill,
+                                     double tolerance, double* state, double* result, sirenb200_stream_t stream) {
+  if (!sorted_mags || n < 1 || !state || !result || tokill < 1 || !(tolerance >= 0.0))
+    return fail(SIRENB200_ERR_INVALID, "prune_threshold_search: bad argument");
+  prune_threshold_search_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      sorted_mags, static_cast<long long>(n), static_cast<long long>(nonzero_total), static_cast<long long>(tokill),
+      tolerance, state, result);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 int sirenb200_fakequant_per_channel(const float* w, int32_t rows, int32_t cols,
                                     const float* row_min, const float* row_max, float neg_div,
                                     float pos_div, int8_t* codes, float* scales, float* w_out,

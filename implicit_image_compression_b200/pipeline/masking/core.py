@@ -274,25 +274,30 @@ class Masking:
         if self.global_prune:
             self.stats.total_removed = self.prune_func(self)
         else:
+            kept = []
             for name, weight in self._masked_parameters():
                 new_mask = self.prune_func(self, self.mask_dict[name], weight, name)
-                removed = self.stats.nonzeros_dict[name] - int(new_mask.sum().item())
+                kept.append(new_mask.sum())
+                self.mask_dict[name] = new_mask
+            kept = torch.stack(kept).tolist() if kept else []  # one sync for all layers
+            for (name, _), k in zip(self._masked_parameters(), kept):
+                removed = self.stats.nonzeros_dict[name] - int(k)
                 self.stats.total_removed += removed
                 self.stats.removed_dict[name] = removed
-                self.mask_dict[name] = new_mask
         if self.growth_mode == "none":
             total_nonzero_new = self.stats.total_nonzero - self.stats.total_removed
         else:
             redistribute = self.redistribution_mode not in ["nonzero", "none"]
             if redistribute:
                 name2regrowth = self.calc_redistributed_densities()
+            grown = []
             for name, weight in self._masked_parameters():
                 num_growth = name2regrowth[name] if redistribute else self.stats.removed_dict[name]
                 new_mask = self.growth_func(self, name, num_growth, weight)
-                new_nonzero = new_mask.sum().item()
+                grown.append(new_mask.sum())
                 self.mask_dict.pop(name)
                 self.mask_dict[name] = new_mask.float()
-                total_nonzero_new += new_nonzero
+            total_nonzero_new += sum(torch.stack(grown).tolist()) if grown else 0  # one sync for all layers
         self.apply_mask()
         if not self.dense_gradients:
             self.reset_momentum()

@@ -20,8 +20,8 @@ def momentum_growth(masking, name, total_regrowth, weight):
 def abs_grad_growth(masking, name, total_regrowth, weight):
     """grow.py:58-97: enable the masked-out positions with the largest |grad|; grown weights start at 0."""
     new_mask = masking.mask_dict[name].data.bool()
-    if (new_mask == 0).sum().item() == 0:
-        return new_mask
+    # (the reference returns early when the layer has no inactive position; then nothing was pruned either, so
+    # total_regrowth is 0 and the selection below is empty - no need to synchronise for the count)
     grad = weight.grad * _inactive(new_mask, weight.grad)
     _, order = torch.sort(torch.abs(grad).flatten(), descending=True)
     pick = order[: int(total_regrowth)]

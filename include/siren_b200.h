@@ -132,6 +132,15 @@ int sirenb200_adam_step_dev(int32_t n_tensors, float* const* h_params, float* co
 /* Masking.apply_mask for one tensor (pipeline/masking/core.py:272-279): w <- w * mask (bit-exact). */
 int sirenb200_apply_mask(float* w, const float* mask, int64_t n, sirenb200_stream_t stream);
 
+/* Global-magnitude prune threshold search (pipeline/masking/funcs/prune.py:54-104) on the device.
+ * sorted_mags: the |w| of all masked layers, ascending (NaNs last), n elements; nonzero_total: weights currently
+ * active; tokill: ceil(prune_rate * baseline_nonzero).  state (device, 2 doubles): [0] the persistent threshold
+ * (in/out), [1] the increment (in).  result (device, 1 double): the number of weights the final threshold removes.
+ * The threshold trajectory is the reference's, step for step (IEEE double arithmetic, unfused products, fp32
+ * rounding of the threshold in every comparison). */
+int sirenb200_prune_threshold_search(const float* sorted_mags, int64_t n, int64_t nonzero_total, int64_t tokill,
+                                     double tolerance, double* state, double* result, sirenb200_stream_t stream);
+
 /* KmeansQuant.find_centroids (pipeline/quant/kmeans.py:110-150 + kmeans_helper.py:59-116) on n weights.
  * init_centers: optional [2^bits - 1] initial guess (kmeans.py:123-129 builds it with torch.linspace on the
  * weights' device; NULL = linspace(min, max) of the non-zero weights evaluated in-kernel with CUDA

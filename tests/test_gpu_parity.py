@@ -468,3 +468,33 @@ def test_fused_kernel_variants_match_the_kernels_they_replace(monkeypatch, hidde
                 assert torch.equal(a, b), (env, i)
             else:
                 assert _rel(a, b) <= 1e-5, (env, i, _rel(a, b))
+
+
+@pytest.mark.parametrize("n,seed", [(331_000, 0), (4097, 1), (31, 2), (65_536, 3)])
+def test_device_prune_threshold_search_matches_the_reference_loop(n, seed):
+    """sirenb200_prune_threshold_search (one warp, on the sorted magnitudes) follows the reference's multiplicative
+    search (prune.py:74-95) step for step: same final threshold bit for bit (IEEE doubles), same removed count —
+    including ties, zeros (already pruned weights), a NaN, and searches that end through the ten-stalls rule."""
+    from implicit_image_compression_b200 import _lib
+    from implicit_image_compression_b200.pipeline.masking.funcs.prune import _host_threshold_search
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(n, generator=g) * 0.05
+    w[::5] = 0.0
+    if n > 100:
+        w[3::13] = w[7]       # ties
+        w[11] = float("nan")
+    mags = torch.sort(w.abs())[0]
+    nonzero_total = int((w != 0).sum())  # NaN != 0 counts, as it does in the reference's mask statistics
+    lib = _lib.load()
+    for threshold, increment, frac, tol in [(1e-3, 0.2, 0.3, 0.02), (0.5, 0.2, 0.1, 0.0), (1e-6, 0.5, 0.6, 0.05),
+                                            (0.02, 0.01, 0.25, 1e-4)]:
+        tokill = max(1, math.ceil(frac * nonzero_total))
+        want_t, want_removed = _host_threshold_search(mags.numpy(), nonzero_total, tokill, tol, threshold, increment)
+        state = torch.tensor([threshold, increment, 0.0], dtype=torch.float64, device="cuda")
+        dm = mags.cuda()
+        _lib.check(lib.sirenb200_prune_threshold_search(dm.data_ptr(), dm.numel(), nonzero_total, tokill, tol,
+                                                        state.data_ptr(), state.data_ptr() + 16,
+                                                        torch.cuda.current_stream().cuda_stream))
+        got_t, _, got_removed = state.tolist()
+        assert got_t == want_t, (n, threshold, increment, frac, tol, got_t, want_t)
+        assert int(got_removed) == want_removed
