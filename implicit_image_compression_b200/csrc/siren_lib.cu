@@ -127,6 +127,9 @@ struct sirenb200_plan {
   bool bwd_merged = true;      // dX GEMM and weight-gradient reduction of a layer in ONE launch (SIRENB200_BWD_MERGED=0: separate)
   int dw_ctas = 0;             // CTAs of that launch that run the reduction
   int merged_splits = 0;       // pixel splits of the reduction role
+  int merged_splits_l0 = 0;    // ... in the first hidden layer's launch (its dX role also reduces layer 0's gradient and
+                               // is the slower role there, so it gets more of the SMs); 0: same as merged_splits
+  int l1_splits = 0;           // split slabs the first hidden layer's reduction wrote in the last backward
   int pace_window = 192;       // tiles the reduction role may run ahead of the dX role
   int pace_window_dx = 192;    // ... the dX role ahead of the reduction role (negative: it follows that far behind)
   int stall_slot = 0;
@@ -256,7 +259,7 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
                    cudaStream_t st) {
   constexpr int NT = W < 256 ? W : 256;  // output columns per work item
   constexpr int NPARTS = W / NT;
-  using Cfg = RowGemmCfg<W, NT, MODE, NPARTS>;
+  using Cfg = RowGemmCfg<W, NT, MODE, NPARTS, RED>;
   auto kfn = rowgemm_kernel<W, NT, MODE, false, NPARTS, GEN, RED>;
   static bool attr_set[64] = {};
   if (!attr_set[p->device & 63]) {
@@ -540,7 +543,7 @@ template <int W, bool RED>
 int launch_bwd_merged(sirenb200_plan* p, const RowGemmArgs& ra, const ColGemmJobs& jobs, int l, cudaStream_t st) {
   constexpr int NT = W < 256 ? W : 256;
   constexpr int NPARTS = W / NT;
-  using RCfg = RowGemmCfg<W, NT, MODE_DX, NPARTS>;
+  using RCfg = RowGemmCfg<W, NT, MODE_DX, NPARTS, RED>;
   using CCfg = ColGemmCfg<NT>;
   constexpr uint32_t SMEM1 = RCfg::SMEM_BYTES > CCfg::SMEM_BYTES ? RCfg::SMEM_BYTES : CCfg::SMEM_BYTES;
   constexpr uint32_t SMEM = SMEM1 > ColGemm2Cfg::SMEM_BYTES ? SMEM1 : ColGemm2Cfg::SMEM_BYTES;
@@ -629,13 +632,15 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
     bool done = false;
     if (merged) {
       ColGemmJobs jobs{};
-      fill_jobs(jobs, l, 1, p->active_splits, 1);
+      const bool own_split = l == 1 && fuse_l0 && p->merged_splits_l0 > 0;
+      fill_jobs(jobs, l, 1, own_split ? p->merged_splits_l0 : p->active_splits, 1);
+      if (l == 1) p->l1_splits = jobs.splits;
       if (l == 1 && fuse_l0) {
         ra.gen_coord = p->coord;
         ra.gen_coord.p_offset = ch.p0;
         ra.red_part = p->l0_part;
         rc = launch_bwd_merged<W, true>(p, ra, jobs, l, st);
-        p->l0_used = 2 * p->last_rowgemm_grid;
+        p->l0_used = kRedWarpsPerChunk * p->last_rowgemm_grid;
       } else {
         rc = launch_bwd_merged<W, false>(p, ra, jobs, l, st);
       }
@@ -648,7 +653,7 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
         ra.gen_coord.p_offset = ch.p0;
         ra.red_part = p->l0_part;
         rc = launch_rowgemm<W, MODE_DX, false, true>(p, p->tm_dz, p->tm_wt[0], p->tm_act, p->tm_dz, ra, st);
-        p->l0_used = 2 * p->last_rowgemm_grid;  // two reducer warps (pixel halves) per chunk
+        p->l0_used = kRedWarpsPerChunk * p->last_rowgemm_grid;  // one partial row per reducer warp of a chunk
         done = true;
       }
     }
@@ -706,8 +711,9 @@ void tc_build_reduce(const sirenb200_plan* p, float* const* grads, float scale, 
   add(grads[0], p->l0_part, 2 * Wm, p->l0_used, 3 * W, 0);   // [W, 2] block: the model's rows come first
   add(grads[1], p->l0_part + 2 * W, Wm, p->l0_used, 3 * W, 0);
   for (int l = 1; l <= nh; ++l) {
-    add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, Wm * Wm, p->active_splits, int64_t(nh) * W * W, Wm);
-    add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, Wm, p->active_splits, int64_t(nh) * W, 0);
+    const int ns = (l == 1 && p->l1_splits > 0) ? p->l1_splits : p->active_splits;
+    add(grads[2 * l], p->dw_part + size_t(l - 1) * W * W, Wm * Wm, ns, int64_t(nh) * W * W, Wm);
+    add(grads[2 * l + 1], p->db_part + size_t(l - 1) * W, Wm, ns, int64_t(nh) * W, 0);
   }
   const int64_t lstride = int64_t(C) * W + C + 1;
   add(grads[2 * (D - 1)], p->last_part, C * Wm, p->last_grid * nchunks, lstride, Wm);
@@ -1146,6 +1152,18 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       env = getenv("SIRENB200_PAIR");
       p->bwd_pair = !(env && atoi(env) == 0);
       if (p->bwd_merged) p->merged_splits = ms;
+      // the first hidden layer's launch: its dX role also reduces layer 0's gradient (~6.8 k cycles per tile against
+      // ~5.5 k) and writes no dz, so the reduction role gets 30 % of the SMs there (A/B at c2, dX-class time per step:
+      // 52 / 44 / 36 / 28 CTAs = 535 / 518 / 546 / 585 us)
+      {
+        int want0 = (p->nsm * 30 + 50) / 100;
+        env = getenv("SIRENB200_DW_CTAS_L0");
+        if (env && atoi(env) > 0) want0 = atoi(env);
+        int m0 = want0 / per_split;
+        if (m0 < 1) m0 = 1;
+        if (m0 > ms) m0 = ms;  // the partial slabs are sized for merged_splits
+        if (p->bwd_merged) p->merged_splits_l0 = m0;
+      }
     }
     const int slabs = (p->bwd_merged && p->merged_splits > splits) ? p->merged_splits : splits;
     ALLOC(p->dw_part, int64_t(slabs) * (nh > 0 ? nh : 1) * W * W);
@@ -1177,7 +1195,7 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
     p->l0_grid = p->nsm * 2;
     if (p->l0_grid > p->chunk_tiles) p->l0_grid = p->chunk_tiles;
     {  // room for the stand-alone kernel's l0_grid rows or the dX-fused reducer's 2 rows per CTA
-      int rows = 2 * p->nsm;
+      int rows = kRedWarpsPerChunk * p->nsm;
       if (rows < p->l0_grid) rows = p->l0_grid;
       ALLOC(p->l0_part, int64_t(p->nchunks) * rows * 3 * W);
     }

@@ -164,7 +164,7 @@ __device__ __forceinline__ void pace_post(const PaceCtx& pc, unsigned int n = 1u
 // B operand (NDIM x KDIM fp16) fits next to the rings it stays RESIDENT in shared memory for the kernel's
 // lifetime (hidden <= 256); otherwise (hidden 512) its 64-wide k-blocks are streamed through the same
 // ring stage as the A k-blocks and every 128-row tile is visited once per output part.
-template <int KDIM, int NDIM, int MODE, int NPARTS = 1>
+template <int KDIM, int NDIM, int MODE, int NPARTS = 1, bool RED = false>
 struct RowGemmCfg {
   static_assert(KDIM % 64 == 0 && NDIM % 64 == 0, "hidden size must be a multiple of 64");
   static_assert(NDIM >= 16 && NDIM <= 256, "UMMA N range");
@@ -175,8 +175,16 @@ struct RowGemmCfg {
 #define SB_FWD_SA 4
 #define SB_FWD_SEO 2
 #endif
-  static constexpr int SA = (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
-  static constexpr int SEO = (MODE == MODE_DX) ? 3 : ((KDIM * NDIM * 2 <= 131072) ? SB_FWD_SEO : 2);  // epilogue in/out ring depth
+  // RED (resident B): the reducer warps hold every staging slot ~2 k cycles longer than the store does, and the MMA
+  // (2 k cycles per tile) is far from the limit there: one A stage less buys a fourth staging slot
+#ifndef SB_RED_SA
+#define SB_RED_SA 2
+#define SB_RED_SEO 4
+#endif
+  static constexpr bool RED_RING = RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072;
+  static constexpr int SA = RED_RING ? SB_RED_SA : (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
+  static constexpr int SEO = RED_RING ? SB_RED_SEO
+                                      : (MODE == MODE_DX) ? 3 : ((KDIM * NDIM * 2 <= 131072) ? SB_FWD_SEO : 2);  // epilogue in/out ring depth
   static constexpr uint32_t B_KB_BYTES = NDIM * 128;
   static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u);
   static constexpr uint32_t A_STAGE = kChunkBytes + (STREAM_B ? B_KB_BYTES : 0u);
@@ -231,11 +239,18 @@ struct RowGemmArgs {
 #ifndef SB_DX_EPW
 #define SB_DX_EPW 16
 #endif
+// RED (the first hidden layer's dX GEMM also reduces layer 0's gradient): SB_RED_RW reducer warps per 64-column
+// chunk (each takes 128 / SB_RED_RW of the tile's pixel rows) next to SB_RED_EPW epilogue warps
+#ifndef SB_RED_RW
+#define SB_RED_RW 2
+#define SB_RED_EPW 16
+#endif
+constexpr int kRedWarpsPerChunk = SB_RED_RW;
 __host__ __device__ constexpr int rowgemm_epi_warps(int mode, bool gen, bool red) {
-  return (mode == MODE_DX && !gen) ? SB_DX_EPW : 8;
+  return (mode == MODE_DX && !gen) ? (red ? SB_RED_EPW : SB_DX_EPW) : 8;
 }
 __host__ __device__ constexpr int rowgemm_threads(int mode, bool gen, bool red) {
-  return gen ? 576 : 32 * (4 + rowgemm_epi_warps(mode, gen, red) + (red ? 8 : 0));
+  return gen ? 576 : 32 * (4 + rowgemm_epi_warps(mode, gen, red) + (red ? 4 * SB_RED_RW : 0));
 }
 
 template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
@@ -249,7 +264,7 @@ template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN 
 __device__ __forceinline__ void
 rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmE, const CUtensorMap& tmO,
              const RowGemmArgs& args, const uint32_t idesc, const int cta, const int ncta, const PaceCtx pace) {
-  using C = RowGemmCfg<KDIM, NDIM, MODE, NPARTS>;
+  using C = RowGemmCfg<KDIM, NDIM, MODE, NPARTS, RED>;
   // epilogue warps: 8 (two per TMEM lane quadrant, 32 of a chunk's 64 columns each), or 16 for the plain dX GEMM
   // (four per quadrant, 16 columns each): its cvt -> FFMA -> MUFU.SQRT -> FMUL -> F2FP chains need more than two
   // warps per scheduler to hide their latency (stall accounting: the 8-warp epilogue was busy 5.1 k cycles per tile)
@@ -258,6 +273,14 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   const int num_items = args.num_tiles * NPARTS;  // item = (tile, output part)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // SIRENB200_STALLS: lifetime of the CTA in SM cycles and in globaltimer ns (-> effective SM clock, set-up and drain
+  // time outside the role loops, gaps between consecutive launches)
+  long long life_c0 = 0;
+  unsigned long long life_g0 = 0;
+  if (args.stall && threadIdx.x == 0) {
+    life_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(life_g0));
+  }
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* a_full = bars;
@@ -287,7 +310,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     mbar_init(b_full, 1);
     for (int i = 0; i < C::SEO; ++i) {
       mbar_init(&eo_full[i], 1);
-      mbar_init(&eo_empty[i], RED ? 3 : 1);  // RED: the store has read the chunk AND both reducer warps have
+      mbar_init(&eo_empty[i], RED ? 1 + kRedWarpsPerChunk : 1);  // RED: the store has read the chunk AND both reducer warps have
     }
     for (int i = 0; i < 4; ++i) mbar_init(&red_full[i], 1);
     for (int i = 0; i < 2; ++i) {
@@ -510,10 +533,13 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   } else if (RED && warp >= 4 + EPW) {
     // ===================== layer-0 gradient: reduce each finished dz[0] chunk over its 128 pixels =========
     static_assert(!RED || (MODE == MODE_DX && NPARTS <= 2 && C::NB <= 4), "RED: dX of the first hidden layer");
-    // two warps per 64-column chunk (64 pixel rows each); lane -> columns part*NDIM + nb*64 + 2*lane, +1.
+    // RW warps per 64-column chunk (128 / RW pixel rows each); lane -> columns part*NDIM + nb*64 + 2*lane, +1.
     // With two output parts (hidden 512) every tile is visited twice, once per part; each part has its own
     // accumulators.
-    const int nb = (warp - 4 - EPW) >> 1, half = (warp - 4 - EPW) & 1;
+    constexpr int RW = kRedWarpsPerChunk;
+    constexpr int QN = (128 / RW + 31) / 32;  // coordinate registers per lane (rows lane + 32 q of the warp's range)
+    const int nb = (warp - 4 - EPW) / RW, sub = (warp - 4 - EPW) % RW;
+    const int row_lo = sub * 128 / RW, row_hi = (sub + 1) * 128 / RW;
     if (nb < C::NB) {
       const CoordSrc& cs = args.gen_coord;
       float acc[NPARTS][6];
@@ -527,23 +553,25 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       uint32_t ic = uint32_t(nb), il = 0;
       for (int item = cta; item < num_items; item += ncta, ic += C::NB, ++il) {
         const int t = item / NPARTS, part = item % NPARTS;
-        // coordinates of rows lane + 32 q (zero for the padding rows: their dz is zero anyway)
-        float xh[2], xw[2];
+        // coordinates of rows row_lo + lane + 32 q (zero for the padding rows: their dz is zero anyway)
+        float xh[QN], xw[QN];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int r = t * kRowsPerTile + half * 64 + lane + 32 * q;
+        for (int q = 0; q < QN; ++q) {
+          const int rl = row_lo + lane + 32 * q;
+          const int r = t * kRowsPerTile + rl;
           xh[q] = xw[q] = 0.f;
-          if (r < args.valid_rows) load_xy(cs, r, xh[q], xw[q]);
+          if (rl < row_hi && r < args.valid_rows) load_xy(cs, r, xh[q], xw[q]);
         }
         const uint32_t s = ic % C::SEO;
         const uint32_t buf = smem_u32(smem + C::OFF_EO + s * kChunkBytes);
         mbar_wait(&red_full[nb], il & 1u);
         float sh0 = 0.f, sw0 = 0.f, sb0 = 0.f, sh1 = 0.f, sw1 = 0.f, sb1 = 0.f;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < QN; ++q) {
+          const int nrow = (row_hi - row_lo - 32 * q) < 32 ? (row_hi - row_lo - 32 * q) : 32;
 #pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const int r = half * 64 + q * 32 + rr;
+          for (int rr = 0; rr < nrow; ++rr) {
+            const int r = row_lo + q * 32 + rr;
             const uint32_t addr = buf + r * 128 + (((uint32_t(lane) >> 2) ^ uint32_t(r & 7)) << 4) + lane_off;
             const uint32_t hv = ld_shared_u32(addr);
             const float v0 = __half2float(__ushort_as_half(static_cast<unsigned short>(hv & 0xFFFFu)));
@@ -572,7 +600,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
           }
       }
       constexpr int WFULL = NDIM * NPARTS;
-      float* part_out = args.red_part + (size_t(cta) * 2 + half) * 3 * WFULL;
+      float* part_out = args.red_part + (size_t(cta) * RW + sub) * 3 * WFULL;
 #pragma unroll
       for (int pp = 0; pp < NPARTS; ++pp) {
         const int c0 = pp * NDIM + nb * 64 + 2 * lane;
@@ -705,6 +733,14 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+  if (args.stall && threadIdx.x == 0) {
+    unsigned long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    args.stall[cta * 16 + 12] = clock64() - life_c0;
+    args.stall[cta * 16 + 13] = (long long)(g1 - life_g0);
+    args.stall[cta * 16 + 14] = (long long)life_g0;
+    args.stall[cta * 16 + 15] = (long long)g1;
   }
 }
 

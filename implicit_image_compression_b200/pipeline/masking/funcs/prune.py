@@ -60,7 +60,7 @@ def global_magnitude_prune(masking):
     mags = torch.sort(torch.cat([torch.abs(w.data).reshape(-1) for _, w in masked]))[0]
     nonzero_total = sum(masking.stats.nonzeros_dict[n] for n, _ in masked)
     if mags.is_cuda:
-        from ... import _lib
+        from .... import _lib
         state = torch.tensor([masking.prune_threshold, masking.increment, 0.0], dtype=torch.float64,
                              device=mags.device)
         with torch.cuda.device(mags.device):

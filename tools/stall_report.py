@@ -52,6 +52,14 @@ for slot in range(12):
     if rowg:
         print("  row : " + "  ".join(f"{nm}={sum(r[k] for r in rowg) / len(rowg):.0f}" for k, nm in enumerate(names_row)))
         print("  row max: " + "  ".join(f"{nm}={max(r[k] for r in rowg)}" for k, nm in enumerate(names_row)))
+    if rowg:
+        life_c = sum(r[12] for r in rowg) / len(rowg)
+        life_ns = sum(r[13] for r in rowg) / len(rowg)
+        t0, t1 = min(r[14] for r in rowg), max(r[15] for r in rowg)
+        if life_ns > 0:
+            print(f"  row CTA lifetime: {life_c:.0f} cycles = {life_ns / 1e3:.1f} us -> SM clock {life_c / life_ns * 1e3:.0f} MHz; "
+                  f"launch span (first CTA start .. last CTA end) {(t1 - t0) / 1e3:.1f} us; first start @{t0 % 10**9 / 1e3:.1f} us, "
+                  f"last end @{t1 % 10**9 / 1e3:.1f} us")
     if colg:
         print("  red : " + "  ".join(f"{nm}={sum(r[k] for r in colg) / len(colg):.0f}" for k, nm in enumerate(names_col) if nm != "-"))
         print("  red max: " + "  ".join(f"{nm}={max(r[k] for r in colg)}" for k, nm in enumerate(names_col) if nm != "-"))
