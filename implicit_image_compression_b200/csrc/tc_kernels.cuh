@@ -182,9 +182,17 @@ struct RowGemmCfg {
 #define SB_RED_SEO 4
 #endif
   static constexpr bool RED_RING = RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072;
-  static constexpr int SA = RED_RING ? SB_RED_SA : (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
+#ifndef SB_DX_SA
+#define SB_DX_SA 3
+#define SB_DX_SEO 3
+#endif
+  static constexpr bool DX_RING = !RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072;
+  static constexpr int SA = RED_RING ? SB_RED_SA
+                            : DX_RING ? SB_DX_SA
+                                      : (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
   static constexpr int SEO = RED_RING ? SB_RED_SEO
-                                      : (MODE == MODE_DX) ? 3 : ((KDIM * NDIM * 2 <= 131072) ? SB_FWD_SEO : 2);  // epilogue in/out ring depth
+                             : DX_RING ? SB_DX_SEO
+                                       : (MODE == MODE_DX) ? 3 : ((KDIM * NDIM * 2 <= 131072) ? SB_FWD_SEO : 2);  // epilogue in/out ring depth
   static constexpr uint32_t B_KB_BYTES = NDIM * 128;
   static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u);
   static constexpr uint32_t A_STAGE = kChunkBytes + (STREAM_B ? B_KB_BYTES : 0u);
