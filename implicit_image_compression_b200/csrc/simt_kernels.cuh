@@ -1484,10 +1484,22 @@ struct StepEndArgs {
   unsigned long long timeout_ns;
 };
 
-__global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
+// The Adam inputs of the block's first kStepEndPre chunks are loaded next to the partials (phase 1) and the whole
+// update is computed while the grid barrier fills; what follows the barrier is the skip decision and the stores.
+constexpr int kStepEndPre = 3;
+struct StepEndPre {
+  float g[4], p[4], m[4], v[4], k[4];
+  int t, e, n;  // descriptor, first element, elements of this thread (0: nothing)
+};
+
+// 8 worker warps + 1 warp whose lane 0 evaluates the schedule (three double-precision pow: ~3 us on one thread,
+// which used to sit between the grid barrier and the Adam arithmetic of every block)
+constexpr int kStepEndThreads = 288;
+__global__ void __launch_bounds__(kStepEndThreads) step_end_kernel(const StepEndArgs a) {
   __shared__ float red_s[8][32];
-  __shared__ float sh_scal[2];
+  __shared__ double sh_sched[2];
   const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+  const bool worker = tid < 256;
   const ReduceArgs& r = a.red;
   const int nchunks = r.chunk_begin[r.ndesc];
   const float scale = r.gscale ? r.scale / *r.gscale : r.scale;  // the OLD seed scale: read before the barrier
@@ -1501,15 +1513,24 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
     mine = a.cp.data[a.rank] + int64_t(par) * a.max_floats;
   }
   bool bad = false;
+  if (tid == 256) {
+    // schedule of the step about to be applied (sched_step_kernel's arithmetic, bit for bit); the spare
+    // warp computes it while the workers reduce
+    const double lr = double(float(a.sched[1] * pow(a.sched[2], double(step / int(a.sched[3])))));
+    const double bc1 = 1.0 - pow(double(float(a.sched[4])), double(step + 1));
+    const double bc2 = 1.0 - pow(double(float(a.sched[5])), double(step + 1));
+    sh_sched[0] = lr / bc1;
+    sh_sched[1] = sqrt(bc2);
+  }
 
   // ---- squared error (block 0) ----
   float sse = 0.f;
   if (b == 0) {
     float s = 0.f;
-    for (int i = tid; i < a.loss_nparts; i += 256) s += a.loss_partial[i * a.loss_stride];
+    for (int i = tid; worker && i < a.loss_nparts; i += 256) s += a.loss_partial[i * a.loss_stride];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((tid & 31) == 0) red_s[0][tid >> 5] = s;
+    if (worker && (tid & 31) == 0) red_s[0][tid >> 5] = s;
     __syncthreads();
     if (tid == 0) {
       for (int k = 0; k < 8; ++k) sse += red_s[0][k];
@@ -1517,15 +1538,34 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
     __syncthreads();
   }
 
+  StepEndPre pre[kStepEndPre];
+#pragma unroll
+  for (int i = 0; i < kStepEndPre; ++i) pre[i].n = 0;
+  // Adam inputs of (descriptor t, elements e .. e + n): issued early, consumed after the gradients are final
+  auto load_state = [&](StepEndPre& q, int t, int e, int n) {
+    q.t = t;
+    q.e = e;
+    q.n = a.p[t] ? n : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < q.n) {
+        q.p[j] = a.p[t][e + j];
+        q.m[j] = a.m[t][e + j];
+        q.v[j] = a.v[t][e + j];
+        q.k[j] = a.mask[t] ? a.mask[t][e + j] : 1.0f;
+      }
+  };
+
   // ---- phase 1: reduce this block's chunks over the splits ----
   int t = 0;
-  for (int c = b; c < nchunks; c += G) {
+  auto phase1_chunk = [&](int c, StepEndPre* q) {
     while (t + 1 < r.ndesc && c >= r.chunk_begin[t + 1]) ++t;
     const ReduceDesc d = r.d[t];
     float* out = comm ? mine + a.flat_off[t] : d.dst;
     if (d.vec) {
       const int e4 = (c - r.chunk_begin[t]) * 1024 + tid * 4;
-      if (e4 < d.n) {
+      if (worker && e4 < d.n) {
+        if (q) load_state(*q, t, e4, 4);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* src = d.src + reduce_src_index(d, e4);
 #pragma unroll 8
@@ -1541,13 +1581,22 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
         acc.z *= scale;
         acc.w *= scale;
         *reinterpret_cast<float4*>(out + e4) = acc;
-        if (!comm) bad |= !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+        if (!comm) {
+          bad |= !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+          if (q) {
+            q->g[0] = acc.x;
+            q->g[1] = acc.y;
+            q->g[2] = acc.z;
+            q->g[3] = acc.w;
+          }
+        }
       }
     } else {
       const int e = (c - r.chunk_begin[t]) * 32 + (tid & 31);
       const int lane = tid >> 5;
       float s = 0.f;
-      if (e < d.n) {
+      if (worker && e < d.n) {
+        if (q && lane == 0) load_state(*q, t, e, 1);
         const float* src = d.src + reduce_src_index(d, e);
         int sp = lane;
         for (; sp + 24 < d.nsplit; sp += 32) {  // 4 independent loads in flight
@@ -1559,7 +1608,7 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
         }
         for (; sp < d.nsplit; sp += 8) s += src[int64_t(sp) * d.split_stride];
       }
-      red_s[lane][tid & 31] = s;
+      if (worker) red_s[lane][tid & 31] = s;
       __syncthreads();
       if (lane == 0 && e < d.n) {
         float x = 0.f;
@@ -1567,11 +1616,20 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
         for (int k = 0; k < 8; ++k) x += red_s[k][tid];
         x *= scale;
         out[e] = x;
-        if (!comm) bad |= !isfinite(x);
+        if (!comm) {
+          bad |= !isfinite(x);
+          if (q) q->g[0] = x;
+        }
       }
       __syncthreads();
     }
+  };
+#pragma unroll
+  for (int i = 0; i < kStepEndPre; ++i) {
+    const int c = b + i * G;
+    if (c < nchunks) phase1_chunk(c, &pre[i]);
   }
+  for (int c = b + kStepEndPre * G; c < nchunks; c += G) phase1_chunk(c, nullptr);
 
   // ---- exchange over NVLink peer memory ----
   if (comm) {
@@ -1587,12 +1645,12 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
     __syncthreads();
     const int64_t poff = int64_t(par) * a.max_floats;
     t = 0;
-    for (int c = b; c < nchunks; c += G) {
+    auto exchange_chunk = [&](int c, StepEndPre* qp) {
       while (t + 1 < r.ndesc && c >= r.chunk_begin[t + 1]) ++t;
       const ReduceDesc d = r.d[t];
       if (d.vec) {
         const int e4 = (c - r.chunk_begin[t]) * 1024 + tid * 4;
-        if (e4 < d.n) {
+        if (worker && e4 < d.n) {
           float4 v[kCommMaxRanks];
 #pragma unroll
           for (int q = 0; q < kCommMaxRanks; ++q)
@@ -1608,6 +1666,12 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
             }
           *reinterpret_cast<float4*>(d.dst + e4) = acc;
           bad |= !(isfinite(acc.x) && isfinite(acc.y) && isfinite(acc.z) && isfinite(acc.w));
+          if (qp) {
+            qp->g[0] = acc.x;
+            qp->g[1] = acc.y;
+            qp->g[2] = acc.z;
+            qp->g[3] = acc.w;
+          }
         }
       } else {
         const int e = (c - r.chunk_begin[t]) * 32 + tid;
@@ -1622,9 +1686,16 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
             if (q < a.world) acc += v[q];
           d.dst[e] = acc;
           bad |= !isfinite(acc);
+          if (qp) qp->g[0] = acc;
         }
       }
+    };
+#pragma unroll
+    for (int i = 0; i < kStepEndPre; ++i) {
+      const int c = b + i * G;
+      if (c < nchunks) exchange_chunk(c, &pre[i]);
     }
+    for (int c = b + kStepEndPre * G; c < nchunks; c += G) exchange_chunk(c, nullptr);
     if (b == 0 && tid == 0) {
       sse = 0.f;
       for (int q = 0; q < a.world; ++q) sse += ld_volatile_f1(a.cp.data[q] + poff + a.stats_off);
@@ -1636,11 +1707,31 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
   }
   if (__syncthreads_or(bad) && tid == 0) r.stats[2] = 1.0f;
 
-  // ---- grid barrier ----
+  // ---- grid barrier: arrive, do the Adam arithmetic of the preloaded chunks, then wait ----
+  unsigned long long target = 0;
   if (tid == 0) {
     __threadfence();
     const unsigned long long old = atomicAdd(a.bar, 1ull);
-    const unsigned long long target = (old / G + 1ull) * G;
+    target = (old / G + 1ull) * G;
+  }
+  const float step_size = float(sh_sched[0]), bc2_sqrt = float(sh_sched[1]);  // (written before the barrier above)
+  // torch.optim.Adam.step + Masking.apply_mask (train_helper.py:72-84,177; core.py:272-279,687): pnew if the step
+  // is taken, pskip (mask only) if a non-finite gradient anywhere makes every rank skip it
+  auto adam_math = [&](float g, float& pv, float& mv, float& vv, float k, float& pskip) {
+    mv = mv + (g - mv) * a.omb1;                  // exp_avg.lerp_(grad, 1-beta1)
+    vv = vv * a.beta2 + (a.omb2 * g) * g;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float denom = sqrtf(vv) / bc2_sqrt + a.eps;
+    const float pn = pv + (-step_size * mv) / denom;  // addcdiv_(m, denom, -step_size)
+    pskip = pv;
+    pv = pn;
+  };
+  float pskip[kStepEndPre][4];
+#pragma unroll
+  for (int i = 0; i < kStepEndPre; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < pre[i].n) adam_math(pre[i].g[j], pre[i].p[j], pre[i].m[j], pre[i].v[j], pre[i].k[j], pskip[i][j]);
+  if (tid == 0) {
     uint32_t ns = 16;
     while (true) {
       unsigned long long cur;
@@ -1649,13 +1740,6 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
       __nanosleep(ns);
       if (ns < 256) ns <<= 1;
     }
-    // schedule of the step about to be applied (sched_step_kernel's arithmetic, bit for bit)
-    const double lr = double(float(a.sched[1] * pow(a.sched[2], double(step / int(a.sched[3])))));
-    const double bc1 = 1.0 - pow(double(float(a.sched[4])), double(step + 1));
-    const double bc2 = 1.0 - pow(double(float(a.sched[5])), double(step + 1));
-    const double step_size = lr / bc1, bc2_sqrt = sqrt(bc2);
-    sh_scal[0] = float(step_size);
-    sh_scal[1] = float(bc2_sqrt);
     if (b == 0) {
       const float loss = ld_volatile_f1(r.stats + 1);
       const float flag = ld_volatile_f1(r.stats + 2);
@@ -1669,8 +1753,8 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
         a.gstate[0] = g;
         a.gstate[1] = cap;
       }
-      a.sched[6] = step_size;
-      a.sched[7] = bc2_sqrt;
+      a.sched[6] = sh_sched[0];
+      a.sched[7] = sh_sched[1];
       if (a.loss_ring) a.loss_ring[step % a.ring_len] = loss;
       if (a.loss_host) {
         a.loss_host[0] = loss;
@@ -1682,31 +1766,46 @@ __global__ void __launch_bounds__(256) step_end_kernel(const StepEndArgs a) {
   }
   __syncthreads();
   const bool skip = ld_volatile_f1(r.stats + 2) != 0.f;
-  const float step_size = sh_scal[0], bc2_sqrt = sh_scal[1];
 
-  // ---- phase 2: Adam (+ mask) on the block's own chunks ----
+  // ---- phase 2: the stores of the preloaded chunks ----
+#pragma unroll
+  for (int i = 0; i < kStepEndPre; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < pre[i].n) {
+        const int tt = pre[i].t, e = pre[i].e + j;
+        const bool masked = a.mask[tt] != nullptr;
+        float pv = skip ? pskip[i][j] : pre[i].p[j];
+        if (masked) pv = pv * pre[i].k[j];          // Masking.apply_mask
+        a.p[tt][e] = pv;
+        if (!skip) {
+          a.m[tt][e] = pre[i].m[j];
+          a.v[tt][e] = pre[i].v[j];
+        }
+      }
+  // ---- ... and Adam (+ mask) on the block's remaining chunks (models with more than kStepEndPre chunks per block) ----
   auto adam1 = [&](float* P, float* M, float* V, const float* K, int i, float g) {
     float pv = P[i];
     if (!skip) {
       float mv = M[i], vv = V[i];
-      mv = mv + (g - mv) * a.omb1;                  // exp_avg.lerp_(grad, 1-beta1)
-      vv = vv * a.beta2 + (a.omb2 * g) * g;         // mul_(beta2).addcmul_(g, g, 1-beta2)
+      mv = mv + (g - mv) * a.omb1;
+      vv = vv * a.beta2 + (a.omb2 * g) * g;
       const float denom = sqrtf(vv) / bc2_sqrt + a.eps;
-      pv = pv + (-step_size * mv) / denom;          // addcdiv_(m, denom, -step_size)
+      pv = pv + (-step_size * mv) / denom;
       M[i] = mv;
       V[i] = vv;
     }
-    if (K) pv = pv * K[i];                          // Masking.apply_mask
+    if (K) pv = pv * K[i];
     P[i] = pv;
   };
   t = 0;
-  for (int c = b; c < nchunks; c += G) {
+  for (int c = b + kStepEndPre * G; c < nchunks; c += G) {
     while (t + 1 < r.ndesc && c >= r.chunk_begin[t + 1]) ++t;
     const ReduceDesc d = r.d[t];
     if (a.p[t] == nullptr) continue;
     if (d.vec) {
       const int e4 = (c - r.chunk_begin[t]) * 1024 + tid * 4;
-      if (e4 < d.n) {
+      if (worker && e4 < d.n) {
         const float4 g = *reinterpret_cast<const float4*>(d.dst + e4);
         adam1(a.p[t], a.m[t], a.v[t], a.mask[t], e4 + 0, g.x);
         adam1(a.p[t], a.m[t], a.v[t], a.mask[t], e4 + 1, g.y);

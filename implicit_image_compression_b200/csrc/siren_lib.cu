@@ -1852,7 +1852,7 @@ int sirenb200_fit_step(sirenb200_handle_t h, const float* img, const sirenb200_f
   }
   {
     ProfScope ps(h, PK_REDUCE, st);
-    step_end_kernel<<<grid, 256, 0, st>>>(a);
+    step_end_kernel<<<grid, kStepEndThreads, 0, st>>>(a);
   }
   LAUNCH_CHECK();
   return 0;
