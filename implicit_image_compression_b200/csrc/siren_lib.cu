@@ -274,7 +274,7 @@ int launch_rowgemm(sirenb200_plan* p, const CUtensorMap& tmA, const CUtensorMap&
   ra.stall = p->dbg_stall ? p->dbg_stall + int64_t(p->stall_slot % kStallLaunches) * 160 * 16 : nullptr;
   {
     ProfScope ps(p, MODE == MODE_FWD ? PK_FWD_GEMM : PK_DX_GEMM, st);
-    launch_ex(kfn, dim3(grid), dim3(rowgemm_threads(MODE, GEN, RED)), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, tmA,
+    launch_ex(kfn, dim3(grid), dim3(rowgemm_threads(MODE, GEN, RED, Cfg::STREAM_B)), Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, tmA,
               tmB, tmE, tmO, ra, idesc);
   }
   LAUNCH_CHECK();
@@ -403,6 +403,7 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     ra.valid_rows = int(ch.npix);
     ra.omega = omega_of(p, l);
     ra.bias = p->bias_raw + size_t(l - 1) * W;  // staged (zero-padded) copy of prm[2 * l + 1]
+    ra.bias_w = p->bias_w + size_t(l - 1) * W;  // omega * bias (the streamed-B kernel reads it through L1)
     ra.b_early = (l >= 2) ? 1 : 0;  // layer 1 follows the weight-staging kernel directly
     p->stall_slot = l;
     int rc;
@@ -538,6 +539,27 @@ int tc_last_chunk(sirenb200_plan* p, const float* const* prm, int mode, const fl
   return 0;
 }
 
+// hidden 512: the weight-gradient reduction of all hidden layers on CTA pairs (2-CTA clusters), one launch
+template <int W>
+int launch_colgemm2(sirenb200_plan* p, const ColGemmJobs& jobs, cudaStream_t st) {
+  auto kfn = colgemm2_kernel<W>;
+  static bool attr_set[64] = {};
+  if (!attr_set[p->device & 63]) {
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ColGemm2Cfg::SMEM_BYTES)));
+    attr_set[p->device & 63] = true;
+  }
+  const int grid = jobs.num_problems * (W / 256) * (W / 256) * jobs.splits * 2;
+  {
+    ProfScope ps(p, PK_DW_GEMM, st);
+    ColGemmJobs cj = jobs;
+    cj.stall = p->dbg_stall ? p->dbg_stall + int64_t(11 % kStallLaunches) * 160 * 16 : nullptr;  // slot 11
+    CUDA_TRY(launch_pairs(kfn, dim3(grid), dim3(256), ColGemm2Cfg::SMEM_BYTES, st, p->pdl && !p->prof_on, p->tm_dz_c,
+                          p->tm_act_c2, cj));
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
 // one backward layer: dX GEMM of layer l (CTAs [0, dx)) + its weight-gradient reduction (the rest), one launch
 template <int W, bool RED>
 int launch_bwd_merged(sirenb200_plan* p, const RowGemmArgs& ra, const ColGemmJobs& jobs, int l, cudaStream_t st) {
@@ -663,8 +685,14 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
   // hidden-layer weight / bias gradients: one split-K launch over all layers
   if (nh > 0 && !merged) {
     ColGemmJobs jobs{};
-    fill_jobs(jobs, 1, nh, p->col_splits, 0);
-    int rc = launch_colgemm<W>(p, jobs, st);
+    static const int col_interleave = getenv("SIRENB200_COL_INTERLEAVE") ? atoi(getenv("SIRENB200_COL_INTERLEAVE")) : 0;
+    fill_jobs(jobs, 1, nh, p->col_splits, col_interleave);
+    int rc;
+    if constexpr (W == 512) {
+      rc = p->bwd_pair ? launch_colgemm2<W>(p, jobs, st) : launch_colgemm<W>(p, jobs, st);
+    } else {
+      rc = launch_colgemm<W>(p, jobs, st);
+    }
     if (rc) return rc;
   }
   if (!fuse_l0) {

@@ -187,11 +187,26 @@ struct RowGemmCfg {
 #define SB_DX_SEO 3
 #endif
   static constexpr bool DX_RING = !RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072;
+  // streamed-B forward (hidden 512): the MMA issuer waited for operands 38 % of the time with three 48 KiB stages
+  // (one k-block = 512 cycles of MMA against ~2 k cycles of load latency); the bias table moves out of shared memory
+  // (read through L1 instead) to make room for a fourth
+#ifndef SB_WIDE_FWD_SA
+#define SB_WIDE_FWD_SA 4
+#endif
+  static constexpr bool WIDE_FWD = MODE == MODE_FWD && KDIM * NDIM * 2 > 131072;
+#ifndef SB_WIDE_DX_SA
+#define SB_WIDE_DX_SA 3
+#define SB_WIDE_DX_SEO 3
+#endif
+  static constexpr bool WIDE_DX = MODE == MODE_DX && KDIM * NDIM * 2 > 131072;
   static constexpr int SA = RED_RING ? SB_RED_SA
                             : DX_RING ? SB_DX_SA
-                                      : (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
+                                      : WIDE_FWD ? SB_WIDE_FWD_SA
+                                      : WIDE_DX ? SB_WIDE_DX_SA
+                                                 : (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
   static constexpr int SEO = RED_RING ? SB_RED_SEO
                              : DX_RING ? SB_DX_SEO
+                             : WIDE_DX ? SB_WIDE_DX_SEO
                                        : (MODE == MODE_DX) ? 3 : ((KDIM * NDIM * 2 <= 131072) ? SB_FWD_SEO : 2);  // epilogue in/out ring depth
   static constexpr uint32_t B_KB_BYTES = NDIM * 128;
   static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u);
@@ -200,7 +215,7 @@ struct RowGemmCfg {
   static constexpr uint32_t OFF_A = OFF_B + (STREAM_B ? 0u : KB * B_KB_BYTES);
   static constexpr uint32_t OFF_EO = OFF_A + SA * A_STAGE;
   static constexpr uint32_t OFF_CONST = OFF_EO + SEO * kChunkBytes;
-  static constexpr uint32_t CONST_BYTES = (MODE == MODE_FWD) ? NDIM * NPARTS * 4 : 0;
+  static constexpr uint32_t CONST_BYTES = (MODE == MODE_FWD && !(WIDE_FWD && SA > 3)) ? NDIM * NPARTS * 4 : 0;
   static constexpr uint32_t OFF_BAR = OFF_CONST + CONST_BYTES;
   static constexpr int NUM_BARS = 2 * SA + 1 + 3 * SEO + 4 + 4;
   static constexpr uint32_t SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024;  // + align slack
@@ -216,6 +231,7 @@ struct RowGemmArgs {
   int valid_rows;     // rows >= valid_rows (relative to the launch) are written as zero (MODE_DX)
   float omega;        // MODE_FWD: sine frequency
   const float* bias;  // MODE_FWD: fp32 bias[NDIM]
+  const float* bias_w;  // MODE_FWD, streamed B: omega * bias (device table, 16-byte aligned), read through L1
   // GEN (first hidden layer): the A operand is not loaded but GENERATED — layer 0 of the network,
   // a0 = sin(w0 (W0 x + b0)) from in-kernel coordinates (siren.py:62,66 with is_first) — by four extra
   // warps straight into the A ring, and stored to the activation stash from there.
@@ -254,11 +270,16 @@ struct RowGemmArgs {
 #define SB_RED_EPW 16
 #endif
 constexpr int kRedWarpsPerChunk = SB_RED_RW;
-__host__ __device__ constexpr int rowgemm_epi_warps(int mode, bool gen, bool red) {
-  return (mode == MODE_DX && !gen) ? (red ? SB_RED_EPW : SB_DX_EPW) : 8;
+// `wide`: the streamed-B configuration (hidden 512).  Its forward GEMM is not HBM-bound like hidden 256's: two sin
+// epilogues per 128-pixel tile against 8 k cycles of MMA - but 16 epilogue warps measured no faster than 8 there
+#ifndef SB_FWD_WIDE_EPW
+#define SB_FWD_WIDE_EPW 8
+#endif
+__host__ __device__ constexpr int rowgemm_epi_warps(int mode, bool gen, bool red, bool wide = false) {
+  return (mode == MODE_DX && !gen) ? (red ? SB_RED_EPW : SB_DX_EPW) : ((wide && !gen) ? SB_FWD_WIDE_EPW : 8);
 }
-__host__ __device__ constexpr int rowgemm_threads(int mode, bool gen, bool red) {
-  return gen ? 576 : 32 * (4 + rowgemm_epi_warps(mode, gen, red) + (red ? 4 * SB_RED_RW : 0));
+__host__ __device__ constexpr int rowgemm_threads(int mode, bool gen, bool red, bool wide = false) {
+  return gen ? 576 : 32 * (4 + rowgemm_epi_warps(mode, gen, red, wide) + (red ? 4 * SB_RED_RW : 0));
 }
 
 template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
@@ -276,7 +297,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
   // epilogue warps: 8 (two per TMEM lane quadrant, 32 of a chunk's 64 columns each), or 16 for the plain dX GEMM
   // (four per quadrant, 16 columns each): its cvt -> FFMA -> MUFU.SQRT -> FMUL -> F2FP chains need more than two
   // warps per scheduler to hide their latency (stall accounting: the 8-warp epilogue was busy 5.1 k cycles per tile)
-  constexpr int EPW = rowgemm_epi_warps(MODE, GEN, RED);
+  constexpr int EPW = rowgemm_epi_warps(MODE, GEN, RED, C::STREAM_B);
   constexpr int CPW = 64 / (EPW / 4);
   const int num_items = args.num_tiles * NPARTS;  // item = (tile, output part)
   extern __shared__ uint8_t smem_raw[];
@@ -335,7 +356,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
-  if (MODE == MODE_FWD && warp >= 4) {
+  if (MODE == MODE_FWD && C::CONST_BYTES > 0 && warp >= 4) {
     float* cst = reinterpret_cast<float*>(smem + C::OFF_CONST);
     for (int i = threadIdx.x - 128; i < NDIM * NPARTS; i += 32 * EPW) cst[i] = args.omega * args.bias[i];
   }
@@ -656,13 +677,24 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
             SB_WAIT_TIMED(args.stall, st_eo, mbar_wait(&eo_empty[s], ph ^ 1u));
           uint32_t o[CPW / 2];
           if (MODE == MODE_FWD) {
+            const int col0 = part * NDIM + nb * 64 + hb * CPW;
+            float4 bw[CPW / 4];
+            if constexpr (C::CONST_BYTES == 0) {
+#pragma unroll
+              for (int j = 0; j < CPW / 4; ++j) bw[j] = __ldg(reinterpret_cast<const float4*>(args.bias_w + col0) + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CPW / 4; ++j) bw[j] = *reinterpret_cast<const float4*>(cst + col0 + 4 * j);
+            }
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < CPW / 2; ++j) {
-              const int col = part * NDIM + nb * 64 + hb * CPW + 2 * j;
-              const float t0 = fmaf(__uint_as_float(v[2 * j]), args.omega, cst[col]);
-              const float t1 = fmaf(__uint_as_float(v[2 * j + 1]), args.omega, cst[col + 1]);
-              o[j] = sine_signed_half2(t0, t1);
+            for (int j = 0; j < CPW / 4; ++j) {
+              const float t0 = fmaf(__uint_as_float(v[4 * j]), args.omega, bw[j].x);
+              const float t1 = fmaf(__uint_as_float(v[4 * j + 1]), args.omega, bw[j].y);
+              const float t2 = fmaf(__uint_as_float(v[4 * j + 2]), args.omega, bw[j].z);
+              const float t3 = fmaf(__uint_as_float(v[4 * j + 3]), args.omega, bw[j].w);
+              o[2 * j] = sine_signed_half2(t0, t1);
+              o[2 * j + 1] = sine_signed_half2(t2, t3);
             }
           } else {
             uint32_t e[CPW / 2];
@@ -753,7 +785,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
 }
 
 template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN = false, bool RED = false>
-__global__ void __launch_bounds__(rowgemm_threads(MODE, GEN, RED), 1)
+__global__ void __launch_bounds__(rowgemm_threads(MODE, GEN, RED, RowGemmCfg<KDIM, NDIM, MODE, NPARTS, RED>::STREAM_B), 1)
 rowgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmO,
                const RowGemmArgs args, const uint32_t idesc) {
@@ -995,10 +1027,17 @@ struct ColGemm2Cfg {
   static constexpr uint32_t TMEM_COLS = 512;  // 256 (dW rows of this CTA) + 16 (db), power of two
 };
 
+// W = 256: one pair per pixel split.  W = 512: dW is four 256 x 256 blocks (feature half fp x column half ch), one pair
+// each, so a pixel split is 8 CTAs as with single CTAs - but every CTA loads 64 KiB per 128-pixel stage instead of 96
+// (its 128 dz features + 128 of the block's activation columns) and issues twice the MMA work per loaded byte.
+// job = (((problem * FP + fp) * CH + ch) * splits + split) * 2 + CTA rank.
+template <int W>
 __device__ __forceinline__ void
 colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& jobs, const int job,
               const PaceCtx pace) {
+  static_assert(W == 256 || W == 512, "CTA-pair reduction: hidden 256 or 512");
   using C = ColGemm2Cfg;
+  constexpr int FP = W / 256, CH = W / 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
@@ -1011,10 +1050,25 @@ colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs&
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // == job & 1: which 128 dz features / which half of the columns
   const bool leader = rank == 0;
-  const int split = job >> 1;
-  const int tile_begin = split, tile_step = jobs.splits;
-  const int ntiles = split < jobs.tiles_total ? (jobs.tiles_total - split + jobs.splits - 1) / jobs.splits : 0;
-  const int prob = 0;
+  int jd = job >> 1;
+  const int split = jd % jobs.splits;
+  jd /= jobs.splits;
+  const int ch = jd % CH;
+  jd /= CH;
+  const int fp = jd % FP;
+  const int prob = jd / FP;
+  int tile_begin, tile_step, ntiles;
+  if (jobs.interleave) {
+    tile_begin = split;
+    tile_step = jobs.splits;
+    ntiles = split < jobs.tiles_total ? (jobs.tiles_total - split + jobs.splits - 1) / jobs.splits : 0;
+  } else {
+    tile_begin = split * jobs.tiles_per_split;
+    tile_step = 1;
+    int tile_end = tile_begin + jobs.tiles_per_split;
+    if (tile_end > jobs.tiles_total) tile_end = jobs.tiles_total;
+    ntiles = tile_end > tile_begin ? tile_end - tile_begin : 0;
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
@@ -1056,8 +1110,9 @@ colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs&
         SB_WAIT_TIMED(jobs.stall, st_empty, mbar_wait(&empty[s], ph ^ 1u));
         if (leader) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
         uint8_t* st = smem + s * C::STAGE_BYTES;
-        tma_load_3d_2sm(st, &tmX, &full[s], 0, jobs.x_row0[prob] + prow, int(rank) * C::XC);
-        tma_load_3d_2sm(st + C::XC * kChunkBytes, &tmY, &full[s], 0, jobs.y_row0[prob] + prow, int(rank) * C::YC);
+        tma_load_3d_2sm(st, &tmX, &full[s], 0, jobs.x_row0[prob] + prow, (fp * 2 + int(rank)) * C::XC);
+        tma_load_3d_2sm(st + C::XC * kChunkBytes, &tmY, &full[s], 0, jobs.y_row0[prob] + prow,
+                        (ch * 2 + int(rank)) * C::YC);
       }
       if (jobs.stall) {
         jobs.stall[job * 16 + 0] = st_pace;
@@ -1084,7 +1139,7 @@ colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs&
           const uint64_t dy = umma_smem_desc(y_addr + k * 2048, kChunkBytes, 1024, 2);
           const uint32_t accum = (i | k) != 0 ? 1u : 0u;
           umma_f16_2sm(tmem_base, dx, dy, idesc_main, accum);
-          umma_f16_2sm(tmem_base + 256, dx, d_ones, idesc_ones, accum);
+          if (ch == 0) umma_f16_2sm(tmem_base + 256, dx, d_ones, idesc_ones, accum);  // db: once per feature half
         }
         umma_commit_2sm(&empty[s]);
       }
@@ -1096,9 +1151,9 @@ colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs&
     }
   } else if (warp >= 4 && warp < 8) {
     const int q = warp & 3;
-    const int m = int(rank) * 128 + q * 32 + lane;  // dW row (dz feature) of this thread
+    const int m = fp * 256 + int(rank) * 128 + q * 32 + lane;  // dW row (dz feature) of this thread
     const size_t slab = size_t(split) * jobs.prob_total + jobs.prob0 + prob;
-    float* dw = jobs.dw_partial + (slab * jobs.nx + m) * size_t(jobs.ny_total);
+    float* dw = jobs.dw_partial + (slab * jobs.nx + m) * size_t(jobs.ny_total) + ch * 256;
     float* dbp = jobs.db_partial + slab * jobs.nx + m;
     if (ntiles > 0) {
       mbar_wait(done, 0);
@@ -1122,13 +1177,15 @@ colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs&
           *dst = o;
         }
       }
-      uint32_t b8[8];
-      tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + 256, b8);
-      tmem_ld_wait();
-      *dbp = __uint_as_float(b8[0]) + (jobs.accumulate ? *dbp : 0.f);
+      if (ch == 0) {  // the bias gradient does not depend on the column half
+        uint32_t b8[8];
+        tmem_ld_32x8(tmem_base + (uint32_t(q * 32) << 16) + 256, b8);
+        tmem_ld_wait();
+        *dbp = __uint_as_float(b8[0]) + (jobs.accumulate ? *dbp : 0.f);
+      }
     } else if (!jobs.accumulate) {
       for (int j = 0; j < 256 / 4; ++j) reinterpret_cast<uint4*>(dw)[j] = make_uint4(0, 0, 0, 0);
-      *dbp = 0.0f;
+      if (ch == 0) *dbp = 0.0f;
     }
   }
 
@@ -1146,6 +1203,14 @@ __global__ void __launch_bounds__(256, 1)
 colgemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                const ColGemmJobs jobs, const uint32_t idesc_main, const uint32_t idesc_ones) {
   colgemm_body<NY>(tmX, tmY, jobs, idesc_main, idesc_ones, int(blockIdx.x), PaceCtx{});
+}
+
+// stand-alone launch of the pair reduction (2-CTA clusters): all hidden layers' weight gradients of hidden 512
+template <int W>
+__global__ void __launch_bounds__(256, 1)
+colgemm2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                const ColGemmJobs jobs) {
+  colgemm2_body<W>(tmX, tmY, jobs, int(blockIdx.x), PaceCtx{});
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1175,7 +1240,7 @@ bwd_merged_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constan
     // (tmDzR / tmActR: the reduction role's views of dz / act: one box per operand and stage)
     if constexpr (PAIR) {
       static_assert(!PAIR || W == 256, "CTA-pair reduction: hidden 256");
-      colgemm2_body(tmDzR, tmActR, jobs, int(blockIdx.x) - dx_ctas, pc);
+      colgemm2_body<W>(tmDzR, tmActR, jobs, int(blockIdx.x) - dx_ctas, pc);
     } else {
       colgemm_body<NT>(tmDzR, tmActR, jobs, idesc_main, idesc_ones, int(blockIdx.x) - dx_ctas, pc);
     }
