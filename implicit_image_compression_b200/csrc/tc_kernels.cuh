@@ -182,11 +182,17 @@ struct RowGemmCfg {
 #define SB_RED_SEO 4
 #endif
   static constexpr bool RED_RING = RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072;
+  // SB_DX_STREAM (experiment): the plain dX GEMM of hidden <= 256 streams its B k-blocks from L2 like hidden 512
+  // does instead of keeping the 128 KiB operand resident, which buys two more in-place staging slots
+#ifndef SB_DX_STREAM
+#define SB_DX_STREAM 0
+#endif
+  static constexpr bool DX_STREAMED = SB_DX_STREAM && !RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072;
 #ifndef SB_DX_SA
 #define SB_DX_SA 3
 #define SB_DX_SEO 3
 #endif
-  static constexpr bool DX_RING = !RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072;
+  static constexpr bool DX_RING = !RED && MODE == MODE_DX && KDIM * NDIM * 2 <= 131072 && !DX_STREAMED;
   // streamed-B forward (hidden 512): the MMA issuer waited for operands 38 % of the time with three 48 KiB stages
   // (one k-block = 512 cycles of MMA against ~2 k cycles of load latency); the bias table moves out of shared memory
   // (read through L1 instead) to make room for a fourth
@@ -202,14 +208,16 @@ struct RowGemmCfg {
   static constexpr int SA = RED_RING ? SB_RED_SA
                             : DX_RING ? SB_DX_SA
                                       : WIDE_FWD ? SB_WIDE_FWD_SA
+                                      : DX_STREAMED ? 3
                                       : WIDE_DX ? SB_WIDE_DX_SA
                                                  : (MODE == MODE_FWD && KDIM * NDIM * 2 <= 131072) ? SB_FWD_SA : 3;
   static constexpr int SEO = RED_RING ? SB_RED_SEO
                              : DX_RING ? SB_DX_SEO
+                             : DX_STREAMED ? 5
                              : WIDE_DX ? SB_WIDE_DX_SEO
                                        : (MODE == MODE_DX) ? 3 : ((KDIM * NDIM * 2 <= 131072) ? SB_FWD_SEO : 2);  // epilogue in/out ring depth
   static constexpr uint32_t B_KB_BYTES = NDIM * 128;
-  static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u);
+  static constexpr bool STREAM_B = (uint32_t(KB) * B_KB_BYTES > 131072u) || DX_STREAMED;
   static constexpr uint32_t A_STAGE = kChunkBytes + (STREAM_B ? B_KB_BYTES : 0u);
   static constexpr uint32_t OFF_B = 0;
   static constexpr uint32_t OFF_A = OFF_B + (STREAM_B ? 0u : KB * B_KB_BYTES);
@@ -235,9 +243,9 @@ struct RowGemmArgs {
   // GEN (first hidden layer): the A operand is not loaded but GENERATED — layer 0 of the network,
   // a0 = sin(w0 (W0 x + b0)) from in-kernel coordinates (siren.py:62,66 with is_first) — by four extra
   // warps straight into the A ring, and stored to the activation stash from there.
-  // RED (dX of the first hidden layer): four extra warps read every finished dz[0] chunk back from the
+  // RED (dX of the first hidden layer): extra warps (SB_RED_RW per 64-column chunk) read every finished dz[0] chunk back from the
   // staging buffer and accumulate layer 0's weight / bias gradient (dW0 = dz0^T x, db0 = sum dz0; autograd of
-  // siren.py:62 for the is_first layer), so dz[0] is never re-read from HBM.  red_part: [2 * gridDim.x][3 * hidden]
+  // siren.py:62 for the is_first layer), so dz[0] is never re-read from HBM.  red_part: [kRedWarpsPerChunk * gridDim.x][3 * hidden]
   // = per-CTA partials {dW0 [NDIM, 2], db0 [NDIM]}.
   float* red_part;
   CoordSrc gen_coord;   // GEN and RED: coordinates of this launch's pixels
@@ -287,7 +295,8 @@ template <int KDIM, int NDIM, int MODE, bool OUT_BF16, int NPARTS = 1, bool GEN 
 // 4..4+EPW-1 = epilogue (EPW / 4 warps per TMEM lane quadrant; each takes 64 / (EPW / 4) of the 64 columns of
 // every output chunk; EPW = 16 for the dX GEMMs, 8 otherwise);
 // GEN: warps 0, 2, 3 and 12..16 = A-operand generators (network layer 0), two per 64-wide k-block; the
-// weight load moves to warp 1 and the store warp is warp 17;  RED: 8 more warps = layer-0 gradient reducers.
+// weight load moves to warp 1 and the store warp is warp 17;  RED: 4 * SB_RED_RW more warps = layer-0 gradient
+// reducers (SB_RED_RW per 64-column chunk).
 // `cta` / `ncta`: index of this CTA among the CTAs of the role and their number (== cta / ncta when the
 // whole grid runs this body).
 __device__ __forceinline__ void
@@ -339,7 +348,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     mbar_init(b_full, 1);
     for (int i = 0; i < C::SEO; ++i) {
       mbar_init(&eo_full[i], 1);
-      mbar_init(&eo_empty[i], RED ? 1 + kRedWarpsPerChunk : 1);  // RED: the store has read the chunk AND both reducer warps have
+      mbar_init(&eo_empty[i], RED ? 1 + kRedWarpsPerChunk : 1);  // RED: the store has read the chunk AND its reducer warps have
     }
     for (int i = 0; i < 4; ++i) mbar_init(&red_full[i], 1);
     for (int i = 0; i < 2; ++i) {
