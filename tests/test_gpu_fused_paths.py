@@ -57,6 +57,25 @@ def test_merged_backward_matches_separate_kernels(monkeypatch, hidden, depth, H,
         assert torch.equal(a, b)  # deterministic
 
 
+@pytest.mark.parametrize("depth,H,W", [(4, 64, 96), (8, 128, 160), (3, 37, 53)])
+def test_hidden512_pair_reduction_matches_single_cta_reduction(monkeypatch, depth, H, W):
+    """colgemm2_kernel<512> (the weight-gradient reduction of hidden 512 on CTA pairs: cta_group::2 MMAs over the four
+    256 x 256 blocks of dW) against colgemm_kernel (single CTAs, 128-row blocks x two column parts): the same products
+    on the same fp16 operands with the same pixel splits; the MMA shape (accumulation order inside the tensor core)
+    is the only difference."""
+    get_grid, synth_image, _, Siren, _ = _pkg()
+    monkeypatch.setenv("SIRENB200_PAIR", "1")
+    s1, g1 = _grads(Siren, get_grid, synth_image, 512, depth, H, W)
+    s1b, g1b = _grads(Siren, get_grid, synth_image, 512, depth, H, W)
+    monkeypatch.setenv("SIRENB200_PAIR", "0")
+    s0, g0 = _grads(Siren, get_grid, synth_image, 512, depth, H, W)
+    assert s1[0] == s0[0] and s1[2] == 0.0
+    for i, (a, b) in enumerate(zip(g1, g0)):
+        assert _rel(a, b) <= 5e-5, f"tensor {i}: {_rel(a, b):.3e}"
+    for a, b in zip(g1, g1b):
+        assert torch.equal(a, b)  # deterministic
+
+
 @pytest.mark.parametrize("with_mask", [False, True])
 def test_step_end_kernel_matches_separate_kernels(monkeypatch, with_mask):
     get_grid, synth_image, Fitter, Siren, th = _pkg()
