@@ -106,6 +106,11 @@ struct sirenb200_plan {
   bool last_tc = false;
   bool tail_fused = true;   // last hidden GEMM + output layer + loss + dZ in one kernel (SIRENB200_TAIL=0: two kernels)
   bool pdl = true;          // programmatic dependent launch of the GEMM kernels (SIRENB200_PDL=0: off)
+  int alt_sweep = 7;        // consecutive launches sweep the tiles in alternating directions, so each starts with what
+                            // its predecessor wrote last (still in L2); SIRENB200_ALT_SWEEP bits: 1 forward GEMMs,
+                            // 2 tail kernel, 4 merged backward launches
+  bool tail_ran = false;    // the last forward pass ended with the tail kernel ...
+  int tail_rev = 0;         // ... sweeping in this direction (1 = back to front)
   bool fuse_l0 = true;      // layer-0 gradient reduced inside the dX GEMM of the first hidden layer (SIRENB200_FUSE_L0=0: own kernel)
   int l0_used = 0;          // partial rows of l0_part written by the last backward
   int last_rowgemm_grid = 0;
@@ -404,6 +409,8 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     ra.omega = omega_of(p, l);
     ra.bias = p->bias_raw + size_t(l - 1) * W;  // staged (zero-padded) copy of prm[2 * l + 1]
     ra.bias_w = p->bias_w + size_t(l - 1) * W;  // omega * bias (the streamed-B kernel reads it through L1)
+    // layer 1 sweeps front to back (its input is generated / freshly written front to back), layer 2 back to front, ...
+    ra.reverse = ((p->alt_sweep & 1) && p->nchunks == 1 && (l % 2 == 0)) ? 1 : 0;
     ra.b_early = (l >= 2) ? 1 : 0;  // layer 1 follows the weight-staging kernel directly
     p->stall_slot = l;
     int rc;
@@ -486,6 +493,8 @@ int launch_tail(sirenb200_plan* p, const float* const* prm, const float* img, fl
     ta.npix = ch.npix;
     ta.omega = omega_of(p, nh);
     ta.bias = p->bias_raw + size_t(nh - 1) * W;
+    ta.reverse = ((p->alt_sweep & 2) && p->nchunks == 1 && (nh % 2 == 0)) ? 1 : 0;  // layer nh: as the forward GEMMs alternate
+    p->tail_rev = ta.reverse;
     ta.b_last = prm[2 * (D - 1) + 1];
     ta.img = img + ch.p0 * C;
     ta.pred = pred ? pred + ch.p0 * C : nullptr;
@@ -656,6 +665,9 @@ int tc_backward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& c
       ColGemmJobs jobs{};
       const bool own_split = l == 1 && fuse_l0 && p->merged_splits_l0 > 0;
       fill_jobs(jobs, l, 1, own_split ? p->merged_splits_l0 : p->active_splits, 1);
+      // the tail kernel wrote dz[nh] in direction tail_rev: layer nh's launch sweeps the other way, layer nh - 1's
+      // back again, ... (both roles of a launch sweep the same way: the pace hint counts sweep positions)
+      if ((p->alt_sweep & 4) && p->tail_ran) ra.reverse = jobs.reverse = p->tail_rev ^ (((nh - l) % 2 == 0) ? 1 : 0);
       if (l == 1) p->l1_splits = jobs.splits;
       if (l == 1 && fuse_l0) {
         ra.gen_coord = p->coord;
@@ -783,6 +795,7 @@ int tc_run(sirenb200_plan* p, const float* const* prm, int mode, const float* im
     // training step with at least two hidden GEMM layers: the last one is fused with the output layer
     const bool tail = W <= 256 && mode == 1 && p->tail_fused && p->last_tc && p->D - 2 >= 2 && p->nchunks == 1 &&
                       img_or_dpred;
+    p->tail_ran = tail;
     if (mode != 2) rc = tc_forward_chunk<W>(p, prm, ch, st, tail);
     if (!rc) rc = tail ? launch_tail<W>(p, prm, img_or_dpred, pred, ch, st)
                        : tc_last_chunk<W>(p, prm, mode, img_or_dpred, pred, ch, st);
@@ -1210,6 +1223,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->tail_fused = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_PDL");
       p->pdl = !(env && atoi(env) == 0);
+      env = getenv("SIRENB200_ALT_SWEEP");
+      if (env) p->alt_sweep = atoi(env);
       env = getenv("SIRENB200_FUSE_L0");
       p->fuse_l0 = !(env && atoi(env) == 0);
     }

@@ -237,6 +237,10 @@ struct RowGemmArgs {
   int e_row0;         // ... inside the epilogue-input tensor map (MODE_DX)
   int o_row0;         // ... inside the output tensor map
   int valid_rows;     // rows >= valid_rows (relative to the launch) are written as zero (MODE_DX)
+  // 1: the CTAs sweep the tiles back to front (work item i = tile num_tiles - 1 - i).  Consecutive launches alternate
+  // the direction, so a launch starts with the tiles its predecessor wrote LAST - the part of a 201 MB tensor that is
+  // still in the 126 MB L2
+  int reverse;
   float omega;        // MODE_FWD: sine frequency
   const float* bias;  // MODE_FWD: fp32 bias[NDIM]
   const float* bias_w;  // MODE_FWD, streamed B: omega * bias (device table, 16-byte aligned), read through L1
@@ -490,9 +494,10 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       int pace_seen = 0;
       const long long st_begin = args.stall ? clock64() : 0;
       for (int it = cta; !GEN && it < num_items; it += ncta) {
-        const int t = it / NPARTS, part = it % NPARTS;
+        const int tl = it / NPARTS, part = it % NPARTS;  // tl: position in the sweep (what the pace hint counts)
+        const int t = args.reverse ? args.num_tiles - 1 - tl : tl;
         const int row = args.a_row0 + t * kRowsPerTile;
-        SB_WAIT_TIMED(args.stall, st_pace, pace_wait(pace, t, pace_seen));
+        SB_WAIT_TIMED(args.stall, st_pace, pace_wait(pace, tl, pace_seen));
         pace_post(pace);
         for (int kb = 0; kb < C::KB; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
@@ -556,7 +561,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       uint32_t ic = 0;
       long long st_eoempty = 0;
       for (int item = cta; item < num_items; item += ncta) {
-        const int t = item / NPARTS, part = item % NPARTS;
+        const int t = args.reverse ? args.num_tiles - 1 - item / NPARTS : item / NPARTS, part = item % NPARTS;
         const int row = args.e_row0 + t * kRowsPerTile;
         for (int nb = 0; nb < C::NB; ++nb, ++ic) {
           const uint32_t s = ic % C::SEO, ph = (ic / C::SEO) & 1u;
@@ -590,7 +595,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       // cannot alias (a barrier shared between the chunk indices could be probed more than one phase ahead)
       uint32_t ic = uint32_t(nb), il = 0;
       for (int item = cta; item < num_items; item += ncta, ic += C::NB, ++il) {
-        const int t = item / NPARTS, part = item % NPARTS;
+        const int t = args.reverse ? args.num_tiles - 1 - item / NPARTS : item / NPARTS, part = item % NPARTS;
         // coordinates of rows row_lo + lane + 32 q (zero for the padding rows: their dz is zero anyway)
         float xh[QN], xw[QN];
 #pragma unroll
@@ -661,7 +666,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
     long long st_tmfull = 0, st_eo = 0;
     const long long st_begin = args.stall ? clock64() : 0;
     for (int item = cta; item < num_items; item += ncta, ++it) {
-      const int t = item / NPARTS, part = item % NPARTS;
+      const int t = args.reverse ? args.num_tiles - 1 - item / NPARTS : item / NPARTS, part = item % NPARTS;
       const uint32_t acc = it & 1u, aph = (it >> 1) & 1u;
       if (issuer) SB_DBG_G(5, it, 0);
       SB_WAIT_TIMED(args.stall, st_tmfull, mbar_wait(&tm_full[acc], aph));
@@ -751,7 +756,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       uint32_t ic = 0;
       long long st_ready = 0, st_rd = 0;
       for (int item = cta; item < num_items; item += ncta) {
-        const int t = item / NPARTS, part = item % NPARTS;
+        const int t = args.reverse ? args.num_tiles - 1 - item / NPARTS : item / NPARTS, part = item % NPARTS;
         for (int nb = 0; nb < C::NB; ++nb, ++ic) {
           const uint32_t s = ic % C::SEO, ph = (ic / C::SEO) & 1u;
           SB_WAIT_TIMED(args.stall, st_ready, mbar_wait(&o_ready[s], ph));
@@ -849,6 +854,7 @@ struct ColGemmJobs {
   int interleave;       // 1: split s visits tiles s, s+splits, ... (sweeps the image front to back,
                         //    in step with a concurrently running rowgemm); 0: contiguous tile ranges
   long long* stall;     // SIRENB200_STALLS (debug): stall[job * 16 + k]
+  int reverse;          // 1: sweep position x = tile tiles_total - 1 - x (see RowGemmArgs::reverse)
 };
 
 template <int NY>
@@ -921,7 +927,8 @@ colgemm_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs& 
       for (int ii = 0; ii < ntiles * C::SUB; ++ii) {
         const int i = ii / C::SUB, sub = ii % C::SUB;
         const uint32_t s = ii % C::STAGES, ph = (ii / C::STAGES) & 1u;
-        const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile + sub * PXS;
+        const int tpos = tile_begin + i * tile_step;
+        const int prow = (jobs.tile0 + (jobs.reverse ? jobs.tiles_total - 1 - tpos : tpos)) * kRowsPerTile + sub * PXS;
         if (sub == 0) {
           SB_WAIT_TIMED(jobs.stall, st_pace, pace_wait(pace, tile_begin + i * tile_step, pace_seen));
           pace_post(pace);
@@ -1113,7 +1120,8 @@ colgemm2_body(const CUtensorMap& tmX, const CUtensorMap& tmY, const ColGemmJobs&
       const long long st_begin = jobs.stall ? clock64() : 0;
       for (int i = 0; i < ntiles; ++i) {
         const uint32_t s = i % C::STAGES, ph = (i / C::STAGES) & 1u;
-        const int prow = (jobs.tile0 + tile_begin + i * tile_step) * kRowsPerTile;
+        const int tpos = tile_begin + i * tile_step;
+        const int prow = (jobs.tile0 + (jobs.reverse ? jobs.tiles_total - 1 - tpos : tpos)) * kRowsPerTile;
         SB_WAIT_TIMED(jobs.stall, st_pace, pace_wait(pace, tile_begin + i * tile_step, pace_seen));
         pace_post(pace);
         SB_WAIT_TIMED(jobs.stall, st_empty, mbar_wait(&empty[s], ph ^ 1u));
@@ -1665,6 +1673,7 @@ struct TailArgs {
   int outermost_linear;
   float omega_last;
   long long* dbg;        // optional timeline (block 0): dbg[tile * 16 + k], first 12 tiles
+  int reverse;           // 1: sweep the tiles back to front (see RowGemmArgs::reverse)
 };
 
 #define SB_DBG_T(tile_i, k)                                                 \
@@ -1805,7 +1814,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
           mbar_wait(&a_empty[s], ph ^ 1u);
           mbar_expect_tx(&a_full[s], kChunkBytes);
           tma_load_2d(smem + C::OFF_A + s * kChunkBytes, &tmAct, &a_full[s], kb * 64,
-                      args.a_row0 + t * kRowsPerTile);
+                      args.a_row0 + (args.reverse ? args.num_tiles - 1 - t : t) * kRowsPerTile);
         }
       }
     }
@@ -1942,7 +1951,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
           mbar_wait(&dz_done[half], it & 1u);
           for (int nbl = 0; nbl < C::CPH; ++nbl) {
             const int nb = half * C::CPH + nbl;
-            tma_store_2d(&tmDz, smem + C::OFF_T + nb * kChunkBytes, nb * 64, args.dz_row0 + t * kRowsPerTile);
+            tma_store_2d(&tmDz, smem + C::OFF_T + nb * kChunkBytes, nb * 64,
+                         args.dz_row0 + (args.reverse ? args.num_tiles - 1 - t : t) * kRowsPerTile);
           }
           tma_store_commit();
           SB_DBG_T(it, 6 + 2 * half);
@@ -1968,8 +1978,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
     for (int c = 0; c < kMaxOutTc; ++c) bias[c] = c < args.C ? args.b_last[c] : 0.f;
     float sse = 0.f, dbs[kMaxOutTc] = {};
     float tgt_next[kMaxOutTc] = {};
-    auto fetch_target = [&](int tile) {
-      const int64_t pn = int64_t(tile) * kRowsPerTile + r_in_tile;
+    auto fetch_target = [&](int tile) {  // tile: position in the sweep
+      const int64_t pn = int64_t(args.reverse ? args.num_tiles - 1 - tile : tile) * kRowsPerTile + r_in_tile;
 #pragma unroll
       for (int c = 0; c < kMaxOutTc; ++c)
         tgt_next[c] = (hb == 0 && tile < args.num_tiles && pn < args.npix && c < args.C) ? args.img[pn * args.C + c]
@@ -1978,7 +1988,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
     fetch_target(blockIdx.x);
     uint32_t it = 0;
     for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x, ++it) {
-      const int64_t p = int64_t(t) * kRowsPerTile + r_in_tile;
+      const int64_t p = int64_t(args.reverse ? args.num_tiles - 1 - t : t) * kRowsPerTile + r_in_tile;
       const bool row_valid = p < args.npix;
       float tgt[kMaxOutTc];
 #pragma unroll

@@ -438,6 +438,8 @@ def test_fused_kernel_variants_match_the_kernels_they_replace(monkeypatch, hidde
       tail kernel (last hidden GEMM + output layer + loss + dZ)  -> every gradient and the loss bit-identical
       layer 0 generated inside the first hidden GEMM              -> bit-identical (same arithmetic per element)
       layer-0 gradient reduced inside the first dX GEMM           -> dW0 / db0 differ by summation order only
+    (with one sweep direction for every launch: SIRENB200_ALT_SWEEP=0), and
+      launches sweeping the tiles in alternating directions       -> every reduction differs by summation order only
     """
     _, get_grid, synth_image, Siren, _ = _pkg()
     grid, img = get_grid(H, W, "cuda"), synth_image(H, W, 0, device="cuda")
@@ -445,6 +447,7 @@ def test_fused_kernel_variants_match_the_kernels_they_replace(monkeypatch, hidde
     def run(env):
         for k in ("SIRENB200_TAIL", "SIRENB200_GEN_FIRST", "SIRENB200_FUSE_L0", "SIRENB200_PDL"):
             monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv("SIRENB200_ALT_SWEEP", "0")
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         torch.manual_seed(0)
@@ -468,6 +471,10 @@ def test_fused_kernel_variants_match_the_kernels_they_replace(monkeypatch, hidde
                 assert torch.equal(a, b), (env, i)
             else:
                 assert _rel(a, b) <= 1e-5, (env, i, _rel(a, b))
+    g, s = run({"SIRENB200_ALT_SWEEP": "7"})
+    assert abs(s[1].item() - base_s[1].item()) <= 1e-6 * abs(base_s[1].item())
+    for i, (a, b) in enumerate(zip(g, base_g)):
+        assert _rel(a, b) <= 1e-5, ("alternating sweep", i, _rel(a, b))
 
 
 @pytest.mark.parametrize("n,seed", [(331_000, 0), (4097, 1), (31, 2), (65_536, 3)])
