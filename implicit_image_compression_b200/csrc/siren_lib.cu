@@ -109,6 +109,7 @@ struct sirenb200_plan {
   int alt_sweep = 7;        // consecutive launches sweep the tiles in alternating directions, so each starts with what
                             // its predecessor wrote last (still in L2); SIRENB200_ALT_SWEEP bits: 1 forward GEMMs,
                             // 2 tail kernel, 4 merged backward launches
+  int l2_hints = 0;         // forward GEMMs / tail kernel load their input with an L2 evict_first hint (SIRENB200_L2_HINTS)
   bool tail_ran = false;    // the last forward pass ended with the tail kernel ...
   int tail_rev = 0;         // ... sweeping in this direction (1 = back to front)
   bool fuse_l0 = true;      // layer-0 gradient reduced inside the dX GEMM of the first hidden layer (SIRENB200_FUSE_L0=0: own kernel)
@@ -411,6 +412,7 @@ int tc_forward_chunk(sirenb200_plan* p, const float* const* prm, const Chunk& ch
     ra.bias_w = p->bias_w + size_t(l - 1) * W;  // omega * bias (the streamed-B kernel reads it through L1)
     // layer 1 sweeps front to back (its input is generated / freshly written front to back), layer 2 back to front, ...
     ra.reverse = ((p->alt_sweep & 1) && p->nchunks == 1 && (l % 2 == 0)) ? 1 : 0;
+    ra.l2_hints = p->l2_hints;
     ra.b_early = (l >= 2) ? 1 : 0;  // layer 1 follows the weight-staging kernel directly
     p->stall_slot = l;
     int rc;
@@ -495,6 +497,7 @@ int launch_tail(sirenb200_plan* p, const float* const* prm, const float* img, fl
     ta.bias = p->bias_raw + size_t(nh - 1) * W;
     ta.reverse = ((p->alt_sweep & 2) && p->nchunks == 1 && (nh % 2 == 0)) ? 1 : 0;  // layer nh: as the forward GEMMs alternate
     p->tail_rev = ta.reverse;
+    ta.l2_hints = p->l2_hints;
     ta.b_last = prm[2 * (D - 1) + 1];
     ta.img = img + ch.p0 * C;
     ta.pred = pred ? pred + ch.p0 * C : nullptr;
@@ -1225,6 +1228,8 @@ int sirenb200_create(const sirenb200_config_t* cfg, sirenb200_handle_t* out) {
       p->pdl = !(env && atoi(env) == 0);
       env = getenv("SIRENB200_ALT_SWEEP");
       if (env) p->alt_sweep = atoi(env);
+      env = getenv("SIRENB200_L2_HINTS");
+      if (env) p->l2_hints = atoi(env);
       env = getenv("SIRENB200_FUSE_L0");
       p->fuse_l0 = !(env && atoi(env) == 0);
     }

@@ -241,6 +241,10 @@ struct RowGemmArgs {
   // the direction, so a launch starts with the tiles its predecessor wrote LAST - the part of a 201 MB tensor that is
   // still in the 126 MB L2
   int reverse;
+  // 1 (MODE_FWD): the A operand (the previous layer's activation: not read again before the backward pass) is loaded
+  // with an L2 evict_first hint, and so is the GEN variant's stash store of layer 0's activation, so that what stays
+  // in L2 is this launch's OUTPUT - the next launch's input, swept back to front
+  int l2_hints;
   float omega;        // MODE_FWD: sine frequency
   const float* bias;  // MODE_FWD: fp32 bias[NDIM]
   const float* bias_w;  // MODE_FWD, streamed B: omega * bias (device table, 16-byte aligned), read through L1
@@ -477,7 +481,11 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
         named_bar_sync(2 + kb, 64);
         if (issuer_g) {
           SB_DBG_G(kb, ig / C::KB, 3);
-          tma_store_2d(&tmA, smem + C::OFF_A + s * C::A_STAGE, kb * 64, args.a_row0 + t * kRowsPerTile);
+          if (args.l2_hints)
+            tma_store_2d_hint(&tmA, smem + C::OFF_A + s * C::A_STAGE, kb * 64, args.a_row0 + t * kRowsPerTile,
+                              l2_policy_evict_first());
+          else
+            tma_store_2d(&tmA, smem + C::OFF_A + s * C::A_STAGE, kb * 64, args.a_row0 + t * kRowsPerTile);
           tma_store_commit();
           mbar_arrive(&a_full[s]);
           SB_DBG_G(kb, ig / C::KB, 4);
@@ -492,6 +500,7 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
       uint32_t ia = 0;
       long long st_pace = 0, st_aempty = 0;
       int pace_seen = 0;
+      const uint64_t pol_first = l2_policy_evict_first();
       const long long st_begin = args.stall ? clock64() : 0;
       for (int it = cta; !GEN && it < num_items; it += ncta) {
         const int tl = it / NPARTS, part = it % NPARTS;  // tl: position in the sweep (what the pace hint counts)
@@ -503,7 +512,10 @@ rowgemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& 
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
           SB_WAIT_TIMED(args.stall, st_aempty, mbar_wait(&a_empty[s], ph ^ 1u));
           mbar_expect_tx(&a_full[s], C::A_STAGE);
-          tma_load_2d(smem + C::OFF_A + s * C::A_STAGE, &tmA, &a_full[s], kb * 64, row);
+          if (MODE == MODE_FWD && args.l2_hints)
+            tma_load_2d_hint(smem + C::OFF_A + s * C::A_STAGE, &tmA, &a_full[s], kb * 64, row, pol_first);
+          else
+            tma_load_2d(smem + C::OFF_A + s * C::A_STAGE, &tmA, &a_full[s], kb * 64, row);
           if (C::STREAM_B)
             tma_load_2d(smem + C::OFF_A + s * C::A_STAGE + kChunkBytes, &tmB, &a_full[s], kb * 64,
                         part * NDIM);
@@ -1674,6 +1686,7 @@ struct TailArgs {
   float omega_last;
   long long* dbg;        // optional timeline (block 0): dbg[tile * 16 + k], first 12 tiles
   int reverse;           // 1: sweep the tiles back to front (see RowGemmArgs::reverse)
+  int l2_hints;          // 1: the activation k-blocks are loaded with an L2 evict_first hint (see RowGemmArgs::l2_hints)
 };
 
 #define SB_DBG_T(tile_i, k)                                                 \
@@ -1808,13 +1821,17 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap tmAct, const __grid_constant_
     // ===================== producer: activation k-blocks (HBM) =====================
     if (lane == 0) {
       uint32_t ia = 0;
+      const uint64_t pol_first = l2_policy_evict_first();
       for (int t = blockIdx.x; t < args.num_tiles; t += gridDim.x) {
         for (int kb = 0; kb < C::NCH; ++kb, ++ia) {
           const uint32_t s = ia % C::SA, ph = (ia / C::SA) & 1u;
           mbar_wait(&a_empty[s], ph ^ 1u);
           mbar_expect_tx(&a_full[s], kChunkBytes);
-          tma_load_2d(smem + C::OFF_A + s * kChunkBytes, &tmAct, &a_full[s], kb * 64,
-                      args.a_row0 + (args.reverse ? args.num_tiles - 1 - t : t) * kRowsPerTile);
+          const int arow = args.a_row0 + (args.reverse ? args.num_tiles - 1 - t : t) * kRowsPerTile;
+          if (args.l2_hints)
+            tma_load_2d_hint(smem + C::OFF_A + s * kChunkBytes, &tmAct, &a_full[s], kb * 64, arow, pol_first);
+          else
+            tma_load_2d(smem + C::OFF_A + s * kChunkBytes, &tmAct, &a_full[s], kb * 64, arow);
         }
       }
     }
