@@ -67,3 +67,45 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert "siren_oracle" not in text and "ref_import" not in text, f
+
+
+def test_every_relative_import_in_the_package_resolves():
+    """Function-level relative imports (the CUDA-only branches import `_lib` lazily) are not exercised by the CPU
+    suite: check statically that each `from .x import y` in the package names an existing module or attribute
+    source (a wrong number of dots once shipped in pipeline/masking/funcs/prune.py and only failed on a GPU)."""
+    import ast
+    import importlib
+    import importlib.util
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "implicit_image_compression_b200")
+    bad = []
+    for dirpath, _, files in os.walk(root):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, fn)
+            rel = os.path.relpath(path, os.path.dirname(root))[:-3].split(os.sep)
+            pkg = rel[:-1] if rel[-1] != "__init__" else rel[:-1]
+            tree = ast.parse(open(path).read(), path)
+            for node in ast.walk(tree):
+                if isinstance(node, ast.ImportFrom) and node.level > 0:
+                    base = pkg[: len(pkg) - (node.level - 1)]
+                    if len(base) < 1 or node.level - 1 > len(pkg) - 1:
+                        bad.append((path, node.lineno, "beyond the top-level package"))
+                        continue
+                    target = ".".join(base + (node.module.split(".") if node.module else []))
+                    try:
+                        mod = importlib.import_module(target)
+                    except ImportError:
+                        bad.append((path, node.lineno, target))
+                        continue
+                    for alias in node.names:
+                        if alias.name == "*" or hasattr(mod, alias.name):
+                            continue
+                        try:
+                            ok = importlib.util.find_spec(target + "." + alias.name) is not None
+                        except ImportError:
+                            ok = False
+                        if not ok:
+                            bad.append((path, node.lineno, target + "." + alias.name))
+    assert not bad, bad
