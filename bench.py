@@ -347,6 +347,12 @@ def run_gpu_arm(args):
         # graph replays re-issue the launches captured once: count them per replayed step
         launches = args.steps * fitter.launches_per_step
     clocks = sampler.stop(t0, t1)
+    if args.gpus == 1 and args.workload == "c2":
+        # the timed window (tens of ms) sees one or two nvidia-smi samples; what the kernels themselves measure
+        # (clock64 against globaltimer, tools/stall_report.py) is recorded under profiles/
+        clocks["note"] = ("a 50-step window sees one or two nvidia-smi samples; SM clocks measured inside the kernels "
+                          "(clock64 against globaltimer, tools/stall_report.py) are in profiles/r02_stall_accounting.txt; "
+                          "the >= 2 s window with its own samples is under `sustained`")
     # per-kernel device times: an immediately following EAGER pass of the same K steps with cudaEvent
     # pairs around every library kernel (events cannot be timed inside a replayed graph)
     graph_mode = fitter.use_graph
