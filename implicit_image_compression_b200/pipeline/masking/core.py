@@ -212,15 +212,19 @@ class Masking:
         variance, nonzeros, zeros = {}, {}, {}
         total_variance, total_nonzero, total_zero = 0.0, 0, 0
         counts = []
+        integral = True
         for name, weight in self._masked_parameters():
             mask = self.mask_dict[name]
-            variance[name] = self.redistribution_func(self, name, weight, mask)
+            var = self.redistribution_func(self, name, weight, mask)
+            integral = integral and not var.dtype.is_floating_point
+            # (fp32 -> double is exact, counts are exact in a double: the values read back are those `.item()` gives)
+            counts.append(torch.stack([var.double(), (mask == 1).sum().double(), (mask == 0).sum().double()]))
+        if counts:
+            counts = torch.stack(counts).tolist()  # one sync for all layers: statistic, active and inactive counts
+        for (name, _), (var, nz, z) in zip(self._masked_parameters(), counts):
+            variance[name] = int(var) if integral else var  # the `nonzero` rule counts (Python int in the reference)
             if not np.isnan(variance[name]):
                 total_variance += variance[name]
-            counts.append(torch.stack([(mask == 1).sum(), (mask == 0).sum()]))
-        if counts:
-            counts = torch.stack(counts).tolist()  # one sync for all layers
-        for (name, _), (nz, z) in zip(self._masked_parameters(), counts):
             nonzeros[name], zeros[name] = int(nz), int(z)
             total_nonzero += int(nz)
             total_zero += int(z)
